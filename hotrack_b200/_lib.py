@@ -1,0 +1,54 @@
+"""ctypes binding of libpn2b200.so (C ABI: include/pn2b200.h).
+
+There is no CPU or PyTorch fallback: if the CUDA library has not been built the
+import fails loudly.  Build it with ``python -m hotrack_b200.build``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpn2b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "hotrack_b200: %s is missing -- the sm_100a kernels are not built. "
+        "Run `python -m hotrack_b200.build` (needs nvcc); there is no fallback path." % LIB_PATH
+    )
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_i, _f, _p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes; every function returns int status (0 = ok)
+SIGNATURES = {
+    "pn2_furthest_point_sampling": [_i, _i, _i, _p, _p, _p, _p],
+    "pn2_ball_query": [_i, _i, _i, _f, _i, _p, _p, _p, _p],
+    "pn2_knn": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "pn2_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
+    "pn2_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "pn2_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "pn2_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "pn2_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "pn2_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "pn2_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
+}
+
+for _name, _args in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = _i
+lib.pn2_version.restype = _i
+lib.pn2_last_error.restype = ctypes.c_char_p
+
+
+class Pn2Error(RuntimeError):
+    pass
+
+
+def check(status, name):
+    if status != 0:
+        raise Pn2Error("%s failed (status %d): %s" % (name, status, lib.pn2_last_error().decode()))
+
+
+def call(name, *args):
+    check(getattr(lib, name)(*args), name)

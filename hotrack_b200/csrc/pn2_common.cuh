@@ -1,0 +1,81 @@
+// pn2_common.cuh -- shared device helpers for the sm_100a PointNet++ kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pn2b200.h"
+
+namespace pn2 {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Records the failing call for pn2_last_error() and returns the status code the
+// C ABI hands back (the reference prints and exit(-1)s instead, e.g.
+// ball_query_gpu.cu:62-66).
+int fail(cudaError_t err, const char* where);
+int fail_arg(const char* where, const char* what);
+
+#define PN2_CHECK_LAUNCH(where)                                    \
+    do {                                                           \
+        cudaError_t e__ = cudaGetLastError();                      \
+        if (e__ != cudaSuccess) return ::pn2::fail(e__, where);    \
+    } while (0)
+
+#define PN2_CHECK(call, where)                                     \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return ::pn2::fail(e__, where);    \
+    } while (0)
+
+// Squared distance with the exact rounding sequence of the reference kernels as
+// nvcc 12.9 -O2 contracts them for sm_100 (SASS: FADD,FADD,FMUL,FADD,FFMA,FFMA):
+//   d = fma(dz,dz, fma(dx,dx, rn(dy*dy)))
+// (sampling_gpu.cu:133, ball_query_gpu.cu:33, interpolate_gpu.cu:40,108).
+// Written with intrinsics so no compiler flag or version can re-associate it.
+__device__ __forceinline__ float sqdist(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = __fsub_rn(ax, bx);
+    const float dy = __fsub_rn(ay, by);
+    const float dz = __fsub_rn(az, bz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace pn2
