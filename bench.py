@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: point-clouds/sec (fwd+bwd, B=32 N=4096) of HOTrack's pointnet_lib
+hot path (PointNet2Msg_fast backbone -> q1 -> q2 of HandTrackNet), one training step per "step"
+(forward + backward + gradient all-reduce when N>1 + Adam), B=32 clouds of N=4096 points PER GPU
+(weak scaling: clouds are independent, the only exchange is the gradient all-reduce).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine ops|fused]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...          (N > 1)
+
+Prints ONE JSON line (rank 0).  `value` = clouds/s with the batch already resident in HBM; `e2e` =
+the same step driven from pinned HOST buffers (H2D of the clouds and joints + D2H of the loss inside
+the timed region).  `roofline` = the kernel of OURS with the largest share of the step, its
+algorithmic bytes (SURVEY.md section 8d formulas) over its CUDA-event duration measured inside the
+timed region, against MEASURED_PEAKS.json.  `cpu_baseline` = the reference's own CPU fallback path
+(oracle/_ref/pyref imported with CUDA hidden) on a bounded sample, all host threads.
+
+--impl reference runs the UNMODIFIED reference: its Python layer (oracle/_ref/pyref) on its own CUDA
+kernels (oracle/_ref/libpn2_ref.so, compiled for sm_100a from /root/reference), torch.optim.Adam,
+same step, same loss, same inputs.  HOTrack's pointnet_lib is GPU code, so the like-for-like
+reference arm is that GPU path on the same B200; `--ref-device cpu` times its CPU fallback instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "point-clouds/sec (fwd+bwd, B=32 N=4096)"
+UNIT = "clouds/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "ops", "fused"])
+    ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
+    ap.add_argument("--batch", type=int, default=32, help="clouds per GPU")
+    ap.add_argument("--points", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="clouds in the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ helpers -------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def alg_bytes(name, a):
+    """Algorithmic bytes of one C-ABI call; `a` = the call's argument tuple."""
+    if name == "pn2_furthest_point_sampling":
+        b, n, m = a[:3]
+        return b * n * 12 + b * m * 4
+    if name == "pn2_ball_query":
+        b, n, m, _, ns = a[:5]
+        return b * n * 12 + b * m * 12 + b * m * ns * 4
+    if name == "pn2_knn":
+        b, n, m, k = a[:4]
+        return b * n * 12 + b * m * 12 + b * n * k * 8
+    if name == "pn2_three_nn":
+        b, n, m = a[:3]
+        return b * n * 12 + b * m * 12 + b * n * 24
+    if name == "pn2_three_interpolate":
+        b, c, m, n = a[:4]
+        return b * c * m * 4 + b * n * 24 + b * c * n * 4
+    if name == "pn2_three_interpolate_grad":
+        b, c, n, m = a[:4]
+        return b * c * m * 4 + b * n * 24 + b * c * n * 4
+    if name in ("pn2_group_points", "pn2_group_points_grad"):
+        b, c, n, s, k = a[:5]
+        return b * c * n * 4 + b * s * k * 4 + b * c * s * k * 4
+    if name in ("pn2_gather_points", "pn2_gather_points_grad"):
+        b, c, n, s = a[:4]
+        return b * c * n * 4 + b * s * 4 + b * c * s * 4
+    if name == "pn2_adam_step":
+        return a[0] * 28
+    try:
+        from hotrack_b200 import fused
+        return fused.alg_bytes(name, a)
+    except Exception:
+        return None
+
+
+def loss_fn(src2, f11, f13):
+    return src2.square().mean() + f11.square().mean() + f13.square().mean()
+
+
+def make_inputs(B, N, rank):
+    import torch
+
+    from hotrack_b200 import synthetic
+
+    xyz = torch.from_numpy(synthetic.ball(B, N, seed=1000 + rank))       # (B,N,3) canonicalised hand cloud
+    kps = torch.from_numpy(synthetic.keypoints(B, 21, seed=1000 + rank))  # (B,21,3) jittered joints
+    return xyz, kps
+
+
+def build_model(impl, engine, dev):
+    import torch
+
+    from hotrack_b200 import backbones
+    from hotrack_b200.handtrack_path import HandTrackPointPath, init_weights
+
+    if impl == "ours":
+        from hotrack_b200 import pointnet_utils as pu
+        pu.set_engine(engine)
+        model = HandTrackPointPath(backbones.default_cfg(dev))
+    else:
+        from oracle import ref_modules
+        rpu, rbb = ref_modules.load(cuda=(dev.type == "cuda"))
+        ns = types.SimpleNamespace(
+            PointNet2Msg_fast=rbb.PointNet2Msg_fast,
+            PointNetSetAbstractionMsg_GivenCenterPoints=rpu.PointNetSetAbstractionMsg_GivenCenterPoints)
+        model = HandTrackPointPath(backbones.default_cfg(dev), ns)
+    init_weights(model, seed=0)
+    model = model.to(dev)
+    model.train()
+    return model
+
+
+# ------------------------------------------------------------------ CPU reference ------------
+def cpu_reference(sample, N, steps=3, warmup=1):
+    """The reference's CPU fallback path (pointnet_utils.py CUDA=False branch) on `sample` clouds."""
+    import torch
+
+    dev = torch.device("cpu")
+    model = build_model("reference", None, dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4)
+    xyz, kps = make_inputs(sample, N, 0)
+    x, k = xyz.transpose(1, 2).contiguous(), kps.transpose(1, 2).contiguous()
+    ts = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = loss_fn(*model(x, k)[:3])
+        loss.backward()
+        opt.step()
+        float(loss.detach())
+        if it >= warmup:
+            ts.append(time.perf_counter() - t0)
+    per_step = sum(ts) / len(ts)
+    return {"value": round(sample / per_step, 3), "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "reference", "host_cpus": os.cpu_count(),
+            "sample": "%d clouds x N=%d, %d fwd+bwd+Adam steps of the same path through the reference's own CPU "
+                      "fallback (pointnet_utils.py CUDA=False branch + torch CPU), %.2f s/step" % (sample, N, steps,
+                                                                                                  per_step)}
+
+
+# ------------------------------------------------------------------ main ----------------------
+def main():
+    args = parse()
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    B, N, K, W = args.batch, args.points, args.steps, max(args.warmup, 3)
+
+    if args.impl == "reference" and rank != 0:
+        return  # the reference is single-GPU: rank 0 alone runs it
+
+    if args.impl == "reference" and args.ref_device == "cpu":
+        cb = cpu_reference(args.cpu_sample, N, steps=max(1, min(K, 5)), warmup=1)
+        line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0, "steps": K, "warmup": W,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "impl": "reference", "cpu_baseline": cb,
+                "config": {"workload": "HandTrackNet pointnet_lib path fwd+bwd+Adam, bounded CPU sample", "points": N},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path for --impl ours)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ddp = world > 1 and args.impl == "ours"
+    if ddp:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    engine = args.engine
+    if args.impl == "ours" and engine == "auto":
+        try:
+            from hotrack_b200 import fused  # noqa: F401
+            engine = "fused"
+        except ImportError:
+            engine = "ops"
+
+    model = build_model(args.impl, engine, dev)
+    if args.impl == "ours":
+        from hotrack_b200 import _lib
+        from hotrack_b200.flat import FlatAdam, FlatParams
+        flat = FlatParams(model)
+        flat.broadcast(0)
+        opt = FlatAdam(flat, lr=1e-4, weight_decay=1e-4)
+    else:
+        _lib = None
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4)
+
+    xyz_h, kps_h = make_inputs(B, N, rank)
+    xyz_h, kps_h = xyz_h.pin_memory(), kps_h.pin_memory()
+    xyz_d, kps_d = xyz_h.to(dev), kps_h.to(dev)
+    loss_h = torch.zeros(1).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(xyz, kps):
+        x = xyz.transpose(1, 2).contiguous()   # (B,3,N), the layout canonicalize() hands the backbone
+        k = kps.transpose(1, 2).contiguous()
+        if args.impl == "ours":
+            flat.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=False)
+        loss = loss_fn(*model(x, k)[:3])
+        loss.backward()
+        if args.impl == "ours":
+            opt.step(flat.allreduce_grads())
+        else:
+            opt.step()
+        return loss.detach()
+
+    def barrier():
+        if ddp:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host, probe=False):
+        evs = []
+        barrier()
+        for _ in range(n_steps):
+            flush.zero_()  # untimed: evict L2 between steps
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            if from_host:
+                x = xyz_h.to(dev, non_blocking=True)
+                k = kps_h.to(dev, non_blocking=True)
+                loss = step(x, k)
+                loss_h.copy_(loss.reshape(1), non_blocking=True)
+            else:
+                step(xyz_d, kps_d)
+            e.record()
+            evs.append((s, e))
+            if from_host:
+                e.synchronize()  # the caller consumes the loss every step
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        if ddp:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(W):
+        step(xyz_d, kps_d)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _lib.lib.pn2_launch_count() if _lib else 0
+    if _lib:
+        _lib.PROBE = {}
+    ms_dev = timed(K, from_host=False)
+    probe = _lib.PROBE if _lib else None
+    if _lib:
+        _lib.PROBE = None
+    launches = (_lib.lib.pn2_launch_count() - n0) if _lib else 0
+    ms_e2e = timed(K, from_host=True)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if ddp:
+            dist.destroy_process_group()
+        return
+
+    clouds_per_step = B * (world if ddp else 1)
+    value = clouds_per_step * K / (ms_dev / 1e3)
+    e2e = clouds_per_step * K / (ms_e2e / 1e3)
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world if ddp else 1, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if (args.impl == "ours" and engine == "fused") else "f32(tf32 conv)" if args.impl == "reference" else "f32",
+        "data": "synthetic",
+        "config": {"workload": "HandTrackNet pointnet_lib path (PointNet2Msg_fast shallow1 backbone -> q1 -> q2, 21 joints), "
+                               "train step fwd+bwd+Adam, B=%d N=%d per GPU" % (B, N),
+                   "clouds_per_gpu": B, "points": N, "engine": engine if args.impl == "ours" else "reference-cuda",
+                   "parallelism": "dp%d" % (world if ddp else 1),
+                   "l2": "256 MiB flush between timed steps (untimed); per-step working set >> 126 MB L2"},
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "ms_per_step": round(ms_e2e / K, 4),
+                "h2d_bytes_per_step": int(xyz_h.numel() * 4 + kps_h.numel() * 4) * (world if ddp else 1),
+                "d2h_bytes_per_step": 4 * (world if ddp else 1)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": line["value"], "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                                "sample": "full workload; NOTE the reference's pointnet_lib is CUDA code: this arm runs its "
+                                          "own kernels (compiled for sm_100a) + its Python layer + torch.optim.Adam on the "
+                                          "same B200, host threads only drive launches"}
+        line["e2e"]["note"] = "reference GPU path driven from pinned host buffers"
+    else:
+        # dominant kernel of OURS inside the timed region
+        peak, peak_src = peaks()
+        best = None
+        torch.cuda.synchronize()
+        tot = {}
+        for name, recs in (probe or {}).items():
+            by_shape = {}
+            for a, s, e in recs:
+                key = tuple(x for x in a if isinstance(x, (int, float)))[:6]
+                by_shape.setdefault(key, []).append((a, s.elapsed_time(e)))
+            for key, lst in by_shape.items():
+                t = sum(x[1] for x in lst)
+                tot[(name, key)] = (t, lst)
+        shares = []
+        for (name, key), (t, lst) in sorted(tot.items(), key=lambda kv: -kv[1][0]):
+            shares.append({"kernel": name, "shape": list(key), "calls": len(lst), "ms_total": round(t, 4),
+                           "share_of_step": round(t / ms_dev, 4)})
+            if best is None:
+                nb = alg_bytes(name, lst[0][0])
+                if nb:
+                    avg_ms = t / len(lst)
+                    ach = nb / (avg_ms * 1e-3) / 1e9
+                    best = {"bound": "hbm", "kernel": name, "shape": list(key), "achieved": round(ach, 2), "peak": peak,
+                            "unit": "GB/s", "frac": round(ach / peak, 5), "traffic": None,
+                            "alg_bytes_per_launch": int(nb), "avg_launch_us": round(avg_ms * 1e3, 3), "peak_source": peak_src,
+                            "share_of_step": round(t / ms_dev, 4)}
+        line["roofline"] = best
+        line["kernel_shares"] = shares[:12]
+        if not ddp and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_reference(args.cpu_sample, N, steps=3, warmup=1)
+            except Exception as ex:  # oracle/_ref not staged
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                        "sample": "unavailable: %s" % ex}
+    print(json.dumps(line), flush=True)
+    if ddp:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,7 +1,7 @@
 """ctypes binding of libpn2b200.so (C ABI: include/pn2b200.h).
 
 There is no CPU or PyTorch fallback: if the CUDA library has not been built the
-import fails loudly.  Build it with ``python -m hotrack_b200.build``.
+import fails loudly.  Build it with ``python hotrack_b200/build.py``.
 """
 import ctypes
 import os
@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libpn2b200.so")
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "hotrack_b200: %s is missing -- the sm_100a kernels are not built. "
-        "Run `python -m hotrack_b200.build` (needs nvcc); there is no fallback path." % LIB_PATH
+        "Run `python hotrack_b200/build.py` (needs nvcc); there is no fallback path." % LIB_PATH
     )
 
 lib = ctypes.CDLL(LIB_PATH)
@@ -31,6 +31,7 @@ SIGNATURES = {
     "pn2_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "pn2_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
     "pn2_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "pn2_adam_step": [ctypes.c_longlong, _p, _p, _p, _p, _f, _f, _f, _f, _f, _i, _f, _p],
 }
 
 for _name, _args in SIGNATURES.items():
@@ -39,6 +40,7 @@ for _name, _args in SIGNATURES.items():
     _fn.restype = _i
 lib.pn2_version.restype = _i
 lib.pn2_last_error.restype = ctypes.c_char_p
+lib.pn2_launch_count.restype = ctypes.c_longlong
 
 
 class Pn2Error(RuntimeError):
@@ -50,5 +52,19 @@ def check(status, name):
         raise Pn2Error("%s failed (status %d): %s" % (name, status, lib.pn2_last_error().decode()))
 
 
+# Optional per-op device timing for bench.py's roofline line: when PROBE is a dict, every C-ABI
+# call is bracketed by CUDA events on the current stream and (name, args, start, end) is recorded.
+PROBE = None
+
+
 def call(name, *args):
+    if PROBE is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    import torch
+
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
     check(getattr(lib, name)(*args), name)
+    e.record()
+    PROBE.setdefault(name, []).append((args, s, e))

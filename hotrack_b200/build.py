@@ -1,6 +1,6 @@
 """Build libpn2b200.so in-tree with nvcc for sm_100a (no GPU needed: cross-compiles).
 
-Usage: python -m hotrack_b200.build [--force]
+Usage: python hotrack_b200/build.py [--force] [-v]   (run as a script: importing the package needs the built library)
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 import os

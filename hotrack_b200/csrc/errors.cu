@@ -1,12 +1,16 @@
 // errors.cu -- status / error-string plumbing of the C ABI (include/pn2b200.h).
 #include "pn2_common.cuh"
 
+#include <atomic>
 #include <cstdio>
 
 namespace pn2 {
 namespace {
 thread_local char g_last_error[512] = "";
+std::atomic<long long> g_launches{0};
 }
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int fail(cudaError_t err, const char* where) {
     snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", where, cudaGetErrorString(err),
@@ -21,4 +25,5 @@ int fail_arg(const char* where, const char* what) {
 }  // namespace pn2
 
 extern "C" int pn2_version(void) { return 100; /* 0.1.0 */ }
+extern "C" long long pn2_launch_count(void) { return pn2::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* pn2_last_error(void) { return pn2::g_last_error; }

@@ -15,11 +15,14 @@ constexpr unsigned kFull = 0xffffffffu;
 // ball_query_gpu.cu:62-66).
 int fail(cudaError_t err, const char* where);
 int fail_arg(const char* where, const char* what);
+// Counts kernel launches issued by this library (pn2_launch_count(); bench.py's gpu_launches).
+void count_launch();
 
 #define PN2_CHECK_LAUNCH(where)                                    \
     do {                                                           \
         cudaError_t e__ = cudaGetLastError();                      \
         if (e__ != cudaSuccess) return ::pn2::fail(e__, where);    \
+        ::pn2::count_launch();                                     \
     } while (0)
 
 #define PN2_CHECK(call, where)                                     \

@@ -28,6 +28,8 @@ typedef void* pn2_stream_t; /* cudaStream_t */
 
 /* Library identification.  pn2_version() = 10000*major + 100*minor + patch. */
 int pn2_version(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+long long pn2_launch_count(void);
 /* Message for the last non-zero status returned on this thread ("" if none). */
 const char* pn2_last_error(void);
 
@@ -93,6 +95,16 @@ int pn2_gather_points(int b, int c, int n, int npoints, const float* points, con
  * src/sampling_gpu.cu:65-83; kernel :46-63).  Accumulates into grad_points (B,C,N). */
 int pn2_gather_points_grad(int b, int c, int n, int npoints, const float* grad_out, const int* idx,
                            float* grad_points, pn2_stream_t stream);
+
+/* ---- entry points with no reference C counterpart -------------------------------------- */
+
+/* Flat-buffer Adam step; replaces the torch.optim.Adam the reference trains with
+ * (network/trainer.py:66-73).  All four buffers hold n fp32 values, 16-byte aligned.
+ * Update rule = torch.optim.Adam with L2 weight decay; `step` counts from 1; the gradient is
+ * multiplied by grad_scale first (1/world_size after a SUM all-reduce). */
+int pn2_adam_step(long long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                  pn2_stream_t stream);
 
 #ifdef __cplusplus
 }

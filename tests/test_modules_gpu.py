@@ -1,0 +1,191 @@
+"""Module-level parity on the GPU: this package's SA/FP modules + backbone + q1/q2 (engine "ops":
+our kernels + torch.nn fp32 convs) against the REFERENCE's own modules running on the REFERENCE's
+own kernels (oracle/_ref: pointnet_utils.py / backbones.py staged unmodified + libpn2_ref.so).
+
+BASELINE.json config 2 scale (B=8, N=2048, fp32, TF32 off in both): every index tensor identical,
+features within 1e-5 relative (north_star tolerance), parameter gradients within 1e-4 relative
+(atomics / index_put summation order differs between the two and between runs of either).
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import clouds
+from oracle import pn2_oracle as orc
+from oracle import ref_modules
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref(cuda):
+    if not ref_modules.available(cuda=True):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return ref_modules.load(cuda=True)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_exact():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _pair(ref, cuda, seed=0):
+    from hotrack_b200 import backbones, pointnet_utils as pu
+    from hotrack_b200.handtrack_path import HandTrackPointPath, init_weights
+
+    rpu, rbb = ref
+    pu.set_engine("ops")
+    ours = HandTrackPointPath(backbones.default_cfg(cuda))
+    init_weights(ours, seed=seed)
+    ns = types.SimpleNamespace(PointNet2Msg_fast=rbb.PointNet2Msg_fast,
+                               PointNetSetAbstractionMsg_GivenCenterPoints=rpu.PointNetSetAbstractionMsg_GivenCenterPoints)
+    theirs = HandTrackPointPath(backbones.default_cfg(cuda), ns)
+    missing = theirs.load_state_dict(ours.state_dict(), strict=True)  # identical key set
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return ours.to(cuda), theirs.to(cuda)
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_config2_path_forward_backward_matches_reference(ref, cuda, train):
+    B, N = 8, 2048
+    ours, theirs = _pair(ref, cuda)
+    ours.train(train)
+    theirs.train(train)
+    xyz = clouds.ball(B, N, seed=2)
+    kps = clouds.keypoints(B, 21, seed=2)
+    x = torch.from_numpy(xyz).to(cuda).transpose(1, 2).contiguous()
+    k = torch.from_numpy(kps).to(cuda).transpose(1, 2).contiguous()
+    o = ours(x, k)
+    t = theirs(x, k)
+    # group indices of q1 (kNN K=16, K=64): exact, and equal to the CPU oracle
+    for i, kk in enumerate((16, 64)):
+        assert torch.equal(o[3][i], t[3][i])
+        np.testing.assert_array_equal(o[3][i].cpu().numpy(), orc.knn(kk, kps, xyz)[1])
+    for name, a, b in zip(("src2", "f11", "f13"), o[:3], t[:3]):
+        assert a.shape == b.shape
+        assert _rel(a, b) < 1e-5, "%s rel %.3g" % (name, _rel(a, b))
+    if not train:
+        return
+    lo = sum(v.square().mean() for v in o[:3])
+    lt = sum(v.square().mean() for v in t[:3])
+    lo.backward()
+    lt.backward()
+    for (n1, p1), (n2, p2) in zip(ours.named_parameters(), theirs.named_parameters()):
+        assert n1 == n2
+        if p2.grad is None:
+            continue
+        scale = p2.grad.abs().max().item()
+        if scale < 1e-12:  # conv biases under train-mode BN: gradient is rounding noise around 0
+            continue
+        assert _rel(p1.grad, p2.grad) < 1e-3, "%s grad rel %.3g" % (n1, _rel(p1.grad, p2.grad))
+    # BatchNorm running statistics advanced identically
+    for (n1, b1), (n2, b2) in zip(ours.named_buffers(), theirs.named_buffers()):
+        if b1.dtype.is_floating_point:
+            assert _rel(b1, b2) < 1e-5, n1
+
+
+def test_backbone_index_tensors_match_oracle(cuda):
+    """Every index tensor inside the backbone is a function of coordinates only: check the chain
+    FPS1 -> FPS2 -> ball1 -> ball2 -> three_nn x2 on our kernels against the CPU oracle."""
+    from hotrack_b200 import pointnet2_utils as futils
+
+    B, N = 4, 2048
+    xyz = clouds.shell(B, N, seed=9)
+    x = torch.from_numpy(xyz).to(cuda)
+    f1 = futils.furthest_point_sample(x, 256)
+    w1 = orc.furthest_point_sample(xyz, 256)
+    np.testing.assert_array_equal(f1.cpu().numpy(), w1)
+    l1 = np.stack([xyz[b][w1[b]] for b in range(B)])
+    x1 = torch.from_numpy(l1).to(cuda)
+    f2 = futils.furthest_point_sample(x1, 128)
+    w2 = orc.furthest_point_sample(l1, 128)
+    np.testing.assert_array_equal(f2.cpu().numpy(), w2)
+    l2 = np.stack([l1[b][w2[b]] for b in range(B)])
+    x2 = torch.from_numpy(l2).to(cuda)
+    np.testing.assert_array_equal(futils.ball_query(0.1, 32, x, x1).cpu().numpy(), orc.ball_query(0.1, 32, xyz, l1))
+    np.testing.assert_array_equal(futils.ball_query(0.2, 32, x1, x2).cpu().numpy(), orc.ball_query(0.2, 32, l1, l2))
+    np.testing.assert_array_equal(futils.three_nn(x, x1)[1].cpu().numpy(), orc.three_nn(xyz, l1)[1])
+    np.testing.assert_array_equal(futils.three_nn(x1, x2)[1].cpu().numpy(), orc.three_nn(l1, l2)[1])
+
+
+def test_sa_and_fp_modules_nonfast_and_parts(ref, cuda):
+    """The non-_fast twins and the part dimension (P=2) of the _fast modules against the reference."""
+    from hotrack_b200 import pointnet_utils as pu
+
+    rpu, _ = ref
+    pu.set_engine("ops")
+    torch.manual_seed(0)
+    B, N = 2, 512
+    xyz = torch.from_numpy(clouds.ball(B, N, seed=5)).to(cuda).transpose(1, 2).contiguous()
+    feats = torch.randn(B, 6, N, device=cuda)
+
+    def clone(ours, theirs):
+        theirs.load_state_dict(ours.state_dict())
+        return ours.to(cuda).train(), theirs.to(cuda).train()
+
+    a, b = clone(pu.PointNetSetAbstractionMsg(64, [0.1, 0.2], [8, 16], 9, [[16, 32], [16, 32]]),
+                 rpu.PointNetSetAbstractionMsg(64, [0.1, 0.2], [8, 16], 9, [[16, 32], [16, 32]]))
+    (xa, fa), (xb, fb) = a(xyz, feats), b(xyz, feats)
+    assert torch.equal(xa, xb) and _rel(fa, fb) < 1e-5
+    a, b = clone(pu.PointNetSetAbstractionMsg(64, [0.2], [8], 9, [[16, 32]], knn=True),
+                 rpu.PointNetSetAbstractionMsg(64, [0.2], [8], 9, [[16, 32]], knn=True))
+    assert _rel(a(xyz, feats)[1], b(xyz, feats)[1]) < 1e-5
+    a, b = clone(pu.PointNetSetAbstraction(None, None, None, 9, [16, 32], True),
+                 rpu.PointNetSetAbstraction(None, None, None, 9, [16, 32], True))
+    assert _rel(a(xyz, feats)[1], b(xyz, feats)[1]) < 1e-5
+    a, b = clone(pu.PointNetFeaturePropagation(6 + 32, [32, 16]), rpu.PointNetFeaturePropagation(6 + 32, [32, 16]))
+    coarse = torch.randn(B, 32, 64, device=cuda)
+    assert _rel(a(xyz, xa, feats, coarse), b(xyz, xa, feats, coarse)) < 1e-5
+    # part dimension
+    P = 2
+    xyz4 = xyz.unsqueeze(1).expand(B, P, 3, N).contiguous()
+    f4 = torch.randn(B, P, 6, N, device=cuda)
+    a, b = clone(pu.PointNetSetAbstractionMsg_fast(64, [0.15], [8], 9, [[16, 32]]),
+                 rpu.PointNetSetAbstractionMsg_fast(64, [0.15], [8], 9, [[16, 32]]))
+    (xa4, fa4), (xb4, fb4) = a(xyz4, f4), b(xyz4, f4)
+    assert torch.equal(xa4, xb4) and fa4.shape == fb4.shape and _rel(fa4, fb4) < 1e-5
+    a, b = clone(pu.PointNetFeaturePropagation_fast(6 + 32, [32, 16]), rpu.PointNetFeaturePropagation_fast(6 + 32, [32, 16]))
+    ra, rb = a(xyz4, xa4, f4, fa4), b(xyz4, xb4.contiguous(), f4, fb4)
+    assert ra.shape == rb.shape and _rel(ra, rb) < 1e-5
+    a, b = clone(pu.PointNetSetAbstraction_fast(None, None, None, 9, [16, 32], True),
+                 rpu.PointNetSetAbstraction_fast(None, None, None, 9, [16, 32], True))
+    assert _rel(a(xyz4, f4)[1], b(xyz4, f4)[1]) < 1e-5
+    # q module with broadcast centre features and the 4-NN distance output
+    cen = torch.from_numpy(clouds.keypoints(B, 21, seed=5)).to(cuda).transpose(1, 2).contiguous()
+    cf = torch.randn(B, 10, 21, device=cuda)
+    a, b = clone(pu.PointNetSetAbstractionMsg_GivenCenterPoints([0.2, 0.2], [4, 8], [[16, 24], [16, 24]], 6 + 3 + 10, knn=True),
+                 rpu.PointNetSetAbstractionMsg_GivenCenterPoints([0.2, 0.2], [4, 8], [[16, 24], [16, 24]], 6 + 3 + 10, knn=True))
+    (oa, da), (ob, db) = a(xyz, feats, cen, cf, return_4nn=True), b(xyz, feats, cen, cf, return_4nn=True)
+    assert _rel(oa, ob) < 1e-5 and _rel(da, db) < 1e-6
+
+
+def test_flat_adam_matches_torch_adam(cuda):
+    from hotrack_b200.flat import FlatAdam, FlatParams
+
+    torch.manual_seed(1)
+    m1 = torch.nn.Sequential(torch.nn.Linear(7, 13), torch.nn.Linear(13, 5)).to(cuda)
+    m2 = torch.nn.Sequential(torch.nn.Linear(7, 13), torch.nn.Linear(13, 5)).to(cuda)
+    m2.load_state_dict(m1.state_dict())
+    flat = FlatParams(m1)
+    opt1 = FlatAdam(flat, lr=1e-3, weight_decay=1e-2)
+    opt2 = torch.optim.Adam(m2.parameters(), lr=1e-3, weight_decay=1e-2)
+    x = torch.randn(32, 7, device=cuda)
+    for _ in range(5):
+        flat.zero_grad()
+        m1(x).square().mean().backward()
+        opt1.step(flat.allreduce_grads())
+        opt2.zero_grad()
+        m2(x).square().mean().backward()
+        opt2.step()
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        torch.testing.assert_close(p1, p2, rtol=1e-5, atol=1e-6)
