@@ -97,7 +97,7 @@ class PointNet2Msg_fast(nn.Module):
         l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
         skip = torch.cat([l0_xyz, l0_points], dim=-2) if l0_points.shape[-2] else l0_xyz  # backbones.py:127-130
         l0_points = self.fp1(l0_xyz, l1_xyz, skip, l1_points)
-        return _head(self, l0_points.reshape(B, -1, N))
+        return _head(self, pu._carry(l0_points, l0_points.reshape(B, -1, N)))
 
 
 def _head(self, feats):

@@ -33,7 +33,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers.append(os.path.join(HERE, "..", "include", "pn2b200.h"))
+    headers += [os.path.join(HERE, "..", "include", h) for h in os.listdir(os.path.join(HERE, "..", "include")) if h.endswith(".h")]
     jobs = []
     objs = []
     for src in _sources():

@@ -1,0 +1,666 @@
+// mlp_gemm.cu -- the grouped per-point MLP as bf16 tensor-core GEMMs over row matrices, sm_100a.
+//
+// Replaces the per-layer  relu(bn(conv1x1(x)))  chain of the reference's SA / FP modules
+// (network/models/pointnet_utils.py:399-403,458-460,505-507,577-580; backbones.py:131-132), which
+// runs as conv (cuDNN) + BatchNorm (cuDNN) + ReLU (elementwise) launches, each materialising a
+// (B,C,S,K) fp32 tensor, and 5+ more launches per layer in backward.
+//
+// Layout: activations are ROW matrices  X[R][C]  (R = B*S*K grouped rows or B*N points; channels
+// contiguous; bf16; leading dimension a multiple of 8).  Only the PRE-BatchNorm conv output Y_l of each
+// layer is ever stored; BatchNorm + ReLU are applied by the CONSUMER while it stages its A operand
+// ("prologue"), and the batch statistics BatchNorm needs are column sums produced by the PRODUCER's
+// epilogue.  Per layer that is one read of Y_{l-1} and one write of Y_l (2 B/element each) instead
+// of five fp32 round trips.
+//
+//   gemm_rows_kernel<BN, AMODE, MASK>      C[R][n] = A'[R][k] * B[n][k]^T
+//      AMODE PLAIN   A' = A                               (first layer: gathered rows)
+//            AFFINE  A' = relu(A*scale + shift)           (forward: BN+ReLU of the previous layer)
+//            BNBWD   A' = cA*dZ + cB*Y + cC               (backward: BatchNorm-backward of this layer)
+//      epilogue: bf16 tile staged in shared memory, written with coalesced 16-byte stores; column sums
+//      sum(v), sum(v*v)  (forward BN statistics)  or, with MASK (backward):  v *= [prev act > 0],
+//      sum(v), sum(v*xhat_prev)  -- the two reductions BatchNorm-backward of the previous layer needs.
+//   wgrad_kernel<AFFINE>                   dW[n][k] += sum_r dY[r][n] * X'[r][k]   (split over rows,
+//      transposed ldmatrix fragments, fp32 atomics into the zeroed gradient).
+//
+// Machine mapping: persistent CTAs (<= 2 per SM) walk 128-row tiles; A is register-prefetched one
+// chunk ahead (so the prologue runs once per element, not once per consuming warp), B (weights,
+// L2-resident) streams through cp.async; mma.sync.m16n8k16 bf16 with fp32 accumulation.  Every layer
+// of this network is far below the tensor roofline (K <= 800, N <= 512): the bound is the HBM
+// traffic of the row matrices, which is what the design minimises.
+#include "mma_common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int BM = 128, BK = 32, LDS = BK + 8;
+constexpr int kThreads = 256;
+
+enum { A_PLAIN = 0, A_AFFINE = 1, A_BNBWD = 2 };
+
+struct GemmArgs {
+    long long rows;
+    int kdim, n;
+    const bf16* a0; int a0_ld;
+    const bf16* a1; int a1_ld;
+    const float *c0, *c1, *c2;
+    const bf16* b;
+    bf16* out; int out_ld;
+    float* sums;
+    const bf16* yp; int yp_ld;
+    const float *p_scale, *p_shift, *p_mean, *p_rstd;
+};
+
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+template <int BN, int AMODE, bool MASK>
+__global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p) {
+    constexpr int WN = BN / 32, WM = 8 / WN, MF = BM / WM / 16;
+    constexpr int CLD = BN + 8;
+    constexpr int CPR = BN / 8;
+    constexpr int RPP = kThreads / CPR;
+    constexpr int PASSES = BM / RPP;
+    constexpr int NCOEF = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    bf16* sA = reinterpret_cast<bf16*>(smem_raw);
+    bf16* sB = sA + 2 * BM * LDS;
+    bf16* sC = sB + 2 * BN * LDS;
+    float* sCoef = reinterpret_cast<float*>(sC + BM * CLD);
+    float* sPrev = sCoef + NCOEF * p.kdim;  // [4][BN], MASK only
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int n0 = blockIdx.y * BN;
+    const int KT = p.kdim / BK;
+    const long long tiles = (p.rows + BM - 1) / BM;
+
+    for (int i = tid; i < NCOEF * p.kdim; i += kThreads) {
+        const int which = i / p.kdim, c = i - which * p.kdim;
+        const float* src = which == 0 ? p.c0 : (which == 1 ? p.c1 : p.c2);
+        sCoef[i] = src[c];
+    }
+    if (MASK) {
+        for (int i = tid; i < 4 * BN; i += kThreads) {
+            const int which = i / BN, c = n0 + (i - which * BN);
+            const float* src = which == 0 ? p.p_scale : (which == 1 ? p.p_shift : (which == 2 ? p.p_mean : p.p_rstd));
+            sPrev[i] = c < p.n ? src[c] : 0.f;
+        }
+    }
+    __syncthreads();
+
+    const int a_row = tid >> 2, a_col = (tid & 3) * 8;
+    uint4 ra0[2], ra1[2];
+    bool rvalid[2];
+
+    auto load_A = [&](long long tile, int kc) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long row = tile * BM + a_row + j * 64;
+            rvalid[j] = row < p.rows;
+            if (rvalid[j]) {
+                ra0[j] = ldg128(p.a0 + row * p.a0_ld + kc * BK + a_col);
+                if (AMODE == A_BNBWD) ra1[j] = ldg128(p.a1 + row * p.a1_ld + kc * BK + a_col);
+            }
+        }
+    };
+    auto store_A = [&](int st, int kc) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (rvalid[j]) {
+                if (AMODE == A_PLAIN) {
+                    v = ra0[j];
+                } else {
+                    const int c = kc * BK + a_col;
+                    const uint32_t* x0 = reinterpret_cast<const uint32_t*>(&ra0[j]);
+                    const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&ra1[j]);
+                    uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 a = bf2_to_f2(x0[e]);
+                        const float2 k0 = *reinterpret_cast<const float2*>(&sCoef[c + 2 * e]);
+                        const float2 k1 = *reinterpret_cast<const float2*>(&sCoef[p.kdim + c + 2 * e]);
+                        float r0, r1;
+                        if (AMODE == A_AFFINE) {
+                            r0 = fmaxf(fmaf(a.x, k0.x, k1.x), 0.f);
+                            r1 = fmaxf(fmaf(a.y, k0.y, k1.y), 0.f);
+                        } else {
+                            const float2 y = bf2_to_f2(x1[e]);
+                            const float2 k2 = *reinterpret_cast<const float2*>(&sCoef[2 * p.kdim + c + 2 * e]);
+                            r0 = fmaf(k0.x, a.x, fmaf(k1.x, y.x, k2.x));
+                            r1 = fmaf(k0.y, a.y, fmaf(k1.y, y.y, k2.y));
+                        }
+                        o[e] = f2_to_bf2(r0, r1);
+                    }
+                }
+            }
+            *reinterpret_cast<uint4*>(&sA[(st * BM + a_row + j * 64) * LDS + a_col]) = v;
+        }
+    };
+    auto load_B = [&](int st, int kc) {
+        for (int i = tid; i < BN * 4; i += kThreads) {
+            const int r = i >> 2, ch = i & 3;
+            const int nrow = n0 + r;
+            const bool ok = nrow < p.n;
+            const bf16* src = p.b + (size_t)(ok ? nrow : 0) * p.kdim + kc * BK + ch * 8;
+            cp_async16(&sB[(st * BN + r) * LDS + ch * 8], src, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+
+    float acc[MF][4][4];
+    float s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+
+    const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total = my_tiles * KT;
+    if (total > 0) {
+        load_A(blockIdx.x, 0);
+        load_B(0, 0);
+    }
+    for (long long it = 0; it < total; ++it) {
+        const long long tile = blockIdx.x + (it / KT) * gridDim.x;
+        const int kc = (int)(it % KT);
+        const int st = (int)(it & 1);
+        store_A(st, kc);
+        cp_async_wait_all();
+        __syncthreads();
+        if (it + 1 < total) {
+            const long long nit = it + 1;
+            load_A(blockIdx.x + (nit / KT) * gridDim.x, (int)(nit % KT));
+            load_B(st ^ 1, (int)(nit % KT));
+        }
+        if (kc == 0) {
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[mf][nf][e] = 0.f;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t af[MF][4], bfr[2][4];
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf)
+                ldsm_x4(af[mf], smem_u32(&sA[(st * BM + wm * (MF * 16) + mf * 16 + (lane & 15)) * LDS + ks * 16 +
+                                             (lane >> 4) * 8]));
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+                ldsm_x4(bfr[nb], smem_u32(&sB[(st * BN + wn * 32 + nb * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS +
+                                              ks * 16 + ((lane >> 3) & 1) * 8]));
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf)
+                    mma_bf16_16816(acc[mf][nf], af[mf], bfr[nf >> 1][(nf & 1) * 2], bfr[nf >> 1][(nf & 1) * 2 + 1]);
+        }
+        if (kc == KT - 1) {
+            // ---- epilogue: fp32 accumulators -> bf16 tile in shared memory -> coalesced stores + column sums
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf) {
+                    const int r = wm * (MF * 16) + mf * 16 + g, c = wn * 32 + nf * 8 + t4 * 2;
+                    *reinterpret_cast<uint32_t*>(&sC[r * CLD + c]) = f2_to_bf2(acc[mf][nf][0], acc[mf][nf][1]);
+                    *reinterpret_cast<uint32_t*>(&sC[(r + 8) * CLD + c]) = f2_to_bf2(acc[mf][nf][2], acc[mf][nf][3]);
+                }
+            __syncthreads();
+            const int chunk = tid % CPR;
+            const int col0 = n0 + chunk * 8;
+            if (col0 < p.n) {
+#pragma unroll
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    const int r = tid / CPR + ps * RPP;
+                    const long long grow = tile * BM + r;
+                    if (grow < p.rows) {
+                        uint4 v = *reinterpret_cast<const uint4*>(&sC[r * CLD + chunk * 8]);
+                        uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
+                        if (MASK) {
+                            const uint4 yq = ldg128(p.yp + grow * p.yp_ld + col0);
+                            const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yq);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 d = bf2_to_f2(vv[e]);
+                                const float2 y = bf2_to_f2(yy[e]);
+                                const int c = chunk * 8 + 2 * e;
+                                const float a0 = fmaf(y.x, sPrev[c], sPrev[BN + c]);
+                                const float a1 = fmaf(y.y, sPrev[c + 1], sPrev[BN + c + 1]);
+                                d.x = a0 > 0.f ? d.x : 0.f;
+                                d.y = a1 > 0.f ? d.y : 0.f;
+                                const float h0 = (y.x - sPrev[2 * BN + c]) * sPrev[3 * BN + c];
+                                const float h1 = (y.y - sPrev[2 * BN + c + 1]) * sPrev[3 * BN + c + 1];
+                                s1[2 * e] += d.x; s1[2 * e + 1] += d.y;
+                                s2[2 * e] = fmaf(d.x, h0, s2[2 * e]);
+                                s2[2 * e + 1] = fmaf(d.y, h1, s2[2 * e + 1]);
+                                vv[e] = f2_to_bf2(d.x, d.y);
+                            }
+                        } else if (p.sums) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 d = bf2_to_f2(vv[e]);
+                                s1[2 * e] += d.x; s1[2 * e + 1] += d.y;
+                                s2[2 * e] = fmaf(d.x, d.x, s2[2 * e]);
+                                s2[2 * e + 1] = fmaf(d.y, d.y, s2[2 * e + 1]);
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(p.out + grow * p.out_ld + col0) = v;
+                    }
+                }
+            }
+            // sC is next written after the main-loop barrier of the following iteration
+        }
+    }
+
+    if (p.sums) {
+        // column sums: lanes sharing a chunk within the warp, then the 8 warps through shared memory
+        __syncthreads();
+        float* red = reinterpret_cast<float*>(sC);  // [8 warps][2][BN]
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+#pragma unroll
+            for (int o = CPR; o < 32; o <<= 1) {
+                s1[e] += __shfl_xor_sync(kFull, s1[e], o);
+                s2[e] += __shfl_xor_sync(kFull, s2[e], o);
+            }
+        }
+        if (CPR >= 32 || lane < CPR) {
+            const int chunk = tid % CPR;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                red[(warp * 2 + 0) * BN + chunk * 8 + e] = s1[e];
+                red[(warp * 2 + 1) * BN + chunk * 8 + e] = s2[e];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * BN; i += kThreads) {
+            const int which = i / BN, c = i - which * BN;
+            if (n0 + c < p.n) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += red[(w * 2 + which) * BN + c];
+                atomicAdd(p.sums + (size_t)which * p.n + n0 + c, s);
+            }
+        }
+    }
+}
+
+template <int BN, int AMODE, bool MASK>
+int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+    constexpr int NCOEF = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
+    const size_t smem = (size_t)(2 * BM * LDS + 2 * BN * LDS + BM * (BN + 8)) * sizeof(bf16) +
+                        (size_t)(NCOEF * a.kdim + (MASK ? 4 * BN : 0)) * sizeof(float);
+    if (smem > 110 * 1024) return fail_arg("pn2_mlp_gemm", "reduction dimension too large for shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        PN2_CHECK(cudaFuncSetAttribute(gemm_rows_kernel<BN, AMODE, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       110 * 1024),
+                  "gemm: cudaFuncSetAttribute");
+        configured = 110 * 1024;
+    }
+    const long long tiles = (a.rows + BM - 1) / BM;
+    const int ny = (a.n + BN - 1) / BN;
+    long long gx = (2 * 148) / ny;
+    if (gx < 1) gx = 1;
+    if (gx > tiles) gx = tiles;
+    dim3 grid((unsigned)gx, ny);
+    gemm_rows_kernel<BN, AMODE, MASK><<<grid, kThreads, smem, stream>>>(a);
+    PN2_CHECK_LAUNCH("gemm_rows_kernel");
+    return 0;
+}
+
+template <int AMODE, bool MASK>
+int dispatch_bn(const GemmArgs& a, cudaStream_t stream) {
+    if (a.n <= 32) return launch_gemm<32, AMODE, MASK>(a, stream);
+    if (a.n <= 64) return launch_gemm<64, AMODE, MASK>(a, stream);
+    return launch_gemm<128, AMODE, MASK>(a, stream);
+}
+
+int check_common(const char* who, long long rows, int kdim, int n) {
+    if (rows < 0 || kdim <= 0 || n <= 0) return fail_arg(who, "non-positive size");
+    if (kdim % 32 != 0) return fail_arg(who, "reduction dimension must be a multiple of 32");
+    if (n % 8 != 0) return fail_arg(who, "output columns must be a multiple of 8");
+    return 0;
+}
+
+// ------------------------------------------------------------------ wgrad -------------------
+constexpr int TN = 128, TK = 128, BR = 32, SLD = 128 + 8;
+
+struct WgradArgs {
+    long long rows;
+    int n, kp, k_true;
+    const bf16* dz; int dz_ld;
+    const bf16* y; int y_ld;
+    const float *cA, *cB, *cC;
+    const bf16* x; int x_ld;
+    const float *in_scale, *in_shift;
+    float* dw; int dw_ld;
+};
+
+template <bool AFFINE>
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs p) {
+    __shared__ __align__(16) bf16 sD[2][BR][SLD];
+    __shared__ __align__(16) bf16 sX[2][BR][SLD];
+    __shared__ float sCo[5][128];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.x * TN, k0 = blockIdx.y * TK;
+    for (int i = tid; i < 5 * 128; i += kThreads) {
+        const int which = i >> 7, c = i & 127;
+        float v = 0.f;
+        if (which < 3) {
+            if (n0 + c < p.n) v = (which == 0 ? p.cA : (which == 1 ? p.cB : p.cC))[n0 + c];
+        } else if (AFFINE) {
+            if (k0 + c < p.kp) v = (which == 3 ? p.in_scale : p.in_shift)[k0 + c];
+        }
+        sCo[which][c] = v;
+    }
+    __syncthreads();
+
+    const int l_row = tid >> 4, l_col = (tid & 15) * 8;
+    const bool ncol_ok = n0 + l_col < p.n, kcol_ok = k0 + l_col < p.kp;
+    uint4 rd[2], ry[2], rx[2];
+    bool rvalid[2];
+    const long long chunks = (p.rows + BR - 1) / BR;
+
+    auto load = [&](long long ch) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long row = ch * BR + l_row + j * 16;
+            rvalid[j] = row < p.rows;
+            if (rvalid[j]) {
+                if (ncol_ok) {
+                    rd[j] = ldg128(p.dz + row * p.dz_ld + n0 + l_col);
+                    ry[j] = ldg128(p.y + row * p.y_ld + n0 + l_col);
+                }
+                if (kcol_ok) rx[j] = ldg128(p.x + row * p.x_ld + k0 + l_col);
+            }
+        }
+    };
+    auto store = [&](int st) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint4 vd = make_uint4(0u, 0u, 0u, 0u), vx = make_uint4(0u, 0u, 0u, 0u);
+            if (rvalid[j]) {
+                if (ncol_ok) {
+                    const uint32_t* a = reinterpret_cast<const uint32_t*>(&rd[j]);
+                    const uint32_t* b = reinterpret_cast<const uint32_t*>(&ry[j]);
+                    uint32_t* o = reinterpret_cast<uint32_t*>(&vd);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 d = bf2_to_f2(a[e]), y = bf2_to_f2(b[e]);
+                        const int c = l_col + 2 * e;
+                        o[e] = f2_to_bf2(fmaf(sCo[0][c], d.x, fmaf(sCo[1][c], y.x, sCo[2][c])),
+                                         fmaf(sCo[0][c + 1], d.y, fmaf(sCo[1][c + 1], y.y, sCo[2][c + 1])));
+                    }
+                }
+                if (kcol_ok) {
+                    if (AFFINE) {
+                        const uint32_t* a = reinterpret_cast<const uint32_t*>(&rx[j]);
+                        uint32_t* o = reinterpret_cast<uint32_t*>(&vx);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 x = bf2_to_f2(a[e]);
+                            const int c = l_col + 2 * e;
+                            o[e] = f2_to_bf2(fmaxf(fmaf(x.x, sCo[3][c], sCo[4][c]), 0.f),
+                                             fmaxf(fmaf(x.y, sCo[3][c + 1], sCo[4][c + 1]), 0.f));
+                        }
+                    } else {
+                        vx = rx[j];
+                    }
+                }
+            }
+            *reinterpret_cast<uint4*>(&sD[st][l_row + j * 16][l_col]) = vd;
+            *reinterpret_cast<uint4*>(&sX[st][l_row + j * 16][l_col]) = vx;
+        }
+    };
+
+    const int wn2 = warp >> 2, wk = warp & 3;
+    const bool warp_on = (n0 + wn2 * 64 < p.n) && (k0 + wk * 32 < p.kp);
+    float acc[4][4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
+
+    const int mi = lane >> 3, l7 = lane & 7;
+    long long ch = blockIdx.z;
+    if (ch < chunks) load(ch);
+    int st = 0;
+    for (; ch < chunks; ch += gridDim.z, st ^= 1) {
+        store(st);
+        __syncthreads();
+        if (ch + gridDim.z < chunks) load(ch + gridDim.z);
+        if (warp_on) {
+#pragma unroll
+            for (int rs = 0; rs < BR; rs += 16) {
+                uint32_t af[4][4], bfr[2][4];
+#pragma unroll
+                for (int mf = 0; mf < 4; ++mf)
+                    ldsm_x4_trans(af[mf], smem_u32(&sD[st][rs + (mi >> 1) * 8 + l7][wn2 * 64 + mf * 16 + (mi & 1) * 8]));
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb)
+                    ldsm_x4_trans(bfr[nb], smem_u32(&sX[st][rs + (mi & 1) * 8 + l7][wk * 32 + nb * 16 + (mi >> 1) * 8]));
+#pragma unroll
+                for (int mf = 0; mf < 4; ++mf) {
+                    if (n0 + wn2 * 64 + mf * 16 < p.n) {
+#pragma unroll
+                        for (int nf = 0; nf < 4; ++nf)
+                            mma_bf16_16816(acc[mf][nf], af[mf], bfr[nf >> 1][(nf & 1) * 2], bfr[nf >> 1][(nf & 1) * 2 + 1]);
+                    }
+                }
+            }
+        }
+        // the buffer written at the next iteration (st^1) was last read one iteration ago; the
+        // barrier above orders those reads before these writes
+    }
+    if (warp_on) {
+        const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+        for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int n = n0 + wn2 * 64 + mf * 16 + g + (e >> 1) * 8;
+                    const int k = k0 + wk * 32 + nf * 8 + t4 * 2 + (e & 1);
+                    if (n < p.n && k < p.k_true) atomicAdd(p.dw + (size_t)n * p.dw_ld + k, acc[mf][nf][e]);
+                }
+    }
+}
+
+// ------------------------------------------------------------------ small per-channel kernels
+__global__ void bn_finalize_kernel(int n, float inv_rows, float unbias, const float* __restrict__ sums,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ bias, float momentum, float eps, float* running_mean,
+                                   float* running_var, long long* num_batches_tracked, float* scale, float* shift,
+                                   float* mean_out, float* rstd_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    if (c >= n) return;
+    const float mean = sums[c] * inv_rows;
+    const float var = fmaxf(fmaf(-mean, mean, sums[n + c] * inv_rows), 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = fmaf(-mean, sc, beta[c]);
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+    if (running_mean) {
+        // the conv bias shifts the batch mean BatchNorm sees; the GEMM omits it (BN cancels it exactly)
+        const float m = mean + (bias ? bias[c] : 0.f);
+        running_mean[c] = fmaf(momentum, m - running_mean[c], running_mean[c]);
+        running_var[c] = fmaf(momentum, var * unbias - running_var[c], running_var[c]);
+    }
+}
+
+__global__ void bn_eval_affine_kernel(int n, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ bias, const float* __restrict__ running_mean,
+                                      const float* __restrict__ running_var, float eps, float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+    scale[c] = sc;
+    shift[c] = fmaf((bias ? bias[c] : 0.f) - running_mean[c], sc, beta[c]);
+}
+
+__global__ void bn_bwd_coefs_kernel(int n, float inv_rows, const float* __restrict__ sums,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, float* cA, float* cB, float* cC, float* dgamma,
+                                    float* dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const float s1 = sums[c], s2 = sums[n + c];
+    const float m1 = s1 * inv_rows, m2 = s2 * inv_rows;
+    const float gr = gamma[c] * rstd[c];
+    cA[c] = gr;
+    cB[c] = -gr * m2 * rstd[c];
+    cC[c] = gr * (m2 * rstd[c] * mean[c] - m1);
+    dgamma[c] = s2;
+    dbeta[c] = s1;
+}
+
+__global__ void prep_weights_kernel(int n, int k_true, int kp, const float* __restrict__ w, bf16* __restrict__ wb,
+                                    bf16* __restrict__ wt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * kp) return;
+    const int r = i / kp, c = i - r * kp;
+    const bf16 v = __float2bfloat16(c < k_true ? w[(size_t)r * k_true + c] : 0.f);
+    wb[i] = v;
+    if (wt) wt[(size_t)c * n + r] = v;
+}
+
+}  // namespace
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
+                                const float* in_shift, const void* w, void* y, int y_ld, float* stats,
+                                pn2_stream_t stream) {
+    if (int e = check_common("pn2_mlp_gemm_fwd", rows, kdim, n)) return e;
+    if (rows == 0) return 0;
+    if (!x || !w || !y) return fail_arg("pn2_mlp_gemm_fwd", "null pointer");
+    if (x_ld % 8 || y_ld % 8 || x_ld < kdim || y_ld < n) return fail_arg("pn2_mlp_gemm_fwd", "bad leading dimension");
+    GemmArgs a{};
+    a.rows = rows; a.kdim = kdim; a.n = n;
+    a.a0 = (const bf16*)x; a.a0_ld = x_ld;
+    a.c0 = in_scale; a.c1 = in_shift;
+    a.b = (const bf16*)w;
+    a.out = (bf16*)y; a.out_ld = y_ld;
+    a.sums = stats;
+    if (in_scale) return dispatch_bn<A_AFFINE, false>(a, (cudaStream_t)stream);
+    return dispatch_bn<A_PLAIN, false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const void* dz, int dz_ld, const void* y,
+                                  int y_ld, const float* cA, const float* cB, const float* cC, const void* wt,
+                                  const void* y_prev, int y_prev_ld, const float* prev_scale, const float* prev_shift,
+                                  const float* prev_mean, const float* prev_rstd, void* dz_prev, int dz_prev_ld,
+                                  float* sums_prev, pn2_stream_t stream) {
+    if (int e = check_common("pn2_mlp_gemm_dgrad", rows, n_red, k_out)) return e;
+    if (rows == 0) return 0;
+    if (!dz || !y || !cA || !cB || !cC || !wt || !dz_prev) return fail_arg("pn2_mlp_gemm_dgrad", "null pointer");
+    if (dz_ld % 8 || y_ld % 8 || dz_prev_ld % 8 || dz_prev_ld < k_out)
+        return fail_arg("pn2_mlp_gemm_dgrad", "bad leading dimension");
+    GemmArgs a{};
+    a.rows = rows; a.kdim = n_red; a.n = k_out;
+    a.a0 = (const bf16*)dz; a.a0_ld = dz_ld;
+    a.a1 = (const bf16*)y; a.a1_ld = y_ld;
+    a.c0 = cA; a.c1 = cB; a.c2 = cC;
+    a.b = (const bf16*)wt;
+    a.out = (bf16*)dz_prev; a.out_ld = dz_prev_ld;
+    if (y_prev) {
+        if (!prev_scale || !prev_shift || !prev_mean || !prev_rstd || !sums_prev || y_prev_ld % 8)
+            return fail_arg("pn2_mlp_gemm_dgrad", "masking needs the previous layer's constants");
+        a.sums = sums_prev;
+        a.yp = (const bf16*)y_prev; a.yp_ld = y_prev_ld;
+        a.p_scale = prev_scale; a.p_shift = prev_shift; a.p_mean = prev_mean; a.p_rstd = prev_rstd;
+        return dispatch_bn<A_BNBWD, true>(a, (cudaStream_t)stream);
+    }
+    a.sums = nullptr;
+    return dispatch_bn<A_BNBWD, false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, const void* dz, int dz_ld,
+                                  const void* y, int y_ld, const float* cA, const float* cB, const float* cC,
+                                  const void* x, int x_ld, const float* in_scale, const float* in_shift, float* dw,
+                                  int dw_ld, pn2_stream_t stream) {
+    if (rows < 0 || n <= 0 || kp <= 0 || k_true <= 0 || k_true > kp) return fail_arg("pn2_mlp_gemm_wgrad", "bad size");
+    if (rows == 0) return 0;
+    if (n % 8 || kp % 8 || dz_ld % 8 || y_ld % 8 || x_ld % 8) return fail_arg("pn2_mlp_gemm_wgrad", "sizes must be multiples of 8");
+    if (!dz || !y || !cA || !cB || !cC || !x || !dw) return fail_arg("pn2_mlp_gemm_wgrad", "null pointer");
+    WgradArgs a{};
+    a.rows = rows; a.n = n; a.kp = kp; a.k_true = k_true;
+    a.dz = (const bf16*)dz; a.dz_ld = dz_ld;
+    a.y = (const bf16*)y; a.y_ld = y_ld;
+    a.cA = cA; a.cB = cB; a.cC = cC;
+    a.x = (const bf16*)x; a.x_ld = x_ld;
+    a.in_scale = in_scale; a.in_shift = in_shift;
+    a.dw = dw; a.dw_ld = dw_ld;
+    const int gx = (n + TN - 1) / TN, gy = (kp + TK - 1) / TK;
+    const long long chunks = (rows + BR - 1) / BR;
+    long long gz = (2 * 148) / (gx * gy);
+    if (gz < 1) gz = 1;
+    if (gz > chunks) gz = chunks;
+    dim3 grid(gx, gy, (unsigned)gz);
+    if (in_scale)
+        wgrad_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    else
+        wgrad_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    PN2_CHECK_LAUNCH("wgrad_kernel");
+    return 0;
+}
+
+extern "C" int pn2_bn_finalize(int n, long long rows, const float* sums, const float* gamma, const float* beta,
+                               const float* conv_bias, float momentum, float eps, float* running_mean,
+                               float* running_var, long long* num_batches_tracked, float* scale, float* shift,
+                               float* mean, float* rstd, pn2_stream_t stream) {
+    if (n <= 0 || rows <= 0) return fail_arg("pn2_bn_finalize", "non-positive size");
+    if (!sums || !gamma || !beta || !scale || !shift || !mean || !rstd) return fail_arg("pn2_bn_finalize", "null pointer");
+    const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
+    bn_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        n, (float)(1.0 / (double)rows), unbias, sums, gamma, beta, conv_bias, momentum, eps, running_mean, running_var,
+        num_batches_tracked, scale, shift, mean, rstd);
+    PN2_CHECK_LAUNCH("bn_finalize_kernel");
+    return 0;
+}
+
+extern "C" int pn2_bn_eval_affine(int n, const float* gamma, const float* beta, const float* conv_bias,
+                                  const float* running_mean, const float* running_var, float eps, float* scale,
+                                  float* shift, pn2_stream_t stream) {
+    if (n <= 0) return fail_arg("pn2_bn_eval_affine", "non-positive size");
+    if (!gamma || !beta || !running_mean || !running_var || !scale || !shift)
+        return fail_arg("pn2_bn_eval_affine", "null pointer");
+    bn_eval_affine_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, gamma, beta, conv_bias, running_mean,
+                                                                            running_var, eps, scale, shift);
+    PN2_CHECK_LAUNCH("bn_eval_affine_kernel");
+    return 0;
+}
+
+extern "C" int pn2_bn_bwd_coefs(int n, long long rows, const float* sums, const float* gamma, const float* mean,
+                                const float* rstd, float* cA, float* cB, float* cC, float* dgamma, float* dbeta,
+                                pn2_stream_t stream) {
+    if (n <= 0 || rows <= 0) return fail_arg("pn2_bn_bwd_coefs", "non-positive size");
+    if (!sums || !gamma || !mean || !rstd || !cA || !cB || !cC || !dgamma || !dbeta)
+        return fail_arg("pn2_bn_bwd_coefs", "null pointer");
+    bn_bwd_coefs_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, (float)(1.0 / (double)rows), sums, gamma,
+                                                                          mean, rstd, cA, cB, cC, dgamma, dbeta);
+    PN2_CHECK_LAUNCH("bn_bwd_coefs_kernel");
+    return 0;
+}
+
+extern "C" int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_bf16, void* wt_bf16,
+                                    pn2_stream_t stream) {
+    if (n <= 0 || k_true <= 0 || kp < k_true) return fail_arg("pn2_mlp_prep_weights", "bad size");
+    if (!w || !w_bf16) return fail_arg("pn2_mlp_prep_weights", "null pointer");
+    const int total = n * kp;
+    prep_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, k_true, kp, w, (bf16*)w_bf16,
+                                                                               (bf16*)wt_bf16);
+    PN2_CHECK_LAUNCH("prep_weights_kernel");
+    return 0;
+}

@@ -1,0 +1,445 @@
+// mlp_rows.cu -- building and consuming the ROW matrices of the grouped MLP, sm_100a.
+//
+// The two ends of every fused SA / FP layer (mlp_gemm.cu holds the middle):
+//
+//   to_rows          (B,C,N) fp32 channel-major  ->  rows [B*N][ld] bf16        (smem transpose)
+//   sa_build_rows    grouping + "- centre" + concat of reference pointnet_utils.py:389-396 (SA-MSG:
+//                    [features, xyz - centre]), :570-575 (given centres: ... + centre features
+//                    broadcast over K) and :170-186 (group_all: [xyz, features]) in ONE pass, written
+//                    as bf16 rows; the source features are themselves rows, optionally still in
+//                    pre-BatchNorm form (scale/shift + ReLU applied on the fly).
+//   fp_build_rows    three-NN inverse-distance weights (pointnet_utils.py:446-449), three-point
+//                    interpolation (interpolate_gpu.cu:149-169) and the [skip, interpolated] concat
+//                    (:455-456) in one pass; S == 1 broadcasts (:443-444).
+//   pool_fwd         BatchNorm + ReLU of the last layer, max over the K rows of a group (:403,509),
+//                    written channel-major fp32 (the module's output layout), as bf16 rows for the next
+//                    fused consumer, plus the arg-max for backward.  K == 1 is the FP / head case.
+//   pool_bwd         routes the output gradient to the arg-max rows through the ReLU mask and reduces
+//                    the two BatchNorm-backward sums.
+//   sa_rows_bwd / fp_rows_bwd   scatter the gradient of the built rows back to the feature tensors.
+//
+// All of these are HBM/L2-bound gathers, scatters and transposes: one warp per row with lanes
+// along the contiguous channel dimension, shared-memory tiles where a transpose is needed.
+#include "mma_common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------ to_rows -----------------
+__global__ void __launch_bounds__(256) to_rows_kernel(int c, int n, int ld, const float* __restrict__ src,
+                                                       bf16* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int cc = c0 + j, nn = n0 + tx;
+        tile[j][tx] = (cc < c && nn < n) ? src[((size_t)b * c + cc) * n + nn] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int nn = n0 + j, cc = c0 + tx;
+        if (nn < n && cc < ld) dst[((size_t)b * n + nn) * ld + cc] = __float2bfloat16(tile[tx][j]);
+    }
+}
+
+// ------------------------------------------------------------------ sa_build_rows -----------
+struct RowSrc {  // bf16 rows with an optional per-channel affine + ReLU ("still pre-BatchNorm")
+    const bf16* p;
+    int c, ld;
+    const float *scale, *shift;
+};
+__device__ __forceinline__ float row_val(const RowSrc& s, size_t row, int ch) {
+    float v = bf_to_f(s.p[row * s.ld + ch]);
+    if (s.scale) v = fmaxf(fmaf(v, __ldg(s.scale + ch), __ldg(s.shift + ch)), 0.f);
+    return v;
+}
+
+struct SaBuildArgs {
+    int b, n, s, k;
+    const float *xyz, *new_xyz;  // (B,3,N), (B,3,S) | null (centre 0)
+    const int* idx;              // (B,S,K) | null (identity: row k of group <-> point k)
+    RowSrc feat, cen;
+    int xyz_first;
+    bf16* out;
+    int out_ld;
+};
+
+__global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long total = (long long)a.b * a.s * a.k;
+    if (row >= total) return;
+    const int kk = (int)(row % a.k);
+    const long long bs = row / a.k;
+    const int s = (int)(bs % a.s), b = (int)(bs / a.s);
+    const int j = a.idx ? a.idx[row] : kk;
+    float rel[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float cx = a.new_xyz ? __ldg(a.new_xyz + ((size_t)b * 3 + d) * a.s + s) : 0.f;
+        rel[d] = __ldg(a.xyz + ((size_t)b * 3 + d) * a.n + j) - cx;
+    }
+    const size_t frow = (size_t)b * a.n + j, crow = (size_t)b * a.s + s;
+    const int fc = a.feat.p ? a.feat.c : 0, cc = a.cen.p ? a.cen.c : 0;
+    const int f0 = a.xyz_first ? 3 : 0, x0 = a.xyz_first ? 0 : fc, c0 = fc + 3;
+    bf16* o = a.out + (size_t)row * a.out_ld;
+    for (int col = lane; col < a.out_ld; col += 32) {
+        float v = 0.f;
+        if (col >= f0 && col < f0 + fc) v = row_val(a.feat, frow, col - f0);
+        else if (col >= x0 && col < x0 + 3) v = rel[col - x0];
+        else if (col >= c0 && col < c0 + cc) v = row_val(a.cen, crow, col - c0);
+        o[col] = __float2bfloat16(v);
+    }
+}
+
+// ------------------------------------------------------------------ fp_build_rows -----------
+struct FpBuildArgs {
+    int b, n, s;
+    RowSrc skip, coarse;
+    const int* idx;       // (B,N,3)
+    const float* dist2;   // (B,N,3) squared distances from three_nn
+    bf16* out;
+    int out_ld;
+};
+// weights of reference pointnet_utils.py:446-449: w_j = (1/(sqrt(d2_j)+1e-8)) / sum_j(...), in fp32
+__device__ __forceinline__ void nn_weights(const float* d2, float (&w)[3]) {
+    float r[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[j] = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d2[j]), 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r[0], r[1]), r[2]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w[j] = __fdiv_rn(r[j], norm);
+}
+
+__global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long total = (long long)a.b * a.n;
+    if (row >= total) return;
+    const int b = (int)(row / a.n);
+    int id[3] = {0, 0, 0};
+    float w[3] = {1.f, 0.f, 0.f};
+    if (a.s > 1) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) id[j] = a.idx[row * 3 + j];
+        nn_weights(a.dist2 + row * 3, w);
+    }
+    const int sc = a.skip.p ? a.skip.c : 0;
+    bf16* o = a.out + (size_t)row * a.out_ld;
+    for (int col = lane; col < a.out_ld; col += 32) {
+        float v = 0.f;
+        if (col < sc) {
+            v = row_val(a.skip, (size_t)row, col);
+        } else if (col < sc + a.coarse.c) {
+            const int ch = col - sc;
+            if (a.s > 1) {
+                const float p0 = row_val(a.coarse, (size_t)b * a.s + id[0], ch);
+                const float p1 = row_val(a.coarse, (size_t)b * a.s + id[1], ch);
+                const float p2 = row_val(a.coarse, (size_t)b * a.s + id[2], ch);
+                v = fmaf(w[2], p2, fmaf(w[0], p0, w[1] * p1));  // interpolate_gpu.cu:168 rounding order
+            } else {
+                v = row_val(a.coarse, (size_t)b, ch);
+            }
+        }
+        o[col] = __float2bfloat16(v);
+    }
+}
+
+// ------------------------------------------------------------------ pool fwd / bwd ----------
+struct PoolArgs {
+    int b, s, k, c;
+    const bf16* y; int y_ld;
+    const float *scale, *shift, *mean, *rstd;
+    float* out_cm;        // (B,C,S)
+    bf16* out_rows; int out_ld;
+    int* argmax;          // (B,S,C)
+    const float* dout_cm; // backward
+    bf16* dz; int dz_ld;
+    float* sums;          // [2][C]
+};
+
+// grid (ceil(S/32), B); a warp owns groups s0+warp, +8, +16, +24; lanes own channel pairs of a 64-wide chunk
+__global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
+    __shared__ float tile[32][65];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, s0 = blockIdx.x * 32;
+    for (int c0 = 0; c0 < a.c; c0 += 64) {
+        const int ch = c0 + lane * 2;
+        const bool ok = ch < a.c;  // c is even (multiple of 8)
+        float sc0 = 0.f, sc1 = 0.f, sh0 = 0.f, sh1 = 0.f;
+        if (ok) { sc0 = a.scale[ch]; sc1 = a.scale[ch + 1]; sh0 = a.shift[ch]; sh1 = a.shift[ch + 1]; }
+        for (int gi = warp; gi < 32; gi += 8) {
+            const int s = s0 + gi;
+            float m0 = -1.f, m1 = -1.f;  // below every ReLU output: the first row always wins
+            int i0 = 0, i1 = 0;
+            if (ok && s < a.s) {
+                const bf16* yr = a.y + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch;
+                for (int kk = 0; kk < a.k; ++kk) {
+                    const float2 v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
+                    const float r0 = fmaxf(fmaf(v.x, sc0, sh0), 0.f), r1 = fmaxf(fmaf(v.y, sc1, sh1), 0.f);
+                    if (r0 > m0) { m0 = r0; i0 = kk; }
+                    if (r1 > m1) { m1 = r1; i1 = kk; }
+                }
+                const size_t g = (size_t)b * a.s + s;
+                if (a.out_rows) *reinterpret_cast<uint32_t*>(a.out_rows + g * a.out_ld + ch) = f2_to_bf2(m0, m1);
+                if (a.argmax) *reinterpret_cast<int2*>(a.argmax + g * a.c + ch) = make_int2(i0, i1);
+            }
+            tile[gi][lane * 2] = m0;
+            tile[gi][lane * 2 + 1] = m1;
+        }
+        __syncthreads();
+        for (int cc = warp; cc < 64; cc += 8) {
+            const int chn = c0 + cc, s = s0 + lane;
+            if (chn < a.c && s < a.s) a.out_cm[((size_t)b * a.c + chn) * a.s + s] = tile[lane][cc];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
+    __shared__ float tile[32][65];
+    __shared__ float red[8][2][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, s0 = blockIdx.x * 32;
+    for (int c0 = 0; c0 < a.c; c0 += 64) {
+        for (int cc = warp; cc < 64; cc += 8) {
+            const int chn = c0 + cc, s = s0 + lane;
+            tile[lane][cc] = (chn < a.c && s < a.s) ? a.dout_cm[((size_t)b * a.c + chn) * a.s + s] : 0.f;
+        }
+        __syncthreads();
+        const int ch = c0 + lane * 2;
+        const bool ok = ch < a.c;
+        float sc0 = 0.f, sc1 = 0.f, sh0 = 0.f, sh1 = 0.f, mu0 = 0.f, mu1 = 0.f, rs0 = 0.f, rs1 = 0.f;
+        if (ok) {
+            sc0 = a.scale[ch]; sc1 = a.scale[ch + 1]; sh0 = a.shift[ch]; sh1 = a.shift[ch + 1];
+            mu0 = a.mean[ch]; mu1 = a.mean[ch + 1]; rs0 = a.rstd[ch]; rs1 = a.rstd[ch + 1];
+        }
+        float p1a = 0.f, p1b = 0.f, p2a = 0.f, p2b = 0.f;
+        for (int gi = warp; gi < 32; gi += 8) {
+            const int s = s0 + gi;
+            if (!(ok && s < a.s)) continue;
+            const size_t g = (size_t)b * a.s + s;
+            int i0 = 0, i1 = 0;
+            if (a.argmax) { const int2 am = *reinterpret_cast<const int2*>(a.argmax + g * a.c + ch); i0 = am.x; i1 = am.y; }
+            const float g0 = tile[gi][lane * 2], g1 = tile[gi][lane * 2 + 1];
+            const bf16* yr = a.y + (g * a.k) * a.y_ld + ch;
+            bf16* dr = a.dz + (g * a.k) * a.dz_ld + ch;
+            for (int kk = 0; kk < a.k; ++kk) {
+                float d0 = 0.f, d1 = 0.f;
+                if (kk == i0 || kk == i1) {
+                    const float2 v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
+                    if (kk == i0 && fmaf(v.x, sc0, sh0) > 0.f) { d0 = g0; p1a += d0; p2a = fmaf(d0, (v.x - mu0) * rs0, p2a); }
+                    if (kk == i1 && fmaf(v.y, sc1, sh1) > 0.f) { d1 = g1; p1b += d1; p2b = fmaf(d1, (v.y - mu1) * rs1, p2b); }
+                }
+                *reinterpret_cast<uint32_t*>(dr + (size_t)kk * a.dz_ld) = f2_to_bf2(d0, d1);
+            }
+        }
+        red[warp][0][lane * 2] = p1a; red[warp][0][lane * 2 + 1] = p1b;
+        red[warp][1][lane * 2] = p2a; red[warp][1][lane * 2 + 1] = p2b;
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int which = threadIdx.x >> 6, cc = threadIdx.x & 63;
+            if (c0 + cc < a.c) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += red[w][which][cc];
+                if (t != 0.f) atomicAdd(a.sums + (size_t)which * a.c + c0 + cc, t);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ rows backward -----------
+struct SaBwdArgs {
+    int b, n, s, k;
+    const int* idx;
+    const bf16* dx; int dx_ld;
+    int feat_c; float* dfeat_cm;   // (B,feat_c,N) zeroed, atomics
+    int cen_c; float* dcen_cm;     // (B,cen_c,S)  zeroed, atomics
+    int xyz_first;
+};
+__global__ void __launch_bounds__(kThreads) sa_rows_bwd_kernel(const SaBwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long total = (long long)a.b * a.s * a.k;
+    if (row >= total) return;
+    const int kk = (int)(row % a.k);
+    const long long bs = row / a.k;
+    const int s = (int)(bs % a.s), b = (int)(bs / a.s);
+    const int j = a.idx ? a.idx[row] : kk;
+    const int fc = a.dfeat_cm ? a.feat_c : 0, cc = a.dcen_cm ? a.cen_c : 0;
+    const int f0 = a.xyz_first ? 3 : 0, c0 = a.feat_c + 3;
+    const bf16* d = a.dx + (size_t)row * a.dx_ld;
+    for (int col = lane; col < fc; col += 32) {
+        const float v = bf_to_f(d[f0 + col]);
+        if (v != 0.f) atomicAdd(a.dfeat_cm + ((size_t)b * a.feat_c + col) * a.n + j, v);
+    }
+    for (int col = lane; col < cc; col += 32) {
+        const float v = bf_to_f(d[c0 + col]);
+        if (v != 0.f) atomicAdd(a.dcen_cm + ((size_t)b * a.cen_c + col) * a.s + s, v);
+    }
+}
+
+struct FpBwdArgs {
+    int b, n, s;
+    const int* idx; const float* dist2;
+    const bf16* dx; int dx_ld;
+    int skip_c; float* dskip_cm;       // (B,skip_c,N) plain stores | null
+    int coarse_c; float* dcoarse_rows; // (B*S, coarse_c) zeroed, atomics | null
+};
+__global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long total = (long long)a.b * a.n;
+    if (row >= total) return;
+    const int b = (int)(row / a.n), i = (int)(row % a.n);
+    const bf16* d = a.dx + (size_t)row * a.dx_ld;
+    if (a.dskip_cm)
+        for (int col = lane; col < a.skip_c; col += 32)
+            a.dskip_cm[((size_t)b * a.skip_c + col) * a.n + i] = bf_to_f(d[col]);
+    if (a.dcoarse_rows) {
+        int id[3] = {0, 0, 0};
+        float w[3] = {1.f, 0.f, 0.f};
+        if (a.s > 1) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) id[j] = a.idx[row * 3 + j];
+            nn_weights(a.dist2 + row * 3, w);
+        }
+        for (int col = lane; col < a.coarse_c; col += 32) {
+            const float v = bf_to_f(d[a.skip_c + col]);
+            if (v == 0.f) continue;
+            if (a.s > 1) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    atomicAdd(a.dcoarse_rows + ((size_t)b * a.s + id[j]) * a.coarse_c + col, v * w[j]);
+            } else {
+                atomicAdd(a.dcoarse_rows + (size_t)b * a.coarse_c + col, v);
+            }
+        }
+    }
+}
+
+RowSrc mk_src(const void* p, int c, int ld, const float* scale, const float* shift) {
+    RowSrc s;
+    s.p = (const bf16*)p; s.c = c; s.ld = ld; s.scale = scale; s.shift = shift;
+    return s;
+}
+unsigned warp_blocks(long long rows) { return (unsigned)((rows + (kThreads / 32) - 1) / (kThreads / 32)); }
+
+}  // namespace
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_to_rows(int b, int c, int n, const float* src, void* dst, int ld, pn2_stream_t stream) {
+    if (b < 0 || c < 0 || n < 0 || ld < c) return fail_arg("pn2_to_rows", "bad size");
+    if (b == 0 || n == 0 || ld == 0) return 0;
+    if (!src || !dst) return fail_arg("pn2_to_rows", "null pointer");
+    if (b > 65535) return fail_arg("pn2_to_rows", "b > 65535");
+    dim3 grid((n + 31) / 32, (ld + 31) / 32, b);
+    to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, ld, src, (bf16*)dst);
+    PN2_CHECK_LAUNCH("to_rows_kernel");
+    return 0;
+}
+
+extern "C" int pn2_sa_build_rows(int b, int n, int s, int k, const float* xyz, const float* new_xyz, const int* idx,
+                                 const void* feat, int feat_c, int feat_ld, const float* feat_scale,
+                                 const float* feat_shift, const void* cen, int cen_c, int cen_ld,
+                                 const float* cen_scale, const float* cen_shift, int xyz_first, void* out, int out_ld,
+                                 pn2_stream_t stream) {
+    if (b < 0 || n <= 0 || s <= 0 || k <= 0) return fail_arg("pn2_sa_build_rows", "bad size");
+    if (b == 0) return 0;
+    if (!xyz || !out) return fail_arg("pn2_sa_build_rows", "null pointer");
+    const int need = (feat ? feat_c : 0) + 3 + (cen ? cen_c : 0);
+    if (out_ld < need || out_ld % 8) return fail_arg("pn2_sa_build_rows", "out_ld too small or not a multiple of 8");
+    if (xyz_first && cen) return fail_arg("pn2_sa_build_rows", "centre features are not part of the group-all layout");
+    if (!idx && k != n) return fail_arg("pn2_sa_build_rows", "identity grouping needs k == n");
+    SaBuildArgs a;
+    a.b = b; a.n = n; a.s = s; a.k = k; a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx;
+    a.feat = mk_src(feat, feat_c, feat_ld, feat_scale, feat_shift);
+    a.cen = mk_src(cen, cen_c, cen_ld, cen_scale, cen_shift);
+    a.xyz_first = xyz_first; a.out = (bf16*)out; a.out_ld = out_ld;
+    sa_build_rows_kernel<<<warp_blocks((long long)b * s * k), kThreads, 0, (cudaStream_t)stream>>>(a);
+    PN2_CHECK_LAUNCH("sa_build_rows_kernel");
+    return 0;
+}
+
+extern "C" int pn2_fp_build_rows(int b, int n, int s, const void* skip, int skip_c, int skip_ld,
+                                 const float* skip_scale, const float* skip_shift, const void* coarse, int coarse_c,
+                                 int coarse_ld, const float* coarse_scale, const float* coarse_shift, const int* idx,
+                                 const float* dist2, void* out, int out_ld, pn2_stream_t stream) {
+    if (b < 0 || n <= 0 || s <= 0) return fail_arg("pn2_fp_build_rows", "bad size");
+    if (b == 0) return 0;
+    if (!coarse || !out || (s > 1 && (!idx || !dist2))) return fail_arg("pn2_fp_build_rows", "null pointer");
+    if (out_ld < (skip ? skip_c : 0) + coarse_c || out_ld % 8) return fail_arg("pn2_fp_build_rows", "bad out_ld");
+    FpBuildArgs a;
+    a.b = b; a.n = n; a.s = s;
+    a.skip = mk_src(skip, skip_c, skip_ld, skip_scale, skip_shift);
+    a.coarse = mk_src(coarse, coarse_c, coarse_ld, coarse_scale, coarse_shift);
+    a.idx = idx; a.dist2 = dist2; a.out = (bf16*)out; a.out_ld = out_ld;
+    fp_build_rows_kernel<<<warp_blocks((long long)b * n), kThreads, 0, (cudaStream_t)stream>>>(a);
+    PN2_CHECK_LAUNCH("fp_build_rows_kernel");
+    return 0;
+}
+
+extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld, const float* scale,
+                            const float* shift, float* out_cm, void* out_rows, int out_ld, int* argmax,
+                            pn2_stream_t stream) {
+    if (b < 0 || s <= 0 || k <= 0 || c <= 0 || c % 8) return fail_arg("pn2_pool_fwd", "bad size");
+    if (b == 0) return 0;
+    if (b > 65535) return fail_arg("pn2_pool_fwd", "b > 65535");
+    if (!y || !scale || !shift || !out_cm) return fail_arg("pn2_pool_fwd", "null pointer");
+    PoolArgs a{};
+    a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const bf16*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
+    a.out_cm = out_cm; a.out_rows = (bf16*)out_rows; a.out_ld = out_ld; a.argmax = argmax;
+    dim3 grid((s + 31) / 32, b);
+    pool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    PN2_CHECK_LAUNCH("pool_fwd_kernel");
+    return 0;
+}
+
+extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const void* y, int y_ld,
+                            const float* scale, const float* shift, const float* mean, const float* rstd,
+                            const int* argmax, void* dz, int dz_ld, float* sums, pn2_stream_t stream) {
+    if (b < 0 || s <= 0 || k <= 0 || c <= 0 || c % 8) return fail_arg("pn2_pool_bwd", "bad size");
+    if (b == 0) return 0;
+    if (b > 65535) return fail_arg("pn2_pool_bwd", "b > 65535");
+    if (!dout_cm || !y || !scale || !shift || !mean || !rstd || !dz || !sums) return fail_arg("pn2_pool_bwd", "null pointer");
+    if (k > 1 && !argmax) return fail_arg("pn2_pool_bwd", "argmax required when k > 1");
+    PoolArgs a{};
+    a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const bf16*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
+    a.mean = mean; a.rstd = rstd; a.argmax = const_cast<int*>(argmax); a.dout_cm = dout_cm; a.dz = (bf16*)dz; a.dz_ld = dz_ld; a.sums = sums;
+    dim3 grid((s + 31) / 32, b);
+    pool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    PN2_CHECK_LAUNCH("pool_bwd_kernel");
+    return 0;
+}
+
+extern "C" int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const void* dx, int dx_ld, int feat_c,
+                               float* dfeat_cm, int cen_c, float* dcen_cm, int xyz_first, pn2_stream_t stream) {
+    if (b < 0 || n <= 0 || s <= 0 || k <= 0) return fail_arg("pn2_sa_rows_bwd", "bad size");
+    if (b == 0 || (!dfeat_cm && !dcen_cm)) return 0;
+    if (!dx) return fail_arg("pn2_sa_rows_bwd", "null pointer");
+    SaBwdArgs a;
+    a.b = b; a.n = n; a.s = s; a.k = k; a.idx = idx; a.dx = (const bf16*)dx; a.dx_ld = dx_ld;
+    a.feat_c = feat_c; a.dfeat_cm = dfeat_cm; a.cen_c = cen_c; a.dcen_cm = dcen_cm; a.xyz_first = xyz_first;
+    sa_rows_bwd_kernel<<<warp_blocks((long long)b * s * k), kThreads, 0, (cudaStream_t)stream>>>(a);
+    PN2_CHECK_LAUNCH("sa_rows_bwd_kernel");
+    return 0;
+}
+
+extern "C" int pn2_fp_rows_bwd(int b, int n, int s, const int* idx, const float* dist2, const void* dx, int dx_ld,
+                               int skip_c, float* dskip_cm, int coarse_c, float* dcoarse_rows, pn2_stream_t stream) {
+    if (b < 0 || n <= 0 || s <= 0) return fail_arg("pn2_fp_rows_bwd", "bad size");
+    if (b == 0 || (!dskip_cm && !dcoarse_rows)) return 0;
+    if (!dx || (s > 1 && dcoarse_rows && (!idx || !dist2))) return fail_arg("pn2_fp_rows_bwd", "null pointer");
+    FpBwdArgs a;
+    a.b = b; a.n = n; a.s = s; a.idx = idx; a.dist2 = dist2; a.dx = (const bf16*)dx; a.dx_ld = dx_ld;
+    a.skip_c = skip_c; a.dskip_cm = dskip_cm; a.coarse_c = coarse_c; a.dcoarse_rows = dcoarse_rows;
+    fp_rows_bwd_kernel<<<warp_blocks((long long)b * n), kThreads, 0, (cudaStream_t)stream>>>(a);
+    PN2_CHECK_LAUNCH("fp_rows_bwd_kernel");
+    return 0;
+}

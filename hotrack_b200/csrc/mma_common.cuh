@@ -1,0 +1,53 @@
+// mma_common.cuh -- bf16 tensor-core building blocks shared by the grouped-MLP kernels.
+//
+// The grouped per-point MLP of PointNet++ (reference pointnet_utils.py:399-403: conv1x1 -> BN -> ReLU
+// per layer, each a separate cuDNN/elementwise launch materialising a (B,C,S,K) fp32 tensor) is
+// restated as GEMMs over "row matrices": one row per (cloud, centre, neighbour) or (cloud, point),
+// channels contiguous, bf16 storage, fp32 accumulation.  Operand tiles are staged in shared
+// memory; fragments come from ldmatrix and feed mma.sync.m16n8k16 (bf16 x bf16 -> fp32).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// 16-byte async copy global -> shared; src_bytes == 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
+    // bf16 -> fp32 is a 16-bit shift: low half = element 0, high half = element 1
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_to_f(bf16 v) { return __bfloat162float(v); }
+
+}  // namespace pn2

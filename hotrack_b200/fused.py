@@ -1,0 +1,396 @@
+"""The "fused" engine: the grouped per-point MLP of the SA / FP modules on bf16 tensor-core kernels.
+
+Host side of include/pn2b200_mlp.h.  One ``autograd.Function`` (``_MlpStack``) runs a whole
+  build rows (gather / interpolate / concat)  ->  [GEMM + BatchNorm statistics] x L  ->  BN+ReLU(+max-pool)
+stack and its backward; ``sa_scale`` / ``sa_group_all`` / ``fp_layer`` / ``dense_stack`` are the
+entry points ``pointnet_utils.py`` / ``backbones.py`` call when the engine is "fused".  They take
+and return the reference's tensor layouts (channel-major fp32), so the modules stay drop-in; the
+bf16 row form of every output is additionally attached to the returned tensor (``_pn2_rows``) and
+picked up by the next fused consumer, which then never touches the fp32 copy.
+
+What replaces what (reference network/models/pointnet_utils.py):
+  :389-403  group_operation x2, "-= centre", cat, 3 x relu(bn(conv)), max   -> sa_scale
+  :484-512  sample_and_group_all, 3 x relu(bn(conv)), max                    -> sa_group_all
+  :443-463  three_nn, weights, three_interpolate, cat, L x relu(bn(conv))    -> fp_layer
+  backbones.py:131-132  relu(bn1(conv1(x)))                                  -> dense_stack
+BatchNorm semantics are nn.BatchNorm's: batch statistics (biased variance) in training with the
+running-statistics update (momentum, unbiased variance, num_batches_tracked), running statistics
+in eval.  Training-mode conv biases cancel in BatchNorm: they only enter the running mean, and
+their gradient is exactly zero.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from . import pointnet2_cuda as pc
+
+_BF16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
+class Rows:
+    """bf16 row matrix [rows][ld] with c valid channels; scale/shift (fp32, length >= c) mean the
+    consumer must read relu(y*scale + shift) -- the producer's BatchNorm+ReLU applied on the fly."""
+
+    __slots__ = ("y", "c", "ld", "scale", "shift", "numel", "version")
+
+    def __init__(self, y, c, ld, scale=None, shift=None):
+        self.y, self.c, self.ld, self.scale, self.shift = y, c, ld, scale, shift
+        self.numel = self.version = None
+
+
+def attach_rows(t, rows):
+    rows.numel, rows.version = t.numel(), t._version
+    t._pn2_rows = rows
+    return t
+
+
+def carry_rows(src, dst):
+    """Propagate the attached row form across a reshape/view of the same values."""
+    r = getattr(src, "_pn2_rows", None)
+    if r is not None and dst.numel() == r.numel:
+        dst._pn2_rows = r
+    return dst
+
+
+def rows_of(t):
+    """Row source of a (B,C,N) fp32 tensor: the attached one if still valid, else a conversion."""
+    r = getattr(t, "_pn2_rows", None)
+    if r is not None and r.numel == t.numel() and r.version == t._version:
+        return r
+    B, C, N = t.shape
+    t = t.contiguous()
+    if t.dtype != torch.float32:
+        raise TypeError("fused engine expects fp32 feature tensors")
+    ld = (C + 7) // 8 * 8
+    y = torch.empty(B * N, ld, dtype=_BF16, device=t.device)
+    _lib.call("pn2_to_rows", B, C, N, t.data_ptr(), y.data_ptr(), ld, _stream())
+    return Rows(y, C, ld)
+
+
+class _Layer:
+    __slots__ = ("w", "wt", "cin", "kp", "cout", "y", "scale", "shift", "mean", "rstd")
+
+
+def _bn_momentum(bn):
+    return 0.1 if bn.momentum is None else float(bn.momentum)
+
+
+class _MlpStack(Function):
+    """kind 'sa'    : meta = (xyz (B,3,N), new_xyz (B,3,S)|None, idx (B,S,K) int32|None, xyz_first)
+                      a = features (B,D,N)|None, b = centre features (B,E,S)|None   -> (B,Cout,S)
+       kind 'fp'    : meta = (idx (B,N,3) int32|None, dist2 (B,N,3)|None, N, S)
+                      a = skip (B,D1,N)|None, b = coarse (B,D2,S)                    -> (B,Cout,N)
+       kind 'dense' : a = x (B,C,N)                                                  -> (B,Cout,N)"""
+
+    @staticmethod
+    def forward(ctx, kind, meta, bns, training, a, b, *params):
+        dev = params[0].device
+        st = _stream()
+        nl = len(params) // 4
+        ra = rows_of(a) if a is not None else None
+        rb = rows_of(b) if b is not None else None
+
+        # ---- layer-0 input rows
+        if kind == "sa":
+            xyz, new_xyz, idx, xyz_first = meta
+            B, _, N = xyz.shape
+            if idx is not None:
+                S, K = idx.shape[1], idx.shape[2]
+            else:
+                S, K = 1, N
+            fc = ra.c if ra is not None else 0
+            cc = rb.c if rb is not None else 0
+            cin = fc + 3 + cc
+            R, groups, pool_k = B * S * K, S, K
+            x0 = torch.empty(R, _pad32(cin), dtype=_BF16, device=dev)
+            _lib.call("pn2_sa_build_rows", B, N, S, K, xyz.data_ptr(), _p(new_xyz), _p(idx),
+                      _p(ra.y) if ra else 0, fc, ra.ld if ra else 0, _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0,
+                      _p(rb.y) if rb else 0, cc, rb.ld if rb else 0, _p(rb.scale) if rb else 0, _p(rb.shift) if rb else 0,
+                      1 if xyz_first else 0, x0.data_ptr(), x0.shape[1], st)
+        elif kind == "fp":
+            idx, dist2, N, S = meta
+            B = b.shape[0]
+            sc = ra.c if ra is not None else 0
+            cin = sc + rb.c
+            R, groups, pool_k = B * N, N, 1
+            x0 = torch.empty(R, _pad32(cin), dtype=_BF16, device=dev)
+            _lib.call("pn2_fp_build_rows", B, N, S, _p(ra.y) if ra else 0, sc, ra.ld if ra else 0,
+                      _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0, rb.y.data_ptr(), rb.c, rb.ld, _p(rb.scale),
+                      _p(rb.shift), _p(idx), _p(dist2), x0.data_ptr(), x0.shape[1], st)
+        else:
+            B, cin, N = a.shape
+            R, groups, pool_k = B * N, N, 1
+            x0 = None  # the dense stack reads its input rows in place
+
+        # ---- L x (GEMM + batch statistics)
+        layers = []
+        if x0 is not None:
+            x, x_ld, xs, xh, kp = x0, x0.shape[1], None, None, x0.shape[1]
+        else:
+            if ra.ld % 32 == 0:
+                x, x_ld, xs, xh, kp = ra.y, ra.ld, ra.scale, ra.shift, ra.ld
+            else:  # re-pad the row form to the GEMM's 32-column granularity
+                kp = _pad32(ra.c)
+                x = torch.zeros(R, kp, dtype=_BF16, device=dev)
+                x[:, :ra.c] = ra.y[:, :ra.c]
+                x_ld, xs, xh = kp, ra.scale, ra.shift
+            if xs is not None and xs.numel() < kp:
+                xs = torch.cat([xs, xs.new_zeros(kp - xs.numel())])
+                xh = torch.cat([xh, xh.new_zeros(kp - xh.numel())])
+        in0 = (x, x_ld, xs, xh)
+        for l in range(nl):
+            w, bias, gamma, beta = params[4 * l: 4 * l + 4]
+            bn = bns[l]
+            L = _Layer()
+            L.cout, L.cin, L.kp = w.shape[0], w.shape[1], kp
+            if L.cout % 32:
+                raise ValueError("fused engine needs layer widths that are multiples of 32 (got %d)" % L.cout)
+            L.w = torch.empty(L.cout, kp, dtype=_BF16, device=dev)
+            L.wt = torch.empty(kp, L.cout, dtype=_BF16, device=dev) if training else None
+            _lib.call("pn2_mlp_prep_weights", L.cout, L.cin, kp, w.data_ptr(), L.w.data_ptr(), _p(L.wt), st)
+            L.y = torch.empty(R, L.cout, dtype=_BF16, device=dev)
+            consts = torch.empty(4, L.cout, dtype=torch.float32, device=dev)
+            L.scale, L.shift, L.mean, L.rstd = consts[0], consts[1], consts[2], consts[3]
+            if training:
+                stats = torch.zeros(2, L.cout, dtype=torch.float32, device=dev)
+                _lib.call("pn2_mlp_gemm_fwd", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
+                          L.y.data_ptr(), L.cout, stats.data_ptr(), st)
+                track = bn.track_running_stats and bn.running_mean is not None
+                _lib.call("pn2_bn_finalize", L.cout, R, stats.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                          _p(bias), _bn_momentum(bn), float(bn.eps), _p(bn.running_mean) if track else 0,
+                          _p(bn.running_var) if track else 0, _p(bn.num_batches_tracked) if track else 0,
+                          L.scale.data_ptr(), L.shift.data_ptr(), L.mean.data_ptr(), L.rstd.data_ptr(), st)
+            else:
+                _lib.call("pn2_bn_eval_affine", L.cout, bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias),
+                          bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps), L.scale.data_ptr(),
+                          L.shift.data_ptr(), st)
+                _lib.call("pn2_mlp_gemm_fwd", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
+                          L.y.data_ptr(), L.cout, 0, st)
+            layers.append(L)
+            x, x_ld, xs, xh, kp = L.y, L.cout, L.scale, L.shift, L.cout
+
+        # ---- BN + ReLU (+ max over the group) -> module output
+        last = layers[-1]
+        C = last.cout
+        out = torch.empty(B, C, groups, dtype=torch.float32, device=dev)
+        out_rows = argmax = None
+        if pool_k > 1:
+            out_rows = torch.empty(B * groups, C, dtype=_BF16, device=dev)
+            argmax = torch.empty(B, groups, C, dtype=torch.int32, device=dev) if training else None
+        _lib.call("pn2_pool_fwd", B, groups, pool_k, C, last.y.data_ptr(), C, last.scale.data_ptr(),
+                  last.shift.data_ptr(), out.data_ptr(), _p(out_rows), C, _p(argmax), st)
+        _MlpStack.last_rows = Rows(out_rows, C, C) if pool_k > 1 else Rows(last.y, C, C, last.scale, last.shift)
+
+        ctx.kind, ctx.meta, ctx.training = kind, meta, training
+        ctx.dims = (B, groups, pool_k, R, cin)
+        ctx.layers, ctx.in0, ctx.argmax = layers, in0, argmax
+        ctx.a_shape = None if a is None else tuple(a.shape)
+        ctx.b_shape = None if b is None else tuple(b.shape)
+        ctx.gammas = [params[4 * l + 2] for l in range(nl)]
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        nl = len(ctx.layers)
+        none_params = [None] * (4 * nl)
+        if dout is None:
+            return (None, None, None, None, None, None, *none_params)
+        if not ctx.training:
+            raise NotImplementedError("fused engine: backward through eval-mode BatchNorm is not implemented; "
+                                      "use engine 'ops' for that")
+        st = _stream()
+        dev = dout.device
+        B, groups, pool_k, R, cin = ctx.dims
+        layers = ctx.layers
+        dout = dout.contiguous().float()
+        last = layers[-1]
+        C = last.cout
+        dz = torch.empty(R, C, dtype=_BF16, device=dev)
+        sums = torch.zeros(2, C, dtype=torch.float32, device=dev)
+        _lib.call("pn2_pool_bwd", B, groups, pool_k, C, dout.data_ptr(), last.y.data_ptr(), C, last.scale.data_ptr(),
+                  last.shift.data_ptr(), last.mean.data_ptr(), last.rstd.data_ptr(), _p(ctx.argmax), dz.data_ptr(), C,
+                  sums.data_ptr(), st)
+        need_a = ctx.needs_input_grad[4] and ctx.a_shape is not None
+        need_b = ctx.needs_input_grad[5] and ctx.b_shape is not None
+        grads = [None] * (4 * nl)
+        dx0 = None
+        for l in range(nl - 1, -1, -1):
+            L = layers[l]
+            coefs = torch.empty(5, L.cout, dtype=torch.float32, device=dev)
+            _lib.call("pn2_bn_bwd_coefs", L.cout, R, sums.data_ptr(), ctx.gammas[l].data_ptr(), L.mean.data_ptr(),
+                      L.rstd.data_ptr(), coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(),
+                      coefs[3].data_ptr(), coefs[4].data_ptr(), st)
+            if l > 0:
+                P = layers[l - 1]
+                x, x_ld, xs, xh = P.y, P.cout, P.scale, P.shift
+            else:
+                x, x_ld, xs, xh = ctx.in0
+            dw = torch.zeros(L.cout, L.cin, dtype=torch.float32, device=dev)
+            _lib.call("pn2_mlp_gemm_wgrad", R, L.cout, L.kp, L.cin, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
+                      coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), x.data_ptr(), x_ld, _p(xs), _p(xh),
+                      dw.data_ptr(), L.cin, st)
+            grads[4 * l] = dw
+            grads[4 * l + 1] = torch.zeros(L.cout, dtype=torch.float32, device=dev)  # bias: cancelled by BN
+            grads[4 * l + 2] = coefs[3]
+            grads[4 * l + 3] = coefs[4]
+            if l > 0:
+                P = layers[l - 1]
+                dzp = torch.empty(R, P.cout, dtype=_BF16, device=dev)
+                sums_p = torch.zeros(2, P.cout, dtype=torch.float32, device=dev)
+                _lib.call("pn2_mlp_gemm_dgrad", R, L.cout, P.cout, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
+                          coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), L.wt.data_ptr(),
+                          P.y.data_ptr(), P.cout, P.scale.data_ptr(), P.shift.data_ptr(), P.mean.data_ptr(),
+                          P.rstd.data_ptr(), dzp.data_ptr(), P.cout, sums_p.data_ptr(), st)
+                dz, sums = dzp, sums_p
+            elif need_a or need_b:
+                # gradient w.r.t. the VALUES the stack consumed (post-activation when the input rows were
+                # still pre-BatchNorm: the producer's own backward applies its ReLU mask)
+                dx0 = torch.empty(R, L.kp, dtype=_BF16, device=dev)
+                _lib.call("pn2_mlp_gemm_dgrad", R, L.cout, L.kp, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
+                          coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), L.wt.data_ptr(), 0, 0, 0, 0, 0,
+                          0, dx0.data_ptr(), L.kp, 0, st)
+        # weight grads come back in the conv weight's own shape
+        da = db = None
+        if dx0 is not None:
+            if ctx.kind == "sa":
+                xyz, new_xyz, idx, xyz_first = ctx.meta
+                N = xyz.shape[2]
+                S, K = (idx.shape[1], idx.shape[2]) if idx is not None else (1, N)
+                fc = ctx.a_shape[1] if ctx.a_shape is not None else 0
+                cc = ctx.b_shape[1] if ctx.b_shape is not None else 0
+                if need_a:
+                    da = torch.zeros(ctx.a_shape, dtype=torch.float32, device=dev)
+                if need_b:
+                    db = torch.zeros(ctx.b_shape, dtype=torch.float32, device=dev)
+                _lib.call("pn2_sa_rows_bwd", B, N, S, K, _p(idx), dx0.data_ptr(), dx0.shape[1], fc, _p(da), cc, _p(db),
+                          1 if xyz_first else 0, st)
+            elif ctx.kind == "fp":
+                idx, dist2, N, S = ctx.meta
+                sc = ctx.a_shape[1] if ctx.a_shape is not None else 0
+                c2 = ctx.b_shape[1]
+                if need_a:
+                    da = torch.empty(ctx.a_shape, dtype=torch.float32, device=dev)
+                dcr = torch.zeros(B * S, c2, dtype=torch.float32, device=dev) if need_b else None
+                _lib.call("pn2_fp_rows_bwd", B, N, S, _p(idx), _p(dist2), dx0.data_ptr(), dx0.shape[1], sc, _p(da), c2,
+                          _p(dcr), st)
+                if need_b:
+                    db = dcr.view(B, S, c2).transpose(1, 2).contiguous()
+            else:
+                Bc, Cc, Nc = ctx.a_shape
+                da = dx0.view(Bc, Nc, -1)[:, :, :Cc].transpose(1, 2).float().contiguous()
+        return (None, None, None, None, da, db, *grads)
+
+
+def _params(convs, bns):
+    ps = []
+    for conv, bn in zip(convs, bns):
+        if conv.bias is None or bn.weight is None:
+            raise ValueError("fused engine expects Conv(bias=True) + affine BatchNorm, as the reference builds them")
+        ps += [conv.weight, conv.bias, bn.weight, bn.bias]
+    return ps
+
+
+def _check_cuda(t):
+    if not t.is_cuda:
+        raise ValueError("hotrack_b200 has no CPU path")
+
+
+def _run(kind, meta, convs, bns, training, a, b):
+    ps = _params(convs, bns)
+    views = []
+    for i, p in enumerate(ps):
+        views.append(p.view(p.shape[0], -1) if i % 4 == 0 else p)  # conv weight (Cout,Cin,1[,1]) -> (Cout,Cin)
+    out = _MlpStack.apply(kind, meta, list(bns), bool(training), a, b, *views)
+    rows, _MlpStack.last_rows = _MlpStack.last_rows, None  # set by forward (single-threaded hand-over)
+    return attach_rows(out, rows) if rows is not None else out
+
+
+_MlpStack.last_rows = None
+
+
+def sa_scale(xyz, points, new_xyz, idx, centre_feat, convs, bns, training):
+    """One SA scale.  xyz (B,3,N), points (B,D,N)|None, new_xyz (B,3,S), idx (B,S,K) int32,
+    centre_feat (B,E,S)|None -> (B,Cout,S)."""
+    _check_cuda(xyz)
+    if points is not None and points.shape[1] == 0:
+        points = None
+    meta = (xyz.contiguous().float(), new_xyz.contiguous().float(), idx.contiguous().int(), False)
+    return _run("sa", meta, convs, bns, training, points, centre_feat)
+
+
+def sa_group_all(xyz, points, convs, bns, training):
+    """Group-all SA.  xyz (B,3,N), points (B,D,N)|None -> (B,Cout,1); channel order [xyz, points]."""
+    _check_cuda(xyz)
+    meta = (xyz.contiguous().float(), None, None, True)
+    return _run("sa", meta, convs, bns, training, points, None)
+
+
+def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1):
+    """FP layer.  xyz1_t (B,N,3), xyz2_t (B,S,3), points1 (B*reps,D1,N)|None, points2 (B*reps,D2,S) -> (B*reps,Cout,N)."""
+    _check_cuda(points2)
+    B, N, _ = xyz1_t.shape
+    S = xyz2_t.shape[1]
+    idx = dist2 = None
+    if S > 1:
+        u, k = xyz1_t.contiguous().float(), xyz2_t.contiguous().float()
+        dist2 = torch.empty(B, N, 3, dtype=torch.float32, device=u.device)
+        idx = torch.empty(B, N, 3, dtype=torch.int32, device=u.device)
+        pc.three_nn_wrapper(B, N, S, u, k, dist2, idx)
+        if reps > 1:
+            dist2, idx = dist2.repeat_interleave(reps, dim=0), idx.repeat_interleave(reps, dim=0)
+    return _run("fp", (idx, dist2, N, S), convs, bns, training, points1, points2)
+
+
+def dense_stack(x, convs, bns, training):
+    """relu(bn(conv1x1(x))) stack on (B,C,N) -> (B,Cout,N)."""
+    _check_cuda(x)
+    return _run("dense", None, convs, bns, training, x, None)
+
+
+def alg_bytes(name, a):
+    """Algorithmic bytes of one C-ABI call of the fused kernels (bench.py's roofline line)."""
+    if name == "pn2_mlp_gemm_fwd":
+        rows, kdim, n = a[:3]
+        return rows * (kdim + n) * 2 + n * kdim * 2
+    if name == "pn2_mlp_gemm_dgrad":
+        rows, n_red, k_out = a[:3]
+        masked = a[11] != 0
+        return rows * (2 * n_red + k_out + (k_out if masked else 0)) * 2 + n_red * k_out * 2
+    if name == "pn2_mlp_gemm_wgrad":
+        rows, n, kp = a[:3]
+        return rows * (2 * n + kp) * 2 + n * kp * 4
+    if name == "pn2_pool_fwd":
+        b, s, k, c = a[:4]
+        return b * s * k * c * 2 + b * s * c * 4 + (b * s * c * 6 if k > 1 else 0)
+    if name == "pn2_pool_bwd":
+        b, s, k, c = a[:4]
+        return b * s * c * 4 + b * s * k * c * 2 + (b * s * c * (4 + 2) if k > 1 else b * s * c * 2)
+    if name == "pn2_sa_build_rows":
+        b, n, s, k = a[:4]
+        return b * s * k * (a[19] * 2 + 4) + b * s * k * 2 * (a[8] + a[13])
+    if name == "pn2_fp_build_rows":
+        b, n, s = a[:3]
+        return b * n * (a[17] * 2 + 24 + 2 * a[4]) + b * s * a[9] * 2
+    if name == "pn2_sa_rows_bwd":
+        b, n, s, k = a[:4]
+        return b * s * k * (a[6] * 2 + 4)
+    if name == "pn2_fp_rows_bwd":
+        b, n, s = a[:3]
+        return b * n * (a[6] * 2 + 24)
+    if name == "pn2_to_rows":
+        b, c, n = a[:3]
+        return b * c * n * 4 + b * n * a[5] * 2
+    return None

@@ -105,6 +105,14 @@ def sample_and_group_all(xyz, points):
     return new_xyz, grouped
 
 
+def _carry(src, dst):
+    """Keep the fused engine's bf16 row form (if any) attached across a reshape of the same values."""
+    r = getattr(src, "_pn2_rows", None)
+    if r is not None and dst.numel() == r.numel:
+        dst._pn2_rows = r
+    return dst
+
+
 # ------------------------------------------------------------------ building blocks -----------
 def _make_stack(in_channel, widths, conv_cls, bn_cls):
     convs, bns = nn.ModuleList(), nn.ModuleList()
@@ -206,14 +214,14 @@ class PointNetSetAbstractionMsg_fast(_MsgBase):
         new_xyz_t = new_xyz.transpose(1, 2).contiguous()
         feats = None
         if points is not None and points.shape[-2] > 0:
-            feats = points.reshape(B * P, -1, N)
+            feats = _carry(points, points.reshape(B * P, -1, N))
         rep = (lambda t: t) if P == 1 else (lambda t: t.repeat_interleave(P, dim=0))
         outs = []
         for i, radius in enumerate(self.radius_list):
             idx = _neighbour_idx(self.knn, radius, self.nsample_list[i], xyz_t, new_xyz_t)
             outs.append(self._scale(i, rep(xyz0), feats, rep(new_xyz), rep(idx)))
-        out = torch.cat(outs, dim=1).reshape(B, P, -1, S)
-        return new_xyz.unsqueeze(1).expand(B, P, C, S), out
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+        return new_xyz.unsqueeze(1).expand(B, P, C, S), _carry(out, out.reshape(B, P, -1, S))
 
 
 class PointNetSetAbstractionMsg_GivenCenterPoints(_MsgBase):
@@ -288,11 +296,11 @@ class PointNetSetAbstraction_fast(_GroupAllBase):
 
     def forward(self, xyz, points):
         B, P, C, N = xyz.shape
-        feats = points.reshape(B * P, -1, N) if points is not None else None
+        feats = _carry(points, points.reshape(B * P, -1, N)) if points is not None else None
         if feats is not None and feats.shape[1] == 0:
             feats = None
         out = self._pool_all(xyz.reshape(B * P, C, N), feats)
-        return torch.zeros(B, P, C, 1, device=xyz.device, dtype=xyz.dtype), out.reshape(B, P, -1, 1)
+        return torch.zeros(B, P, C, 1, device=xyz.device, dtype=xyz.dtype), _carry(out, out.reshape(B, P, -1, 1))
 
 
 class _FpBase(nn.Module, _EngineMixin):
@@ -343,7 +351,7 @@ class PointNetFeaturePropagation_fast(_FpBase):
     def forward(self, xyz1, xyz2, points1, points2):
         B, P, _, N = xyz1.shape
         S = xyz2.shape[-1]
-        p1 = points1.reshape(B * P, -1, N) if points1 is not None else None
+        p1 = _carry(points1, points1.reshape(B * P, -1, N)) if points1 is not None else None
         out = self._propagate(xyz1[:, 0].transpose(1, 2), xyz2[:, 0].transpose(1, 2), p1,
-                              points2.reshape(B * P, -1, S), reps=P)
-        return out.reshape(B, P, -1, N)
+                              _carry(points2, points2.reshape(B * P, -1, S)), reps=P)
+        return _carry(out, out.reshape(B, P, -1, N))

@@ -1,0 +1,106 @@
+/*
+ * pn2b200_mlp.h -- C ABI of the fused grouped-MLP kernels of libpn2b200.so.
+ *
+ * These entry points have no C counterpart in the reference: there the per-point MLP of the SA / FP
+ * modules is torch.nn (Conv2d/Conv1d + BatchNorm + ReLU + max: network/models/pointnet_utils.py:
+ * 389-403, 443-463, 484-512, 536-590; backbones.py:131-132).  They are what a Python binding of the
+ * fused "engine" calls (hotrack_b200/fused.py); conventions as in pn2b200.h: raw device pointers, int
+ * sizes, caller-owned buffers, asynchronous on `stream`, int status (0 = ok, see pn2_last_error()).
+ *
+ * ROW MATRICES: activations are bf16 matrices X[rows][ld], channels contiguous (ld % 8 == 0,
+ * 16-byte aligned base), rows = B*S*K grouped neighbours or B*N points.  A "row source" is such a
+ * matrix plus optional per-channel fp32 scale/shift: when given, the consumer reads
+ * relu(x*scale + shift) -- i.e. the producer's BatchNorm + ReLU, applied on the fly.
+ */
+#ifndef PN2B200_MLP_H_
+#define PN2B200_MLP_H_
+#include "pn2b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* (B,C,N) fp32 channel-major -> rows [B*N][ld] bf16, columns >= C zero-filled. */
+int pn2_to_rows(int b, int c, int n, const float* src, void* dst, int ld, pn2_stream_t stream);
+
+/* Grouped rows of one SA scale (pointnet_utils.py:389-396, 570-575; group-all :170-186).
+ * Row (b,s,k), point j = idx[b,s,k] (idx NULL: j = k, k == n):
+ *   xyz_first == 0: [ feat[b,j,0..feat_c) | xyz[b,:,j] - new_xyz[b,:,s] | cen[b,s,0..cen_c) | 0.. ]
+ *   xyz_first == 1: [ xyz - centre | feat | 0.. ]          (new_xyz NULL: centre = 0)
+ * feat / cen: row sources over (B*N) / (B*S) rows, NULL = absent. */
+int pn2_sa_build_rows(int b, int n, int s, int k, const float* xyz, const float* new_xyz, const int* idx,
+                      const void* feat, int feat_c, int feat_ld, const float* feat_scale, const float* feat_shift,
+                      const void* cen, int cen_c, int cen_ld, const float* cen_scale, const float* cen_shift,
+                      int xyz_first, void* out, int out_ld, pn2_stream_t stream);
+
+/* Rows of one FP layer (pointnet_utils.py:443-456): [ skip[b,i,:] | sum_j w_j * coarse[b, idx[b,i,j], :] | 0.. ]
+ * with w from the three_nn squared distances (w_j = 1/(sqrt(d2_j)+1e-8), normalised); s == 1 broadcasts. */
+int pn2_fp_build_rows(int b, int n, int s, const void* skip, int skip_c, int skip_ld, const float* skip_scale,
+                      const float* skip_shift, const void* coarse, int coarse_c, int coarse_ld,
+                      const float* coarse_scale, const float* coarse_shift, const int* idx, const float* dist2,
+                      void* out, int out_ld, pn2_stream_t stream);
+
+/* y[rows][n] = act(x)[rows][kdim] * w[n][kdim]^T  (bf16 in, fp32 accumulate, bf16 out), act = relu(x*scale+shift)
+ * when in_scale != NULL.  stats != NULL: stats[0..n) += column sums of y, stats[n..2n) += sums of y^2 (zeroed by
+ * the caller) -- the BatchNorm batch statistics.  kdim % 32 == 0, n % 8 == 0. */
+int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
+                     const float* in_shift, const void* w, void* y, int y_ld, float* stats, pn2_stream_t stream);
+
+/* Training-mode BatchNorm constants from the statistics: scale = gamma*rstd, shift = beta - mean*scale, plus
+ * the running-statistics update of nn.BatchNorm (momentum, unbiased variance; conv_bias re-added to the mean
+ * because the GEMM omits the bias BatchNorm cancels).  running_* / num_batches_tracked may be NULL. */
+int pn2_bn_finalize(int n, long long rows, const float* sums, const float* gamma, const float* beta,
+                    const float* conv_bias, float momentum, float eps, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
+                    pn2_stream_t stream);
+/* Eval-mode constants from the running statistics (conv bias folded in). */
+int pn2_bn_eval_affine(int n, const float* gamma, const float* beta, const float* conv_bias,
+                       const float* running_mean, const float* running_var, float eps, float* scale, float* shift,
+                       pn2_stream_t stream);
+
+/* BatchNorm+ReLU of the last layer and max over the k rows of each group: out_cm (B,C,S) fp32, optional bf16
+ * rows (B*S, out_ld) and arg-max (B,S,C).  k == 1: plain BN+ReLU, rows -> channel-major (FP layers, head). */
+int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld, const float* scale, const float* shift,
+                 float* out_cm, void* out_rows, int out_ld, int* argmax, pn2_stream_t stream);
+
+/* Backward of pool_fwd: dz[rows][c] = dout at the arg-max row where the ReLU is active, else 0; sums[0..c) +=
+ * sum(dz), sums[c..2c) += sum(dz * xhat)  (zeroed by the caller). */
+int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const void* y, int y_ld, const float* scale,
+                 const float* shift, const float* mean, const float* rstd, const int* argmax, void* dz, int dz_ld,
+                 float* sums, pn2_stream_t stream);
+
+/* BatchNorm-backward per-channel coefficients: dY = cA*dz + cB*y + cC; dgamma = sums[c..2c), dbeta = sums[0..c). */
+int pn2_bn_bwd_coefs(int n, long long rows, const float* sums, const float* gamma, const float* mean,
+                     const float* rstd, float* cA, float* cB, float* cC, float* dgamma, float* dbeta,
+                     pn2_stream_t stream);
+
+/* dz_prev[rows][k_out] = dY[rows][n_red] * wt[k_out][n_red]^T with dY = cA*dz + cB*y + cC.  y_prev != NULL:
+ * the result is masked by the previous layer's ReLU (y_prev*prev_scale+prev_shift > 0) and sums_prev receives
+ * the two BatchNorm-backward sums of the previous layer.  y_prev == NULL: plain input gradient. */
+int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const void* dz, int dz_ld, const void* y, int y_ld,
+                       const float* cA, const float* cB, const float* cC, const void* wt, const void* y_prev,
+                       int y_prev_ld, const float* prev_scale, const float* prev_shift, const float* prev_mean,
+                       const float* prev_rstd, void* dz_prev, int dz_prev_ld, float* sums_prev, pn2_stream_t stream);
+
+/* dw[n][k_true] += sum_rows dY[r][n] * act(x)[r][k]  (fp32 atomics into the caller's zeroed buffer). */
+int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, const void* dz, int dz_ld, const void* y, int y_ld,
+                       const float* cA, const float* cB, const float* cC, const void* x, int x_ld,
+                       const float* in_scale, const float* in_shift, float* dw, int dw_ld, pn2_stream_t stream);
+
+/* fp32 conv weight [n][k_true] -> bf16 [n][kp] (zero padded) and, if wt != NULL, its transpose [kp][n]. */
+int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_bf16, void* wt_bf16, pn2_stream_t stream);
+
+/* Gradient of sa_build_rows' output rows scattered to the feature tensors (channel-major fp32, zeroed by the
+ * caller, atomics): dfeat_cm (B,feat_c,N), dcen_cm (B,cen_c,S); either may be NULL. */
+int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const void* dx, int dx_ld, int feat_c,
+                    float* dfeat_cm, int cen_c, float* dcen_cm, int xyz_first, pn2_stream_t stream);
+
+/* Gradient of fp_build_rows' output rows: dskip_cm (B,skip_c,N) plain stores; dcoarse_rows (B*S, coarse_c) fp32
+ * rows, zeroed by the caller, atomics; either may be NULL. */
+int pn2_fp_rows_bwd(int b, int n, int s, const int* idx, const float* dist2, const void* dx, int dx_ld, int skip_c,
+                    float* dskip_cm, int coarse_c, float* dcoarse_rows, pn2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN2B200_MLP_H_ */

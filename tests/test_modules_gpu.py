@@ -84,8 +84,10 @@ def test_config2_path_forward_backward_matches_reference(ref, cuda, train):
         assert n1 == n2
         if p2.grad is None:
             continue
-        scale = p2.grad.abs().max().item()
-        if scale < 1e-12:  # conv biases under train-mode BN: gradient is rounding noise around 0
+        if n1.endswith(".bias") and ("conv" in n1):
+            # a conv bias in front of train-mode BatchNorm has an exactly-zero gradient in real
+            # arithmetic; what both implementations return is fp32 rounding noise around 0
+            assert p1.grad.abs().max().item() < 1e-3
             continue
         assert _rel(p1.grad, p2.grad) < 1e-3, "%s grad rel %.3g" % (n1, _rel(p1.grad, p2.grad))
     # BatchNorm running statistics advanced identically
