@@ -33,13 +33,14 @@ SIGNATURES = {
     "pn2_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
     "pn2_adam_step": [ctypes.c_longlong, _p, _p, _p, _p, _f, _f, _f, _f, _f, _i, _f, _p],
     # include/pn2b200_mlp.h
-    "pn2_to_rows": [_i, _i, _i, _p, _p, _i, _p],
+    "pn2_to_rows": [_i, _i, _i, _p, _p, _f, _p, _i, _p],
     "pn2_sa_build_rows": [_i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p],
     "pn2_fp_build_rows": [_i, _i, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p],
-    "pn2_mlp_gemm_fwd": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p],
-    "pn2_bn_finalize": [_i, _ll, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
-    "pn2_bn_eval_affine": [_i, _p, _p, _p, _p, _p, _f, _p, _p, _p],
-    "pn2_pool_fwd": [_i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p],
+    "pn2_mlp_center": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p],
+    "pn2_mlp_gemm_fwd": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p],
+    "pn2_bn_finalize": [_i, _ll, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "pn2_bn_eval_affine": [_i, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p],
+    "pn2_pool_fwd": [_i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p],
     "pn2_pool_bwd": [_i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p],
     "pn2_bn_bwd_coefs": [_i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "pn2_mlp_gemm_dgrad": [_ll, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p],

@@ -1,4 +1,4 @@
-// mlp_gemm.cu -- the grouped per-point MLP as bf16 tensor-core GEMMs over row matrices, sm_100a.
+// mlp_gemm.cu -- the grouped per-point MLP as 16-bit tensor-core GEMMs over row matrices, sm_100a.
 //
 // Replaces the per-layer  relu(bn(conv1x1(x)))  chain of the reference's SA / FP modules
 // (network/models/pointnet_utils.py:399-403,458-460,505-507,577-580; backbones.py:131-132), which
@@ -6,7 +6,7 @@
 // (B,C,S,K) fp32 tensor, and 5+ more launches per layer in backward.
 //
 // Layout: activations are ROW matrices  X[R][C]  (R = B*S*K grouped rows or B*N points; channels
-// contiguous; bf16; leading dimension a multiple of 8).  Only the PRE-BatchNorm conv output Y_l of each
+// contiguous; 16-bit: fp16 forward, bf16 gradients -- see mma_common.cuh; leading dimension a multiple of 8).  Only the PRE-BatchNorm conv output Y_l of each
 // layer is ever stored; BatchNorm + ReLU are applied by the CONSUMER while it stages its A operand
 // ("prologue"), and the batch statistics BatchNorm needs are column sums produced by the PRODUCER's
 // epilogue.  Per layer that is one read of Y_{l-1} and one write of Y_l (2 B/element each) instead
@@ -21,6 +21,12 @@
 //      sum(v), sum(v*xhat_prev)  -- the two reductions BatchNorm-backward of the previous layer needs.
 //   wgrad_kernel<AFFINE>                   dW[n][k] += sum_r dY[r][n] * X'[r][k]   (split over rows,
 //      transposed ldmatrix fragments, fp32 atomics into the zeroed gradient).
+//
+// Centering: a pre-BatchNorm channel can have |mean| >> std (e.g. FP3, whose input is dominated by
+// the broadcast global feature), and bf16 rounding of such values destroys what BatchNorm keeps.
+// The forward GEMM therefore stores  y - c[n]  with c an estimate of the channel mean (center_kernel:
+// W * mean of a few sampled input rows); BatchNorm is shift-invariant, so only the running mean and
+// the eval-mode shift need c added back (bn_finalize / bn_eval_affine).
 //
 // Machine mapping: persistent CTAs (<= 2 per SM) walk 128-row tiles; A is register-prefetched one
 // chunk ahead (so the prologue runs once per element, not once per consuming warp), B (weights,
@@ -40,13 +46,14 @@ enum { A_PLAIN = 0, A_AFFINE = 1, A_BNBWD = 2 };
 struct GemmArgs {
     long long rows;
     int kdim, n;
-    const bf16* a0; int a0_ld;
-    const bf16* a1; int a1_ld;
+    const uint16_t* a0; int a0_ld;   // forward: x (fp16);  BNBWD: dz (bf16)
+    const uint16_t* a1; int a1_ld;   // BNBWD: y (fp16)
     const float *c0, *c1, *c2;
-    const bf16* b;
-    bf16* out; int out_ld;
+    const uint16_t* b;               // forward: w (fp16);  BNBWD: wt (bf16)
+    const float* center;  // [n] subtracted from the accumulators before bf16 rounding (nullable)
+    uint16_t* out; int out_ld;       // forward: y (fp16);  BNBWD: dz_prev (bf16)
     float* sums;
-    const bf16* yp; int yp_ld;
+    const uint16_t* yp; int yp_ld;   // MASK: previous layer's y (fp16)
     const float *p_scale, *p_shift, *p_mean, *p_rstd;
 };
 
@@ -60,13 +67,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
     constexpr int RPP = kThreads / CPR;
     constexpr int PASSES = BM / RPP;
     constexpr int NCOEF = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
+    constexpr bool FWD = AMODE != A_BNBWD;  // forward GEMMs compute and store fp16, backward ones bf16
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    bf16* sA = reinterpret_cast<bf16*>(smem_raw);
-    bf16* sB = sA + 2 * BM * LDS;
-    bf16* sC = sB + 2 * BN * LDS;
+    uint16_t* sA = reinterpret_cast<uint16_t*>(smem_raw);
+    uint16_t* sB = sA + 2 * BM * LDS;
+    uint16_t* sC = sB + 2 * BN * LDS;
     float* sCoef = reinterpret_cast<float*>(sC + BM * CLD);
     float* sPrev = sCoef + NCOEF * p.kdim;  // [4][BN], MASK only
+    float* sCen = sPrev + (MASK ? 4 * BN : 0);  // [BN]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WN, wn = warp % WN;
@@ -80,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
         const float* src = which == 0 ? p.c0 : (which == 1 ? p.c1 : p.c2);
         sCoef[i] = src[c];
     }
+    for (int i = tid; i < BN; i += kThreads) sCen[i] = (p.center && n0 + i < p.n) ? p.center[n0 + i] : 0.f;
     if (MASK) {
         for (int i = tid; i < 4 * BN; i += kThreads) {
             const int which = i / BN, c = n0 + (i - which * BN);
@@ -118,20 +128,17 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
                     uint32_t* o = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float2 a = bf2_to_f2(x0[e]);
                         const float2 k0 = *reinterpret_cast<const float2*>(&sCoef[c + 2 * e]);
                         const float2 k1 = *reinterpret_cast<const float2*>(&sCoef[p.kdim + c + 2 * e]);
-                        float r0, r1;
                         if (AMODE == A_AFFINE) {
-                            r0 = fmaxf(fmaf(a.x, k0.x, k1.x), 0.f);
-                            r1 = fmaxf(fmaf(a.y, k0.y, k1.y), 0.f);
+                            const float2 a = h2_to_f2(x0[e]);
+                            o[e] = f2_to_h2(fmaxf(fmaf(a.x, k0.x, k1.x), 0.f), fmaxf(fmaf(a.y, k0.y, k1.y), 0.f));
                         } else {
-                            const float2 y = bf2_to_f2(x1[e]);
+                            const float2 a = bf2_to_f2(x0[e]);
+                            const float2 y = h2_to_f2(x1[e]);
                             const float2 k2 = *reinterpret_cast<const float2*>(&sCoef[2 * p.kdim + c + 2 * e]);
-                            r0 = fmaf(k0.x, a.x, fmaf(k1.x, y.x, k2.x));
-                            r1 = fmaf(k0.y, a.y, fmaf(k1.y, y.y, k2.y));
+                            o[e] = f2_to_bf2(fmaf(k0.x, a.x, fmaf(k1.x, y.x, k2.x)), fmaf(k0.y, a.y, fmaf(k1.y, y.y, k2.y)));
                         }
-                        o[e] = f2_to_bf2(r0, r1);
                     }
                 }
             }
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
             const int r = i >> 2, ch = i & 3;
             const int nrow = n0 + r;
             const bool ok = nrow < p.n;
-            const bf16* src = p.b + (size_t)(ok ? nrow : 0) * p.kdim + kc * BK + ch * 8;
+            const uint16_t* src = p.b + (size_t)(ok ? nrow : 0) * p.kdim + kc * BK + ch * 8;
             cp_async16(&sB[(st * BN + r) * LDS + ch * 8], src, ok ? 16 : 0);
         }
         cp_async_commit();
@@ -194,8 +201,12 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
-                for (int nf = 0; nf < 4; ++nf)
-                    mma_bf16_16816(acc[mf][nf], af[mf], bfr[nf >> 1][(nf & 1) * 2], bfr[nf >> 1][(nf & 1) * 2 + 1]);
+                for (int nf = 0; nf < 4; ++nf) {
+                    if (FWD)
+                        mma_f16_16816(acc[mf][nf], af[mf], bfr[nf >> 1][(nf & 1) * 2], bfr[nf >> 1][(nf & 1) * 2 + 1]);
+                    else
+                        mma_bf16_16816(acc[mf][nf], af[mf], bfr[nf >> 1][(nf & 1) * 2], bfr[nf >> 1][(nf & 1) * 2 + 1]);
+                }
         }
         if (kc == KT - 1) {
             // ---- epilogue: fp32 accumulators -> bf16 tile in shared memory -> coalesced stores + column sums
@@ -204,8 +215,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
 #pragma unroll
                 for (int nf = 0; nf < 4; ++nf) {
                     const int r = wm * (MF * 16) + mf * 16 + g, c = wn * 32 + nf * 8 + t4 * 2;
-                    *reinterpret_cast<uint32_t*>(&sC[r * CLD + c]) = f2_to_bf2(acc[mf][nf][0], acc[mf][nf][1]);
-                    *reinterpret_cast<uint32_t*>(&sC[(r + 8) * CLD + c]) = f2_to_bf2(acc[mf][nf][2], acc[mf][nf][3]);
+                    const float ce0 = sCen[c], ce1 = sCen[c + 1];
+                    const float v0 = acc[mf][nf][0] - ce0, v1 = acc[mf][nf][1] - ce1;
+                    const float v2 = acc[mf][nf][2] - ce0, v3 = acc[mf][nf][3] - ce1;
+                    *reinterpret_cast<uint32_t*>(&sC[r * CLD + c]) = FWD ? f2_to_h2(v0, v1) : f2_to_bf2(v0, v1);
+                    *reinterpret_cast<uint32_t*>(&sC[(r + 8) * CLD + c]) = FWD ? f2_to_h2(v2, v3) : f2_to_bf2(v2, v3);
                 }
             __syncthreads();
             const int chunk = tid % CPR;
@@ -223,8 +237,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
                             const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yq);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                float2 d = bf2_to_f2(vv[e]);
-                                const float2 y = bf2_to_f2(yy[e]);
+                                float2 d = bf2_to_f2(vv[e]);  // MASK is a backward epilogue: bf16 tile
+                                const float2 y = h2_to_f2(yy[e]);
                                 const int c = chunk * 8 + 2 * e;
                                 const float a0 = fmaf(y.x, sPrev[c], sPrev[BN + c]);
                                 const float a1 = fmaf(y.y, sPrev[c + 1], sPrev[BN + c + 1]);
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
                         } else if (p.sums) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float2 d = bf2_to_f2(vv[e]);
+                                const float2 d = FWD ? h2_to_f2(vv[e]) : bf2_to_f2(vv[e]);
                                 s1[2 * e] += d.x; s1[2 * e + 1] += d.y;
                                 s2[2 * e] = fmaf(d.x, d.x, s2[2 * e]);
                                 s2[2 * e + 1] = fmaf(d.y, d.y, s2[2 * e + 1]);
@@ -290,8 +304,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
 template <int BN, int AMODE, bool MASK>
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     constexpr int NCOEF = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
-    const size_t smem = (size_t)(2 * BM * LDS + 2 * BN * LDS + BM * (BN + 8)) * sizeof(bf16) +
-                        (size_t)(NCOEF * a.kdim + (MASK ? 4 * BN : 0)) * sizeof(float);
+    const size_t smem = (size_t)(2 * BM * LDS + 2 * BN * LDS + BM * (BN + 8)) * sizeof(uint16_t) +
+                        (size_t)(NCOEF * a.kdim + (MASK ? 4 * BN : 0) + BN) * sizeof(float);
     if (smem > 110 * 1024) return fail_arg("pn2_mlp_gemm", "reduction dimension too large for shared memory");
     static size_t configured = 0;
     if (smem > configured) {
@@ -332,9 +346,9 @@ struct WgradArgs {
     long long rows;
     int n, kp, k_true;
     const bf16* dz; int dz_ld;
-    const bf16* y; int y_ld;
+    const act_t* y; int y_ld;
     const float *cA, *cB, *cC;
-    const bf16* x; int x_ld;
+    const act_t* x; int x_ld;
     const float *in_scale, *in_shift;
     float* dw; int dw_ld;
 };
@@ -390,25 +404,25 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs p) {
                     uint32_t* o = reinterpret_cast<uint32_t*>(&vd);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float2 d = bf2_to_f2(a[e]), y = bf2_to_f2(b[e]);
+                        const float2 d = bf2_to_f2(a[e]), y = h2_to_f2(b[e]);
                         const int c = l_col + 2 * e;
                         o[e] = f2_to_bf2(fmaf(sCo[0][c], d.x, fmaf(sCo[1][c], y.x, sCo[2][c])),
                                          fmaf(sCo[0][c + 1], d.y, fmaf(sCo[1][c + 1], y.y, sCo[2][c + 1])));
                     }
                 }
                 if (kcol_ok) {
-                    if (AFFINE) {
-                        const uint32_t* a = reinterpret_cast<const uint32_t*>(&rx[j]);
-                        uint32_t* o = reinterpret_cast<uint32_t*>(&vx);
+                    // the forward operand is fp16; the gradient GEMM runs in bf16
+                    const uint32_t* a = reinterpret_cast<const uint32_t*>(&rx[j]);
+                    uint32_t* o = reinterpret_cast<uint32_t*>(&vx);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 x = bf2_to_f2(a[e]);
-                            const int c = l_col + 2 * e;
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 x = h2_to_f2(a[e]);
+                        const int c = l_col + 2 * e;
+                        if (AFFINE)
                             o[e] = f2_to_bf2(fmaxf(fmaf(x.x, sCo[3][c], sCo[4][c]), 0.f),
                                              fmaxf(fmaf(x.y, sCo[3][c + 1], sCo[4][c + 1]), 0.f));
-                        }
-                    } else {
-                        vx = rx[j];
+                        else
+                            o[e] = f2_to_bf2(x.x, x.y);
                     }
                 }
             }
@@ -473,12 +487,59 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs p) {
     }
 }
 
+// ------------------------------------------------------------------ centre estimate ----------
+// c[n] = sum_k w[n][k] * mean_j act(x[row_j][k]) over <= 16 rows spread evenly over the matrix;
+// c_true[n] = c[n] + sum_k w[n][k] * in_offset[k]: the input rows may themselves be stored centred
+// (x_true = x + in_offset per channel), which the GEMM output inherits as a per-channel constant.
+__global__ void __launch_bounds__(256) center_kernel(long long rows, int kdim, int n, const act_t* __restrict__ x,
+                                                      int x_ld, const float* __restrict__ sc,
+                                                      const float* __restrict__ sh, const act_t* __restrict__ w,
+                                                      const float* __restrict__ in_offset, float* __restrict__ c,
+                                                      float* __restrict__ c_true) {
+    __shared__ float sM[1024];
+    __shared__ float sO[1024];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ns = rows < 16 ? (int)rows : 16;
+    const long long step = rows / ns;
+    for (int k = tid; k < kdim; k += 256) {
+        float m = 0.f;
+        for (int j = 0; j < ns; ++j) {
+            float v = h_to_f(x[(size_t)(j * step) * x_ld + k]);
+            if (sc) v = fmaxf(fmaf(v, sc[k], sh[k]), 0.f);
+            m += v;
+        }
+        sM[k] = m / (float)ns;
+        sO[k] = in_offset ? in_offset[k] : 0.f;
+    }
+    __syncthreads();
+    for (int j = 0; j < 4; ++j) {
+        const int col = blockIdx.x * 32 + warp * 4 + j;
+        if (col >= n) break;
+        float acc = 0.f, acc2 = 0.f;
+        for (int k = lane; k < kdim; k += 32) {
+            const float wv = h_to_f(w[(size_t)col * kdim + k]);
+            acc = fmaf(wv, sM[k], acc);
+            acc2 = fmaf(wv, sO[k], acc2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(kFull, acc, o);
+            acc2 += __shfl_xor_sync(kFull, acc2, o);
+        }
+        if (lane == 0) {
+            c[col] = acc;
+            c_true[col] = acc + acc2;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ small per-channel kernels
 __global__ void bn_finalize_kernel(int n, float inv_rows, float unbias, const float* __restrict__ sums,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ bias, float momentum, float eps, float* running_mean,
-                                   float* running_var, long long* num_batches_tracked, float* scale, float* shift,
-                                   float* mean_out, float* rstd_out) {
+                                   const float* __restrict__ bias, const float* __restrict__ center, float momentum,
+                                   float eps, float* running_mean, float* running_var,
+                                   long long* num_batches_tracked, float* scale, float* shift, float* mean_out,
+                                   float* rstd_out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= n) return;
@@ -491,21 +552,23 @@ __global__ void bn_finalize_kernel(int n, float inv_rows, float unbias, const fl
     mean_out[c] = mean;
     rstd_out[c] = rstd;
     if (running_mean) {
-        // the conv bias shifts the batch mean BatchNorm sees; the GEMM omits it (BN cancels it exactly)
-        const float m = mean + (bias ? bias[c] : 0.f);
+        // the conv bias and the centring constant shift the batch mean BatchNorm sees; the GEMM omits
+        // both (BatchNorm cancels them exactly)
+        const float m = mean + (bias ? bias[c] : 0.f) + (center ? center[c] : 0.f);
         running_mean[c] = fmaf(momentum, m - running_mean[c], running_mean[c]);
         running_var[c] = fmaf(momentum, var * unbias - running_var[c], running_var[c]);
     }
 }
 
 __global__ void bn_eval_affine_kernel(int n, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      const float* __restrict__ bias, const float* __restrict__ running_mean,
-                                      const float* __restrict__ running_var, float eps, float* scale, float* shift) {
+                                      const float* __restrict__ bias, const float* __restrict__ center,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float eps, float* scale, float* shift) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
     scale[c] = sc;
-    shift[c] = fmaf((bias ? bias[c] : 0.f) - running_mean[c], sc, beta[c]);
+    shift[c] = fmaf((bias ? bias[c] : 0.f) + (center ? center[c] : 0.f) - running_mean[c], sc, beta[c]);
 }
 
 __global__ void bn_bwd_coefs_kernel(int n, float inv_rows, const float* __restrict__ sums,
@@ -524,14 +587,14 @@ __global__ void bn_bwd_coefs_kernel(int n, float inv_rows, const float* __restri
     dbeta[c] = s1;
 }
 
-__global__ void prep_weights_kernel(int n, int k_true, int kp, const float* __restrict__ w, bf16* __restrict__ wb,
+__global__ void prep_weights_kernel(int n, int k_true, int kp, const float* __restrict__ w, act_t* __restrict__ wh,
                                     bf16* __restrict__ wt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * kp) return;
     const int r = i / kp, c = i - r * kp;
-    const bf16 v = __float2bfloat16(c < k_true ? w[(size_t)r * k_true + c] : 0.f);
-    wb[i] = v;
-    if (wt) wt[(size_t)c * n + r] = v;
+    const float v = c < k_true ? w[(size_t)r * k_true + c] : 0.f;
+    wh[i] = f_to_h(v);
+    if (wt) wt[(size_t)c * n + r] = __float2bfloat16(v);
 }
 
 }  // namespace
@@ -539,19 +602,33 @@ __global__ void prep_weights_kernel(int n, int k_true, int kp, const float* __re
 
 using namespace pn2;
 
+extern "C" int pn2_mlp_center(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
+                              const float* in_shift, const void* w, const float* in_offset, float* center,
+                              float* center_true, pn2_stream_t stream) {
+    if (int e = check_common("pn2_mlp_center", rows, kdim, n)) return e;
+    if (rows == 0) return 0;
+    if (kdim > 1024) return fail_arg("pn2_mlp_center", "kdim > 1024");
+    if (!x || !w || !center || !center_true) return fail_arg("pn2_mlp_center", "null pointer");
+    center_kernel<<<(n + 31) / 32, 256, 0, (cudaStream_t)stream>>>(rows, kdim, n, (const act_t*)x, x_ld, in_scale, in_shift,
+                                                                  (const act_t*)w, in_offset, center, center_true);
+    PN2_CHECK_LAUNCH("center_kernel");
+    return 0;
+}
+
 extern "C" int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
-                                const float* in_shift, const void* w, void* y, int y_ld, float* stats,
-                                pn2_stream_t stream) {
+                                const float* in_shift, const void* w, const float* center, void* y, int y_ld,
+                                float* stats, pn2_stream_t stream) {
     if (int e = check_common("pn2_mlp_gemm_fwd", rows, kdim, n)) return e;
     if (rows == 0) return 0;
     if (!x || !w || !y) return fail_arg("pn2_mlp_gemm_fwd", "null pointer");
     if (x_ld % 8 || y_ld % 8 || x_ld < kdim || y_ld < n) return fail_arg("pn2_mlp_gemm_fwd", "bad leading dimension");
     GemmArgs a{};
     a.rows = rows; a.kdim = kdim; a.n = n;
-    a.a0 = (const bf16*)x; a.a0_ld = x_ld;
+    a.a0 = (const uint16_t*)x; a.a0_ld = x_ld;
     a.c0 = in_scale; a.c1 = in_shift;
-    a.b = (const bf16*)w;
-    a.out = (bf16*)y; a.out_ld = y_ld;
+    a.b = (const uint16_t*)w;
+    a.center = center;
+    a.out = (uint16_t*)y; a.out_ld = y_ld;
     a.sums = stats;
     if (in_scale) return dispatch_bn<A_AFFINE, false>(a, (cudaStream_t)stream);
     return dispatch_bn<A_PLAIN, false>(a, (cudaStream_t)stream);
@@ -569,16 +646,16 @@ extern "C" int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const vo
         return fail_arg("pn2_mlp_gemm_dgrad", "bad leading dimension");
     GemmArgs a{};
     a.rows = rows; a.kdim = n_red; a.n = k_out;
-    a.a0 = (const bf16*)dz; a.a0_ld = dz_ld;
-    a.a1 = (const bf16*)y; a.a1_ld = y_ld;
+    a.a0 = (const uint16_t*)dz; a.a0_ld = dz_ld;
+    a.a1 = (const uint16_t*)y; a.a1_ld = y_ld;
     a.c0 = cA; a.c1 = cB; a.c2 = cC;
-    a.b = (const bf16*)wt;
-    a.out = (bf16*)dz_prev; a.out_ld = dz_prev_ld;
+    a.b = (const uint16_t*)wt;
+    a.out = (uint16_t*)dz_prev; a.out_ld = dz_prev_ld;
     if (y_prev) {
         if (!prev_scale || !prev_shift || !prev_mean || !prev_rstd || !sums_prev || y_prev_ld % 8)
             return fail_arg("pn2_mlp_gemm_dgrad", "masking needs the previous layer's constants");
         a.sums = sums_prev;
-        a.yp = (const bf16*)y_prev; a.yp_ld = y_prev_ld;
+        a.yp = (const uint16_t*)y_prev; a.yp_ld = y_prev_ld;
         a.p_scale = prev_scale; a.p_shift = prev_shift; a.p_mean = prev_mean; a.p_rstd = prev_rstd;
         return dispatch_bn<A_BNBWD, true>(a, (cudaStream_t)stream);
     }
@@ -597,9 +674,9 @@ extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, con
     WgradArgs a{};
     a.rows = rows; a.n = n; a.kp = kp; a.k_true = k_true;
     a.dz = (const bf16*)dz; a.dz_ld = dz_ld;
-    a.y = (const bf16*)y; a.y_ld = y_ld;
+    a.y = (const act_t*)y; a.y_ld = y_ld;
     a.cA = cA; a.cB = cB; a.cC = cC;
-    a.x = (const bf16*)x; a.x_ld = x_ld;
+    a.x = (const act_t*)x; a.x_ld = x_ld;
     a.in_scale = in_scale; a.in_shift = in_shift;
     a.dw = dw; a.dw_ld = dw_ld;
     const int gx = (n + TN - 1) / TN, gy = (kp + TK - 1) / TK;
@@ -617,26 +694,26 @@ extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, con
 }
 
 extern "C" int pn2_bn_finalize(int n, long long rows, const float* sums, const float* gamma, const float* beta,
-                               const float* conv_bias, float momentum, float eps, float* running_mean,
+                               const float* conv_bias, const float* center, float momentum, float eps, float* running_mean,
                                float* running_var, long long* num_batches_tracked, float* scale, float* shift,
                                float* mean, float* rstd, pn2_stream_t stream) {
     if (n <= 0 || rows <= 0) return fail_arg("pn2_bn_finalize", "non-positive size");
     if (!sums || !gamma || !beta || !scale || !shift || !mean || !rstd) return fail_arg("pn2_bn_finalize", "null pointer");
     const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
     bn_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        n, (float)(1.0 / (double)rows), unbias, sums, gamma, beta, conv_bias, momentum, eps, running_mean, running_var,
+        n, (float)(1.0 / (double)rows), unbias, sums, gamma, beta, conv_bias, center, momentum, eps, running_mean, running_var,
         num_batches_tracked, scale, shift, mean, rstd);
     PN2_CHECK_LAUNCH("bn_finalize_kernel");
     return 0;
 }
 
 extern "C" int pn2_bn_eval_affine(int n, const float* gamma, const float* beta, const float* conv_bias,
-                                  const float* running_mean, const float* running_var, float eps, float* scale,
+                                  const float* center, const float* running_mean, const float* running_var, float eps, float* scale,
                                   float* shift, pn2_stream_t stream) {
     if (n <= 0) return fail_arg("pn2_bn_eval_affine", "non-positive size");
     if (!gamma || !beta || !running_mean || !running_var || !scale || !shift)
         return fail_arg("pn2_bn_eval_affine", "null pointer");
-    bn_eval_affine_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, gamma, beta, conv_bias, running_mean,
+    bn_eval_affine_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, gamma, beta, conv_bias, center, running_mean,
                                                                             running_var, eps, scale, shift);
     PN2_CHECK_LAUNCH("bn_eval_affine_kernel");
     return 0;
@@ -654,12 +731,12 @@ extern "C" int pn2_bn_bwd_coefs(int n, long long rows, const float* sums, const 
     return 0;
 }
 
-extern "C" int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_bf16, void* wt_bf16,
+extern "C" int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_f16, void* wt_bf16,
                                     pn2_stream_t stream) {
     if (n <= 0 || k_true <= 0 || kp < k_true) return fail_arg("pn2_mlp_prep_weights", "bad size");
-    if (!w || !w_bf16) return fail_arg("pn2_mlp_prep_weights", "null pointer");
+    if (!w || !w_f16) return fail_arg("pn2_mlp_prep_weights", "null pointer");
     const int total = n * kp;
-    prep_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, k_true, kp, w, (bf16*)w_bf16,
+    prep_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, k_true, kp, w, (act_t*)w_f16,
                                                                                (bf16*)wt_bf16);
     PN2_CHECK_LAUNCH("prep_weights_kernel");
     return 0;

@@ -2,18 +2,22 @@
 //
 // The two ends of every fused SA / FP layer (mlp_gemm.cu holds the middle):
 //
-//   to_rows          (B,C,N) fp32 channel-major  ->  rows [B*N][ld] bf16        (smem transpose)
+//   to_rows          (B,C,N) fp32 channel-major  ->  rows [B*N][ld] fp16        (smem transpose)
+//                    (forward rows are fp16, gradient rows bf16: see mma_common.cuh)
 //   sa_build_rows    grouping + "- centre" + concat of reference pointnet_utils.py:389-396 (SA-MSG:
 //                    [features, xyz - centre]), :570-575 (given centres: ... + centre features
 //                    broadcast over K) and :170-186 (group_all: [xyz, features]) in ONE pass, written
-//                    as bf16 rows; the source features are themselves rows, optionally still in
+//                    as fp16 rows; the source features are themselves rows, optionally still in
 //                    pre-BatchNorm form (scale/shift + ReLU applied on the fly).
 //   fp_build_rows    three-NN inverse-distance weights (pointnet_utils.py:446-449), three-point
 //                    interpolation (interpolate_gpu.cu:149-169) and the [skip, interpolated] concat
 //                    (:455-456) in one pass; S == 1 broadcasts (:443-444).
 //   pool_fwd         BatchNorm + ReLU of the last layer, max over the K rows of a group (:403,509),
-//                    written channel-major fp32 (the module's output layout), as bf16 rows for the next
-//                    fused consumer, plus the arg-max for backward.  K == 1 is the FP / head case.
+//                    written channel-major fp32 (the module's output layout), plus the arg-max for
+//                    backward and per-channel sums: pooled features are handed to the next fused consumer
+//                    as fp16 rows CENTRED on their channel mean (to_rows), because a max-pooled feature
+//                    is typically a large value with a small spread across groups and plain 16-bit rounding
+//                    would eat the spread.  K == 1 is the FP / head case.
 //   pool_bwd         routes the output gradient to the arg-max rows through the ReLU mask and reduces
 //                    the two BatchNorm-backward sums.
 //   sa_rows_bwd / fp_rows_bwd   scatter the gradient of the built rows back to the feature tensors.
@@ -29,29 +33,33 @@ constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------ to_rows -----------------
 __global__ void __launch_bounds__(256) to_rows_kernel(int c, int n, int ld, const float* __restrict__ src,
-                                                       bf16* __restrict__ dst) {
+                                                       const float* __restrict__ sub_sums, float sub_scale,
+                                                       act_t* __restrict__ dst) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     for (int j = ty; j < 32; j += 8) {
         const int cc = c0 + j, nn = n0 + tx;
-        tile[j][tx] = (cc < c && nn < n) ? src[((size_t)b * c + cc) * n + nn] : 0.f;
+        // optional centring: subtract the channel mean (sub_sums[c] * sub_scale) before bf16 rounding
+        tile[j][tx] = (cc < c && nn < n)
+                          ? src[((size_t)b * c + cc) * n + nn] - (sub_sums ? sub_sums[cc] * sub_scale : 0.f)
+                          : 0.f;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int nn = n0 + j, cc = c0 + tx;
-        if (nn < n && cc < ld) dst[((size_t)b * n + nn) * ld + cc] = __float2bfloat16(tile[tx][j]);
+        if (nn < n && cc < ld) dst[((size_t)b * n + nn) * ld + cc] = f_to_h(tile[tx][j]);
     }
 }
 
 // ------------------------------------------------------------------ sa_build_rows -----------
-struct RowSrc {  // bf16 rows with an optional per-channel affine + ReLU ("still pre-BatchNorm")
-    const bf16* p;
+struct RowSrc {  // fp16 rows with an optional per-channel affine + ReLU ("still pre-BatchNorm")
+    const act_t* p;
     int c, ld;
     const float *scale, *shift;
 };
 __device__ __forceinline__ float row_val(const RowSrc& s, size_t row, int ch) {
-    float v = bf_to_f(s.p[row * s.ld + ch]);
+    float v = h_to_f(s.p[row * s.ld + ch]);
     if (s.scale) v = fmaxf(fmaf(v, __ldg(s.scale + ch), __ldg(s.shift + ch)), 0.f);
     return v;
 }
@@ -62,7 +70,7 @@ struct SaBuildArgs {
     const int* idx;              // (B,S,K) | null (identity: row k of group <-> point k)
     RowSrc feat, cen;
     int xyz_first;
-    bf16* out;
+    act_t* out;
     int out_ld;
 };
 
@@ -84,13 +92,13 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
     const size_t frow = (size_t)b * a.n + j, crow = (size_t)b * a.s + s;
     const int fc = a.feat.p ? a.feat.c : 0, cc = a.cen.p ? a.cen.c : 0;
     const int f0 = a.xyz_first ? 3 : 0, x0 = a.xyz_first ? 0 : fc, c0 = fc + 3;
-    bf16* o = a.out + (size_t)row * a.out_ld;
+    act_t* o = a.out + (size_t)row * a.out_ld;
     for (int col = lane; col < a.out_ld; col += 32) {
         float v = 0.f;
         if (col >= f0 && col < f0 + fc) v = row_val(a.feat, frow, col - f0);
         else if (col >= x0 && col < x0 + 3) v = rel[col - x0];
         else if (col >= c0 && col < c0 + cc) v = row_val(a.cen, crow, col - c0);
-        o[col] = __float2bfloat16(v);
+        o[col] = f_to_h(v);
     }
 }
 
@@ -100,7 +108,7 @@ struct FpBuildArgs {
     RowSrc skip, coarse;
     const int* idx;       // (B,N,3)
     const float* dist2;   // (B,N,3) squared distances from three_nn
-    bf16* out;
+    act_t* out;
     int out_ld;
 };
 // weights of reference pointnet_utils.py:446-449: w_j = (1/(sqrt(d2_j)+1e-8)) / sum_j(...), in fp32
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
         nn_weights(a.dist2 + row * 3, w);
     }
     const int sc = a.skip.p ? a.skip.c : 0;
-    bf16* o = a.out + (size_t)row * a.out_ld;
+    act_t* o = a.out + (size_t)row * a.out_ld;
     for (int col = lane; col < a.out_ld; col += 32) {
         float v = 0.f;
         if (col < sc) {
@@ -143,17 +151,17 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
                 v = row_val(a.coarse, (size_t)b, ch);
             }
         }
-        o[col] = __float2bfloat16(v);
+        o[col] = f_to_h(v);
     }
 }
 
 // ------------------------------------------------------------------ pool fwd / bwd ----------
 struct PoolArgs {
     int b, s, k, c;
-    const bf16* y; int y_ld;
+    const act_t* y; int y_ld;
     const float *scale, *shift, *mean, *rstd;
     float* out_cm;        // (B,C,S)
-    bf16* out_rows; int out_ld;
+    float* chan_sums;     // [C] += sum over (b,s) of the output (nullable)
     int* argmax;          // (B,S,C)
     const float* dout_cm; // backward
     bf16* dz; int dz_ld;
@@ -175,15 +183,14 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
             float m0 = -1.f, m1 = -1.f;  // below every ReLU output: the first row always wins
             int i0 = 0, i1 = 0;
             if (ok && s < a.s) {
-                const bf16* yr = a.y + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch;
+                const act_t* yr = a.y + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch;
                 for (int kk = 0; kk < a.k; ++kk) {
-                    const float2 v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
+                    const float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
                     const float r0 = fmaxf(fmaf(v.x, sc0, sh0), 0.f), r1 = fmaxf(fmaf(v.y, sc1, sh1), 0.f);
                     if (r0 > m0) { m0 = r0; i0 = kk; }
                     if (r1 > m1) { m1 = r1; i1 = kk; }
                 }
                 const size_t g = (size_t)b * a.s + s;
-                if (a.out_rows) *reinterpret_cast<uint32_t*>(a.out_rows + g * a.out_ld + ch) = f2_to_bf2(m0, m1);
                 if (a.argmax) *reinterpret_cast<int2*>(a.argmax + g * a.c + ch) = make_int2(i0, i1);
             }
             tile[gi][lane * 2] = m0;
@@ -192,7 +199,15 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
         __syncthreads();
         for (int cc = warp; cc < 64; cc += 8) {
             const int chn = c0 + cc, s = s0 + lane;
-            if (chn < a.c && s < a.s) a.out_cm[((size_t)b * a.c + chn) * a.s + s] = tile[lane][cc];
+            const bool okw = chn < a.c && s < a.s;
+            const float v = okw ? tile[lane][cc] : 0.f;
+            if (okw) a.out_cm[((size_t)b * a.c + chn) * a.s + s] = v;
+            if (a.chan_sums) {
+                float t = v;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+                if (lane == 0 && chn < a.c) atomicAdd(a.chan_sums + chn, t);
+            }
         }
         __syncthreads();
     }
@@ -224,12 +239,12 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
             int i0 = 0, i1 = 0;
             if (a.argmax) { const int2 am = *reinterpret_cast<const int2*>(a.argmax + g * a.c + ch); i0 = am.x; i1 = am.y; }
             const float g0 = tile[gi][lane * 2], g1 = tile[gi][lane * 2 + 1];
-            const bf16* yr = a.y + (g * a.k) * a.y_ld + ch;
+            const act_t* yr = a.y + (g * a.k) * a.y_ld + ch;
             bf16* dr = a.dz + (g * a.k) * a.dz_ld + ch;
             for (int kk = 0; kk < a.k; ++kk) {
                 float d0 = 0.f, d1 = 0.f;
                 if (kk == i0 || kk == i1) {
-                    const float2 v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
+                    const float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
                     if (kk == i0 && fmaf(v.x, sc0, sh0) > 0.f) { d0 = g0; p1a += d0; p2a = fmaf(d0, (v.x - mu0) * rs0, p2a); }
                     if (kk == i1 && fmaf(v.y, sc1, sh1) > 0.f) { d1 = g1; p1b += d1; p2b = fmaf(d1, (v.y - mu1) * rs1, p2b); }
                 }
@@ -324,7 +339,7 @@ __global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a
 
 RowSrc mk_src(const void* p, int c, int ld, const float* scale, const float* shift) {
     RowSrc s;
-    s.p = (const bf16*)p; s.c = c; s.ld = ld; s.scale = scale; s.shift = shift;
+    s.p = (const act_t*)p; s.c = c; s.ld = ld; s.scale = scale; s.shift = shift;
     return s;
 }
 unsigned warp_blocks(long long rows) { return (unsigned)((rows + (kThreads / 32) - 1) / (kThreads / 32)); }
@@ -334,13 +349,14 @@ unsigned warp_blocks(long long rows) { return (unsigned)((rows + (kThreads / 32)
 
 using namespace pn2;
 
-extern "C" int pn2_to_rows(int b, int c, int n, const float* src, void* dst, int ld, pn2_stream_t stream) {
+extern "C" int pn2_to_rows(int b, int c, int n, const float* src, const float* sub_sums, float sub_scale, void* dst,
+                           int ld, pn2_stream_t stream) {
     if (b < 0 || c < 0 || n < 0 || ld < c) return fail_arg("pn2_to_rows", "bad size");
     if (b == 0 || n == 0 || ld == 0) return 0;
     if (!src || !dst) return fail_arg("pn2_to_rows", "null pointer");
     if (b > 65535) return fail_arg("pn2_to_rows", "b > 65535");
     dim3 grid((n + 31) / 32, (ld + 31) / 32, b);
-    to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, ld, src, (bf16*)dst);
+    to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, ld, src, sub_sums, sub_scale, (act_t*)dst);
     PN2_CHECK_LAUNCH("to_rows_kernel");
     return 0;
 }
@@ -361,7 +377,7 @@ extern "C" int pn2_sa_build_rows(int b, int n, int s, int k, const float* xyz, c
     a.b = b; a.n = n; a.s = s; a.k = k; a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx;
     a.feat = mk_src(feat, feat_c, feat_ld, feat_scale, feat_shift);
     a.cen = mk_src(cen, cen_c, cen_ld, cen_scale, cen_shift);
-    a.xyz_first = xyz_first; a.out = (bf16*)out; a.out_ld = out_ld;
+    a.xyz_first = xyz_first; a.out = (act_t*)out; a.out_ld = out_ld;
     sa_build_rows_kernel<<<warp_blocks((long long)b * s * k), kThreads, 0, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("sa_build_rows_kernel");
     return 0;
@@ -379,22 +395,21 @@ extern "C" int pn2_fp_build_rows(int b, int n, int s, const void* skip, int skip
     a.b = b; a.n = n; a.s = s;
     a.skip = mk_src(skip, skip_c, skip_ld, skip_scale, skip_shift);
     a.coarse = mk_src(coarse, coarse_c, coarse_ld, coarse_scale, coarse_shift);
-    a.idx = idx; a.dist2 = dist2; a.out = (bf16*)out; a.out_ld = out_ld;
+    a.idx = idx; a.dist2 = dist2; a.out = (act_t*)out; a.out_ld = out_ld;
     fp_build_rows_kernel<<<warp_blocks((long long)b * n), kThreads, 0, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("fp_build_rows_kernel");
     return 0;
 }
 
 extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld, const float* scale,
-                            const float* shift, float* out_cm, void* out_rows, int out_ld, int* argmax,
-                            pn2_stream_t stream) {
+                            const float* shift, float* out_cm, float* chan_sums, int* argmax, pn2_stream_t stream) {
     if (b < 0 || s <= 0 || k <= 0 || c <= 0 || c % 8) return fail_arg("pn2_pool_fwd", "bad size");
     if (b == 0) return 0;
     if (b > 65535) return fail_arg("pn2_pool_fwd", "b > 65535");
     if (!y || !scale || !shift || !out_cm) return fail_arg("pn2_pool_fwd", "null pointer");
     PoolArgs a{};
-    a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const bf16*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
-    a.out_cm = out_cm; a.out_rows = (bf16*)out_rows; a.out_ld = out_ld; a.argmax = argmax;
+    a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
+    a.out_cm = out_cm; a.chan_sums = chan_sums; a.argmax = argmax;
     dim3 grid((s + 31) / 32, b);
     pool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("pool_fwd_kernel");
@@ -410,7 +425,7 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
     if (!dout_cm || !y || !scale || !shift || !mean || !rstd || !dz || !sums) return fail_arg("pn2_pool_bwd", "null pointer");
     if (k > 1 && !argmax) return fail_arg("pn2_pool_bwd", "argmax required when k > 1");
     PoolArgs a{};
-    a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const bf16*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
+    a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
     a.mean = mean; a.rstd = rstd; a.argmax = const_cast<int*>(argmax); a.dout_cm = dout_cm; a.dz = (bf16*)dz; a.dz_ld = dz_ld; a.sums = sums;
     dim3 grid((s + 31) / 32, b);
     pool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);

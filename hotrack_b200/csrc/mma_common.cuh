@@ -7,12 +7,22 @@
 // memory; fragments come from ldmatrix and feed mma.sync.m16n8k16 (bf16 x bf16 -> fp32).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "pn2_common.cuh"
 
 namespace pn2 {
 
+// Two 16-bit storage types, fixed per role:
+//   act_t (fp16)  every FORWARD row matrix: gathered inputs, pre-BatchNorm layer outputs, pooled
+//                 features, forward weights.  These are O(1)-O(10) values that BatchNorm normalises, so
+//                 range is no issue and the 11-bit significand matters: measured on the BASELINE
+//                 config, bf16 forward storage puts ~28% relative error on the backbone output (this
+//                 network amplifies perturbations ~5x in FP3 alone), fp16 an eighth of that.
+//   bf16          every BACKWARD row matrix (gradients: wide dynamic range, precision uncritical)
+//                 and the transposed weights the input-gradient GEMM multiplies them with.
 typedef __nv_bfloat16 bf16;
+typedef __half act_t;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -28,6 +38,14 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// D(16x8, fp32) += A(16x16, fp16, row) * B(16x8, fp16, col)
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -49,5 +67,16 @@ __device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float bf_to_f(bf16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ float2 h2_to_f2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
+    // saturate instead of overflowing to inf: a finite fp16 keeps BatchNorm statistics finite
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float h_to_f(act_t v) { return __half2float(v); }
+__device__ __forceinline__ act_t f_to_h(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
 
 }  // namespace pn2

@@ -1,4 +1,5 @@
-"""The "fused" engine: the grouped per-point MLP of the SA / FP modules on bf16 tensor-core kernels.
+"""The "fused" engine: the grouped per-point MLP of the SA / FP modules on 16-bit tensor-core kernels
+(fp16 forward rows, bf16 gradient rows, fp32 accumulation and BatchNorm arithmetic).
 
 Host side of include/pn2b200_mlp.h.  One ``autograd.Function`` (``_MlpStack``) runs a whole
   build rows (gather / interpolate / concat)  ->  [GEMM + BatchNorm statistics] x L  ->  BN+ReLU(+max-pool)
@@ -24,7 +25,8 @@ from torch.autograd import Function
 from . import _lib
 from . import pointnet2_cuda as pc
 
-_BF16 = torch.bfloat16
+_BF16 = torch.bfloat16  # gradient rows
+_F16 = torch.float16    # forward rows (see csrc/mma_common.cuh)
 
 
 def _stream():
@@ -40,13 +42,14 @@ def _pad32(c):
 
 
 class Rows:
-    """bf16 row matrix [rows][ld] with c valid channels; scale/shift (fp32, length >= c) mean the
+    """fp16 row matrix [rows][ld] with c valid channels; scale/shift (fp32, length >= c) mean the
     consumer must read relu(y*scale + shift) -- the producer's BatchNorm+ReLU applied on the fly."""
 
-    __slots__ = ("y", "c", "ld", "scale", "shift", "numel", "version")
+    __slots__ = ("y", "c", "ld", "scale", "shift", "offset", "numel", "version")
 
-    def __init__(self, y, c, ld, scale=None, shift=None):
-        self.y, self.c, self.ld, self.scale, self.shift = y, c, ld, scale, shift
+    def __init__(self, y, c, ld, scale=None, shift=None, offset=None):
+        # offset (fp32 [c]): the rows are stored CENTRED, true value = y + offset (pooled features)
+        self.y, self.c, self.ld, self.scale, self.shift, self.offset = y, c, ld, scale, shift, offset
         self.numel = self.version = None
 
 
@@ -74,8 +77,8 @@ def rows_of(t):
     if t.dtype != torch.float32:
         raise TypeError("fused engine expects fp32 feature tensors")
     ld = (C + 7) // 8 * 8
-    y = torch.empty(B * N, ld, dtype=_BF16, device=t.device)
-    _lib.call("pn2_to_rows", B, C, N, t.data_ptr(), y.data_ptr(), ld, _stream())
+    y = torch.empty(B * N, ld, dtype=_F16, device=t.device)
+    _lib.call("pn2_to_rows", B, C, N, t.data_ptr(), 0, 0.0, y.data_ptr(), ld, _stream())
     return Rows(y, C, ld)
 
 
@@ -114,7 +117,7 @@ class _MlpStack(Function):
             cc = rb.c if rb is not None else 0
             cin = fc + 3 + cc
             R, groups, pool_k = B * S * K, S, K
-            x0 = torch.empty(R, _pad32(cin), dtype=_BF16, device=dev)
+            x0 = torch.empty(R, _pad32(cin), dtype=_F16, device=dev)
             _lib.call("pn2_sa_build_rows", B, N, S, K, xyz.data_ptr(), _p(new_xyz), _p(idx),
                       _p(ra.y) if ra else 0, fc, ra.ld if ra else 0, _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0,
                       _p(rb.y) if rb else 0, cc, rb.ld if rb else 0, _p(rb.scale) if rb else 0, _p(rb.shift) if rb else 0,
@@ -125,7 +128,7 @@ class _MlpStack(Function):
             sc = ra.c if ra is not None else 0
             cin = sc + rb.c
             R, groups, pool_k = B * N, N, 1
-            x0 = torch.empty(R, _pad32(cin), dtype=_BF16, device=dev)
+            x0 = torch.empty(R, _pad32(cin), dtype=_F16, device=dev)
             _lib.call("pn2_fp_build_rows", B, N, S, _p(ra.y) if ra else 0, sc, ra.ld if ra else 0,
                       _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0, rb.y.data_ptr(), rb.c, rb.ld, _p(rb.scale),
                       _p(rb.shift), _p(idx), _p(dist2), x0.data_ptr(), x0.shape[1], st)
@@ -143,13 +146,25 @@ class _MlpStack(Function):
                 x, x_ld, xs, xh, kp = ra.y, ra.ld, ra.scale, ra.shift, ra.ld
             else:  # re-pad the row form to the GEMM's 32-column granularity
                 kp = _pad32(ra.c)
-                x = torch.zeros(R, kp, dtype=_BF16, device=dev)
+                x = torch.zeros(R, kp, dtype=_F16, device=dev)
                 x[:, :ra.c] = ra.y[:, :ra.c]
                 x_ld, xs, xh = kp, ra.scale, ra.shift
             if xs is not None and xs.numel() < kp:
                 xs = torch.cat([xs, xs.new_zeros(kp - xs.numel())])
                 xh = torch.cat([xh, xh.new_zeros(kp - xh.numel())])
         in0 = (x, x_ld, xs, xh)
+        # per-channel constants the layer-0 input rows were centred by (pooled features), by column
+        in_off = None
+        segs = []
+        if kind == "sa":
+            segs = [(ra, 3 if meta[3] else 0), (rb, (ra.c if ra is not None else 0) + 3)]
+        elif kind == "fp":
+            segs = [(ra, 0), (rb, ra.c if ra is not None else 0)]
+        for r, start in segs:
+            if r is not None and r.offset is not None:
+                if in_off is None:
+                    in_off = torch.zeros(kp, dtype=torch.float32, device=dev)
+                in_off[start:start + r.c] = r.offset
         for l in range(nl):
             w, bias, gamma, beta = params[4 * l: 4 * l + 4]
             bn = bns[l]
@@ -157,27 +172,29 @@ class _MlpStack(Function):
             L.cout, L.cin, L.kp = w.shape[0], w.shape[1], kp
             if L.cout % 32:
                 raise ValueError("fused engine needs layer widths that are multiples of 32 (got %d)" % L.cout)
-            L.w = torch.empty(L.cout, kp, dtype=_BF16, device=dev)
+            L.w = torch.empty(L.cout, kp, dtype=_F16, device=dev)
             L.wt = torch.empty(kp, L.cout, dtype=_BF16, device=dev) if training else None
             _lib.call("pn2_mlp_prep_weights", L.cout, L.cin, kp, w.data_ptr(), L.w.data_ptr(), _p(L.wt), st)
-            L.y = torch.empty(R, L.cout, dtype=_BF16, device=dev)
-            consts = torch.empty(4, L.cout, dtype=torch.float32, device=dev)
-            L.scale, L.shift, L.mean, L.rstd = consts[0], consts[1], consts[2], consts[3]
+            L.y = torch.empty(R, L.cout, dtype=_F16, device=dev)
+            consts = torch.empty(6, L.cout, dtype=torch.float32, device=dev)
+            L.scale, L.shift, L.mean, L.rstd, cen, cen_true = (consts[i] for i in range(6))
+            _lib.call("pn2_mlp_center", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
+                      _p(in_off) if l == 0 else 0, cen.data_ptr(), cen_true.data_ptr(), st)
             if training:
                 stats = torch.zeros(2, L.cout, dtype=torch.float32, device=dev)
                 _lib.call("pn2_mlp_gemm_fwd", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
-                          L.y.data_ptr(), L.cout, stats.data_ptr(), st)
+                          cen.data_ptr(), L.y.data_ptr(), L.cout, stats.data_ptr(), st)
                 track = bn.track_running_stats and bn.running_mean is not None
                 _lib.call("pn2_bn_finalize", L.cout, R, stats.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
-                          _p(bias), _bn_momentum(bn), float(bn.eps), _p(bn.running_mean) if track else 0,
+                          _p(bias), cen_true.data_ptr(), _bn_momentum(bn), float(bn.eps), _p(bn.running_mean) if track else 0,
                           _p(bn.running_var) if track else 0, _p(bn.num_batches_tracked) if track else 0,
                           L.scale.data_ptr(), L.shift.data_ptr(), L.mean.data_ptr(), L.rstd.data_ptr(), st)
             else:
                 _lib.call("pn2_bn_eval_affine", L.cout, bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias),
-                          bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps), L.scale.data_ptr(),
-                          L.shift.data_ptr(), st)
+                          cen_true.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps),
+                          L.scale.data_ptr(), L.shift.data_ptr(), st)
                 _lib.call("pn2_mlp_gemm_fwd", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
-                          L.y.data_ptr(), L.cout, 0, st)
+                          cen.data_ptr(), L.y.data_ptr(), L.cout, 0, st)
             layers.append(L)
             x, x_ld, xs, xh, kp = L.y, L.cout, L.scale, L.shift, L.cout
 
@@ -185,13 +202,20 @@ class _MlpStack(Function):
         last = layers[-1]
         C = last.cout
         out = torch.empty(B, C, groups, dtype=torch.float32, device=dev)
-        out_rows = argmax = None
+        chan_sums = argmax = None
         if pool_k > 1:
-            out_rows = torch.empty(B * groups, C, dtype=_BF16, device=dev)
+            chan_sums = torch.zeros(C, dtype=torch.float32, device=dev)
             argmax = torch.empty(B, groups, C, dtype=torch.int32, device=dev) if training else None
         _lib.call("pn2_pool_fwd", B, groups, pool_k, C, last.y.data_ptr(), C, last.scale.data_ptr(),
-                  last.shift.data_ptr(), out.data_ptr(), _p(out_rows), C, _p(argmax), st)
-        _MlpStack.last_rows = Rows(out_rows, C, C) if pool_k > 1 else Rows(last.y, C, C, last.scale, last.shift)
+                  last.shift.data_ptr(), out.data_ptr(), _p(chan_sums), _p(argmax), st)
+        if pool_k > 1:
+            # pooled features go to the next fused consumer as bf16 rows centred on their channel mean
+            inv = 1.0 / (B * groups)
+            out_rows = torch.empty(B * groups, C, dtype=_F16, device=dev)
+            _lib.call("pn2_to_rows", B, C, groups, out.data_ptr(), chan_sums.data_ptr(), inv, out_rows.data_ptr(), C, st)
+            _MlpStack.last_rows = Rows(out_rows, C, C, offset=chan_sums * inv)
+        else:
+            _MlpStack.last_rows = Rows(last.y, C, C, last.scale, last.shift)
 
         ctx.kind, ctx.meta, ctx.training = kind, meta, training
         ctx.dims = (B, groups, pool_k, R, cin)
@@ -374,7 +398,7 @@ def alg_bytes(name, a):
         return rows * (2 * n + kp) * 2 + n * kp * 4
     if name == "pn2_pool_fwd":
         b, s, k, c = a[:4]
-        return b * s * k * c * 2 + b * s * c * 4 + (b * s * c * 6 if k > 1 else 0)
+        return b * s * k * c * 2 + b * s * c * 4 + (b * s * c * 4 if k > 1 else 0)
     if name == "pn2_pool_bwd":
         b, s, k, c = a[:4]
         return b * s * c * 4 + b * s * k * c * 2 + (b * s * c * (4 + 2) if k > 1 else b * s * c * 2)
@@ -392,5 +416,5 @@ def alg_bytes(name, a):
         return b * n * (a[6] * 2 + 24)
     if name == "pn2_to_rows":
         b, c, n = a[:3]
-        return b * c * n * 4 + b * n * a[5] * 2
+        return b * c * n * 4 + b * n * a[7] * 2
     return None

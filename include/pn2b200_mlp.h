@@ -20,8 +20,10 @@
 extern "C" {
 #endif
 
-/* (B,C,N) fp32 channel-major -> rows [B*N][ld] bf16, columns >= C zero-filled. */
-int pn2_to_rows(int b, int c, int n, const float* src, void* dst, int ld, pn2_stream_t stream);
+/* (B,C,N) fp32 channel-major -> rows [B*N][ld] bf16, columns >= C zero-filled.  sub_sums != NULL: the value
+ * sub_sums[c]*sub_scale (a channel mean) is subtracted before rounding ("centred rows"). */
+int pn2_to_rows(int b, int c, int n, const float* src, const float* sub_sums, float sub_scale, void* dst, int ld,
+                pn2_stream_t stream);
 
 /* Grouped rows of one SA scale (pointnet_utils.py:389-396, 570-575; group-all :170-186).
  * Row (b,s,k), point j = idx[b,s,k] (idx NULL: j = k, k == n):
@@ -40,28 +42,40 @@ int pn2_fp_build_rows(int b, int n, int s, const void* skip, int skip_c, int ski
                       const float* coarse_scale, const float* coarse_shift, const int* idx, const float* dist2,
                       void* out, int out_ld, pn2_stream_t stream);
 
-/* y[rows][n] = act(x)[rows][kdim] * w[n][kdim]^T  (bf16 in, fp32 accumulate, bf16 out), act = relu(x*scale+shift)
- * when in_scale != NULL.  stats != NULL: stats[0..n) += column sums of y, stats[n..2n) += sums of y^2 (zeroed by
- * the caller) -- the BatchNorm batch statistics.  kdim % 32 == 0, n % 8 == 0. */
+/* center[n] = w[n][:] . mean_j act(x[row_j][:]) over <= 16 rows spread over the matrix: a cheap estimate of the
+ * per-channel mean of the GEMM output, used to centre it before bf16 rounding (kdim <= 1024).  in_offset[kdim] (nullable): per-channel constants the
+ * input rows were themselves centred by; center_true = center + w . in_offset is what the true (uncentred) output
+ * differs from the stored one by -- bn_finalize / bn_eval_affine take center_true. */
+int pn2_mlp_center(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
+                   const float* in_shift, const void* w, const float* in_offset, float* center, float* center_true,
+                   pn2_stream_t stream);
+
+/* y[rows][n] = act(x)[rows][kdim] * w[n][kdim]^T - center[n]  (bf16 in, fp32 accumulate, bf16 out), act =
+ * relu(x*scale+shift) when in_scale != NULL, center NULL = 0.  stats != NULL: stats[0..n) += column sums of y,
+ * stats[n..2n) += sums of y^2 (zeroed by the caller) -- the BatchNorm batch statistics (shift-invariant, so the
+ * centring only has to be undone in the running mean / eval shift).  kdim % 32 == 0, n % 8 == 0. */
 int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
-                     const float* in_shift, const void* w, void* y, int y_ld, float* stats, pn2_stream_t stream);
+                     const float* in_shift, const void* w, const float* center, void* y, int y_ld, float* stats,
+                     pn2_stream_t stream);
 
 /* Training-mode BatchNorm constants from the statistics: scale = gamma*rstd, shift = beta - mean*scale, plus
  * the running-statistics update of nn.BatchNorm (momentum, unbiased variance; conv_bias re-added to the mean
- * because the GEMM omits the bias BatchNorm cancels).  running_* / num_batches_tracked may be NULL. */
+ * because the GEMM omits
+ * what BatchNorm cancels; likewise the centring constant).  running_* / num_batches_tracked may be NULL. */
 int pn2_bn_finalize(int n, long long rows, const float* sums, const float* gamma, const float* beta,
-                    const float* conv_bias, float momentum, float eps, float* running_mean, float* running_var,
+                    const float* conv_bias, const float* center, float momentum, float eps, float* running_mean, float* running_var,
                     long long* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
                     pn2_stream_t stream);
 /* Eval-mode constants from the running statistics (conv bias folded in). */
-int pn2_bn_eval_affine(int n, const float* gamma, const float* beta, const float* conv_bias,
+int pn2_bn_eval_affine(int n, const float* gamma, const float* beta, const float* conv_bias, const float* center,
                        const float* running_mean, const float* running_var, float eps, float* scale, float* shift,
                        pn2_stream_t stream);
 
-/* BatchNorm+ReLU of the last layer and max over the k rows of each group: out_cm (B,C,S) fp32, optional bf16
- * rows (B*S, out_ld) and arg-max (B,S,C).  k == 1: plain BN+ReLU, rows -> channel-major (FP layers, head). */
+/* BatchNorm+ReLU of the last layer and max over the k rows of each group: out_cm (B,C,S) fp32, optional
+ * per-channel sums of the output (chan_sums[C], zeroed by the caller) and arg-max (B,S,C).
+ * k == 1: plain BN+ReLU, rows -> channel-major (FP layers, head). */
 int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld, const float* scale, const float* shift,
-                 float* out_cm, void* out_rows, int out_ld, int* argmax, pn2_stream_t stream);
+                 float* out_cm, float* chan_sums, int* argmax, pn2_stream_t stream);
 
 /* Backward of pool_fwd: dz[rows][c] = dout at the arg-max row where the ReLU is active, else 0; sums[0..c) +=
  * sum(dz), sums[c..2c) += sum(dz * xhat)  (zeroed by the caller). */
