@@ -31,7 +31,7 @@ SIGNATURES = {
     "pn2_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "pn2_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
     "pn2_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
-    "pn2_adam_step": [ctypes.c_longlong, _p, _p, _p, _p, _f, _f, _f, _f, _f, _i, _f, _p],
+    "pn2_adam_step": [ctypes.c_longlong, _p, _p, _p, _p, _f, _f, _f, _f, _f, _i, _p, _f, _p],
     # include/pn2b200_mlp.h
     "pn2_to_rows": [_i, _i, _i, _p, _p, _f, _p, _i, _p],
     "pn2_sa_build_rows": [_i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p],

@@ -40,6 +40,9 @@ namespace {
 
 constexpr int BM = 128, BK = 32, LDS = BK + 8;
 constexpr int kThreads = 256;
+// cp.async ring depth: forward GEMMs run 2 CTAs per SM with 3 stages, the backward ones (two A matrices
+// per chunk) 1 CTA per SM with 4 stages -- either way >= 32 KB of operand loads in flight per SM
+__host__ __device__ constexpr int nst_of(int amode) { return amode == 2 ? 4 : 3; }
 
 enum { A_PLAIN = 0, A_AFFINE = 1, A_BNBWD = 2 };
 
@@ -60,7 +63,7 @@ struct GemmArgs {
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 template <int BN, int AMODE, bool MASK>
-__global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_kernel(const GemmArgs p) {
     constexpr int WN = BN / 32, WM = 8 / WN, MF = BM / WM / 16;
     constexpr int CLD = BN + 8;
     constexpr int CPR = BN / 8;
@@ -68,11 +71,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
     constexpr int PASSES = BM / RPP;
     constexpr int NCOEF = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
     constexpr bool FWD = AMODE != A_BNBWD;  // forward GEMMs compute and store fp16, backward ones bf16
+    constexpr int NST = nst_of(AMODE);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint16_t* sA = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* sB = sA + 2 * BM * LDS;
-    uint16_t* sC = sB + 2 * BN * LDS;
+    uint16_t* sA = reinterpret_cast<uint16_t*>(smem_raw);          // [NST][BM][LDS]
+    uint16_t* sA1 = sA + NST * BM * LDS;                            // [NST][BM][LDS], BNBWD only
+    uint16_t* sB = sA1 + (AMODE == A_BNBWD ? NST * BM * LDS : 0);   // [NST][BN][LDS]
+    uint16_t* sC = sB + NST * BN * LDS;
     float* sCoef = reinterpret_cast<float*>(sC + BM * CLD);
     float* sPrev = sCoef + NCOEF * p.kdim;  // [4][BN], MASK only
     float* sCen = sPrev + (MASK ? 4 * BN : 0);  // [BN]
@@ -99,61 +104,74 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
     }
     __syncthreads();
 
+    // ---- operand pipeline: NST-deep ring of raw chunks filled by cp.async (deep enough to cover HBM
+    // latency with one CTA of 8 warps), A chunks transformed IN PLACE by the thread that copied them
     const int a_row = tid >> 2, a_col = (tid & 3) * 8;
-    uint4 ra0[2], ra1[2];
-    bool rvalid[2];
+    const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total = my_tiles * KT;
 
-    auto load_A = [&](long long tile, int kc) {
+    auto issue = [&](long long it) {
+        if (it < total) {
+            const long long tile = blockIdx.x + (it / KT) * gridDim.x;
+            const int kc = (int)(it % KT), st = (int)(it % NST);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const long long row = tile * BM + a_row + j * 64;
-            rvalid[j] = row < p.rows;
-            if (rvalid[j]) {
-                ra0[j] = ldg128(p.a0 + row * p.a0_ld + kc * BK + a_col);
-                if (AMODE == A_BNBWD) ra1[j] = ldg128(p.a1 + row * p.a1_ld + kc * BK + a_col);
+            for (int j = 0; j < 2; ++j) {
+                const int r = a_row + j * 64;
+                const long long row = tile * BM + r;
+                const bool ok = row < p.rows;
+                const long long rr = ok ? row : 0;
+                cp_async16(&sA[(st * BM + r) * LDS + a_col], p.a0 + rr * p.a0_ld + kc * BK + a_col, ok ? 16 : 0);
+                if (AMODE == A_BNBWD)
+                    cp_async16(&sA1[(st * BM + r) * LDS + a_col], p.a1 + rr * p.a1_ld + kc * BK + a_col, ok ? 16 : 0);
+            }
+            for (int i = tid; i < BN * 4; i += kThreads) {
+                const int r = i >> 2, ch = i & 3;
+                const int nrow = n0 + r;
+                const bool ok = nrow < p.n;
+                const uint16_t* src = p.b + (size_t)(ok ? nrow : 0) * p.kdim + kc * BK + ch * 8;
+                cp_async16(&sB[(st * BN + r) * LDS + ch * 8], src, ok ? 16 : 0);
             }
         }
+        cp_async_commit();  // always: keeps the group count in step with the iteration count
     };
-    auto store_A = [&](int st, int kc) {
+    auto transform_A = [&](long long it) {
+        if (AMODE == A_PLAIN) return;
+        const long long tile = blockIdx.x + (it / KT) * gridDim.x;
+        const int kc = (int)(it % KT), st = (int)(it % NST);
+        const int c = kc * BK + a_col;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
+            const int r = a_row + j * 64;
+            uint4* slot = reinterpret_cast<uint4*>(&sA[(st * BM + r) * LDS + a_col]);
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (rvalid[j]) {
-                if (AMODE == A_PLAIN) {
-                    v = ra0[j];
-                } else {
-                    const int c = kc * BK + a_col;
-                    const uint32_t* x0 = reinterpret_cast<const uint32_t*>(&ra0[j]);
-                    const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&ra1[j]);
-                    uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+            if (tile * BM + r < p.rows) {
+                const uint4 q0 = *slot;
+                const uint32_t* x0 = reinterpret_cast<const uint32_t*>(&q0);
+                uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+                if (AMODE == A_AFFINE) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float2 k0 = *reinterpret_cast<const float2*>(&sCoef[c + 2 * e]);
                         const float2 k1 = *reinterpret_cast<const float2*>(&sCoef[p.kdim + c + 2 * e]);
-                        if (AMODE == A_AFFINE) {
-                            const float2 a = h2_to_f2(x0[e]);
-                            o[e] = f2_to_h2(fmaxf(fmaf(a.x, k0.x, k1.x), 0.f), fmaxf(fmaf(a.y, k0.y, k1.y), 0.f));
-                        } else {
-                            const float2 a = bf2_to_f2(x0[e]);
-                            const float2 y = h2_to_f2(x1[e]);
-                            const float2 k2 = *reinterpret_cast<const float2*>(&sCoef[2 * p.kdim + c + 2 * e]);
-                            o[e] = f2_to_bf2(fmaf(k0.x, a.x, fmaf(k1.x, y.x, k2.x)), fmaf(k0.y, a.y, fmaf(k1.y, y.y, k2.y)));
-                        }
+                        const float2 a = h2_to_f2(x0[e]);
+                        o[e] = f2_to_h2(fmaxf(fmaf(a.x, k0.x, k1.x), 0.f), fmaxf(fmaf(a.y, k0.y, k1.y), 0.f));
+                    }
+                } else {
+                    const uint4 q1 = *reinterpret_cast<const uint4*>(&sA1[(st * BM + r) * LDS + a_col]);
+                    const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&q1);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 k0 = *reinterpret_cast<const float2*>(&sCoef[c + 2 * e]);
+                        const float2 k1 = *reinterpret_cast<const float2*>(&sCoef[p.kdim + c + 2 * e]);
+                        const float2 k2 = *reinterpret_cast<const float2*>(&sCoef[2 * p.kdim + c + 2 * e]);
+                        const float2 a = bf2_to_f2(x0[e]);
+                        const float2 y = h2_to_f2(x1[e]);
+                        o[e] = f2_to_bf2(fmaf(k0.x, a.x, fmaf(k1.x, y.x, k2.x)), fmaf(k0.y, a.y, fmaf(k1.y, y.y, k2.y)));
                     }
                 }
             }
-            *reinterpret_cast<uint4*>(&sA[(st * BM + a_row + j * 64) * LDS + a_col]) = v;
+            *slot = v;
         }
-    };
-    auto load_B = [&](int st, int kc) {
-        for (int i = tid; i < BN * 4; i += kThreads) {
-            const int r = i >> 2, ch = i & 3;
-            const int nrow = n0 + r;
-            const bool ok = nrow < p.n;
-            const uint16_t* src = p.b + (size_t)(ok ? nrow : 0) * p.kdim + kc * BK + ch * 8;
-            cp_async16(&sB[(st * BN + r) * LDS + ch * 8], src, ok ? 16 : 0);
-        }
-        cp_async_commit();
     };
 
     float acc[MF][4][4];
@@ -161,24 +179,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
 #pragma unroll
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
 
-    const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long total = my_tiles * KT;
-    if (total > 0) {
-        load_A(blockIdx.x, 0);
-        load_B(0, 0);
-    }
+    for (int s0 = 0; s0 < NST - 1; ++s0) issue(s0);
     for (long long it = 0; it < total; ++it) {
         const long long tile = blockIdx.x + (it / KT) * gridDim.x;
         const int kc = (int)(it % KT);
-        const int st = (int)(it & 1);
-        store_A(st, kc);
-        cp_async_wait_all();
-        __syncthreads();
-        if (it + 1 < total) {
-            const long long nit = it + 1;
-            load_A(blockIdx.x + (nit / KT) * gridDim.x, (int)(nit % KT));
-            load_B(st ^ 1, (int)(nit % KT));
-        }
+        const int st = (int)(it % NST);
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");  // this thread's copies of chunk `it` landed
+        transform_A(it);
+        __syncthreads();  // chunk `it` complete for everyone; everyone is done reading chunk it-1
+        issue(it + NST - 1);  // refills the buffer chunk it-1 used
         if (kc == 0) {
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf)
@@ -304,19 +313,27 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_rows_kernel(const GemmArgs p
 template <int BN, int AMODE, bool MASK>
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     constexpr int NCOEF = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
-    const size_t smem = (size_t)(2 * BM * LDS + 2 * BN * LDS + BM * (BN + 8)) * sizeof(uint16_t) +
+    constexpr int NST = nst_of(AMODE);
+    const size_t smem = (size_t)(NST * BM * LDS * (AMODE == A_BNBWD ? 2 : 1) + NST * BN * LDS + BM * (BN + 8)) *
+                            sizeof(uint16_t) +
                         (size_t)(NCOEF * a.kdim + (MASK ? 4 * BN : 0) + BN) * sizeof(float);
-    if (smem > 110 * 1024) return fail_arg("pn2_mlp_gemm", "reduction dimension too large for shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
+    constexpr size_t kMaxSmem = 200 * 1024;
+    if (smem > kMaxSmem) return fail_arg("pn2_mlp_gemm", "reduction dimension too large for shared memory");
+    static bool configured = false;
+    if (!configured) {
         PN2_CHECK(cudaFuncSetAttribute(gemm_rows_kernel<BN, AMODE, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       110 * 1024),
+                                       (int)kMaxSmem),
                   "gemm: cudaFuncSetAttribute");
-        configured = 110 * 1024;
+        configured = true;
     }
     const long long tiles = (a.rows + BM - 1) / BM;
     const int ny = (a.n + BN - 1) / BN;
-    long long gx = (2 * 148) / ny;
+    int occ = 1, sms = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_rows_kernel<BN, AMODE, MASK>, kThreads, smem);
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (occ < 1) occ = 1;
+    long long gx = ((long long)occ * sms) / ny;  // persistent: every CTA resident, tiles dealt round-robin
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
     dim3 grid((unsigned)gx, ny);
@@ -340,7 +357,7 @@ int check_common(const char* who, long long rows, int kdim, int n) {
 }
 
 // ------------------------------------------------------------------ wgrad -------------------
-constexpr int TN = 128, TK = 128, BR = 32, SLD = 128 + 8;
+constexpr int TN = 128, TK = 128, SLD = 128 + 8;
 
 struct WgradArgs {
     long long rows;
@@ -353,11 +370,18 @@ struct WgradArgs {
     float* dw; int dw_ld;
 };
 
+// Stage = WBR rows x 128 columns of dz, y (-> dY in place over dz) and x (-> X' in place), brought in
+// by cp.async WST stages deep; one CTA per SM, >= 100 KB of loads in flight.
+constexpr int WBR = 64, WST = 3;
+constexpr int kWgradSmem = WST * 3 * WBR * SLD * 2 + 5 * 128 * 4;
+
 template <bool AFFINE>
-__global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs p) {
-    __shared__ __align__(16) bf16 sD[2][BR][SLD];
-    __shared__ __align__(16) bf16 sX[2][BR][SLD];
-    __shared__ float sCo[5][128];
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t* sD = reinterpret_cast<uint16_t*>(smem_raw);  // [WST][WBR][SLD] dz -> dY (bf16)
+    uint16_t* sY = sD + WST * WBR * SLD;                   // [WST][WBR][SLD] y (fp16)
+    uint16_t* sX = sY + WST * WBR * SLD;                   // [WST][WBR][SLD] x (fp16) -> X' (bf16)
+    float* sCo = reinterpret_cast<float*>(sX + WST * WBR * SLD);  // [5][128]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0 = blockIdx.x * TN, k0 = blockIdx.y * TK;
@@ -369,65 +393,67 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs p) {
         } else if (AFFINE) {
             if (k0 + c < p.kp) v = (which == 3 ? p.in_scale : p.in_shift)[k0 + c];
         }
-        sCo[which][c] = v;
+        sCo[i] = v;
     }
     __syncthreads();
 
-    const int l_row = tid >> 4, l_col = (tid & 15) * 8;
-    const bool ncol_ok = n0 + l_col < p.n, kcol_ok = k0 + l_col < p.kp;
-    uint4 rd[2], ry[2], rx[2];
-    bool rvalid[2];
-    const long long chunks = (p.rows + BR - 1) / BR;
+    const long long chunks = (p.rows + WBR - 1) / WBR;
+    const long long mine = blockIdx.z < chunks ? (chunks - blockIdx.z + gridDim.z - 1) / gridDim.z : 0;
+    const int p_row = tid >> 4, p_col = (tid & 15) * 8;  // 4 pieces per matrix per thread: rows p_row + 16*j
+    const bool ncol_ok = n0 + p_col < p.n, kcol_ok = k0 + p_col < p.kp;
 
-    auto load = [&](long long ch) {
+    auto issue = [&](long long i) {
+        if (i < mine) {
+            const long long ch = blockIdx.z + i * gridDim.z;
+            const int st = (int)(i % WST);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const long long row = ch * BR + l_row + j * 16;
-            rvalid[j] = row < p.rows;
-            if (rvalid[j]) {
-                if (ncol_ok) {
-                    rd[j] = ldg128(p.dz + row * p.dz_ld + n0 + l_col);
-                    ry[j] = ldg128(p.y + row * p.y_ld + n0 + l_col);
-                }
-                if (kcol_ok) rx[j] = ldg128(p.x + row * p.x_ld + k0 + l_col);
+            for (int j = 0; j < 4; ++j) {
+                const int r = p_row + j * 16;
+                const long long row = ch * WBR + r;
+                const bool ok = row < p.rows;
+                const long long rr = ok ? row : 0;
+                const int off = (st * WBR + r) * SLD + p_col;
+                cp_async16(&sD[off], p.dz + rr * p.dz_ld + (ncol_ok ? n0 + p_col : 0), ok && ncol_ok ? 16 : 0);
+                cp_async16(&sY[off], p.y + rr * p.y_ld + (ncol_ok ? n0 + p_col : 0), ok && ncol_ok ? 16 : 0);
+                cp_async16(&sX[off], p.x + rr * p.x_ld + (kcol_ok ? k0 + p_col : 0), ok && kcol_ok ? 16 : 0);
             }
         }
+        cp_async_commit();
     };
-    auto store = [&](int st) {
+    auto transform = [&](long long i) {
+        const long long ch = blockIdx.z + i * gridDim.z;
+        const int st = (int)(i % WST);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 4; ++j) {
+            const int r = p_row + j * 16;
+            const bool ok = ch * WBR + r < p.rows;
+            const int off = (st * WBR + r) * SLD + p_col;
             uint4 vd = make_uint4(0u, 0u, 0u, 0u), vx = make_uint4(0u, 0u, 0u, 0u);
-            if (rvalid[j]) {
-                if (ncol_ok) {
-                    const uint32_t* a = reinterpret_cast<const uint32_t*>(&rd[j]);
-                    const uint32_t* b = reinterpret_cast<const uint32_t*>(&ry[j]);
-                    uint32_t* o = reinterpret_cast<uint32_t*>(&vd);
+            if (ok) {
+                const uint4 qd = *reinterpret_cast<const uint4*>(&sD[off]);
+                const uint4 qy = *reinterpret_cast<const uint4*>(&sY[off]);
+                const uint4 qx = *reinterpret_cast<const uint4*>(&sX[off]);
+                const uint32_t* a = reinterpret_cast<const uint32_t*>(&qd);
+                const uint32_t* b = reinterpret_cast<const uint32_t*>(&qy);
+                const uint32_t* x = reinterpret_cast<const uint32_t*>(&qx);
+                uint32_t* od = reinterpret_cast<uint32_t*>(&vd);
+                uint32_t* ox = reinterpret_cast<uint32_t*>(&vx);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 d = bf2_to_f2(a[e]), y = h2_to_f2(b[e]);
-                        const int c = l_col + 2 * e;
-                        o[e] = f2_to_bf2(fmaf(sCo[0][c], d.x, fmaf(sCo[1][c], y.x, sCo[2][c])),
-                                         fmaf(sCo[0][c + 1], d.y, fmaf(sCo[1][c + 1], y.y, sCo[2][c + 1])));
-                    }
-                }
-                if (kcol_ok) {
-                    // the forward operand is fp16; the gradient GEMM runs in bf16
-                    const uint32_t* a = reinterpret_cast<const uint32_t*>(&rx[j]);
-                    uint32_t* o = reinterpret_cast<uint32_t*>(&vx);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 x = h2_to_f2(a[e]);
-                        const int c = l_col + 2 * e;
-                        if (AFFINE)
-                            o[e] = f2_to_bf2(fmaxf(fmaf(x.x, sCo[3][c], sCo[4][c]), 0.f),
-                                             fmaxf(fmaf(x.y, sCo[3][c + 1], sCo[4][c + 1]), 0.f));
-                        else
-                            o[e] = f2_to_bf2(x.x, x.y);
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    const int c = p_col + 2 * e;
+                    const float2 d = bf2_to_f2(a[e]), y = h2_to_f2(b[e]), xv = h2_to_f2(x[e]);
+                    // columns beyond n / kp have zero coefficients and zero-filled data: they stay 0
+                    od[e] = f2_to_bf2(fmaf(sCo[c], d.x, fmaf(sCo[128 + c], y.x, sCo[256 + c])),
+                                      fmaf(sCo[c + 1], d.y, fmaf(sCo[128 + c + 1], y.y, sCo[256 + c + 1])));
+                    if (AFFINE)
+                        ox[e] = f2_to_bf2(fmaxf(fmaf(xv.x, sCo[384 + c], sCo[512 + c]), 0.f),
+                                          fmaxf(fmaf(xv.y, sCo[384 + c + 1], sCo[512 + c + 1]), 0.f));
+                    else
+                        ox[e] = f2_to_bf2(xv.x, xv.y);  // the gradient GEMM runs in bf16
                 }
             }
-            *reinterpret_cast<uint4*>(&sD[st][l_row + j * 16][l_col]) = vd;
-            *reinterpret_cast<uint4*>(&sX[st][l_row + j * 16][l_col]) = vx;
+            *reinterpret_cast<uint4*>(&sD[off]) = vd;
+            *reinterpret_cast<uint4*>(&sX[off]) = vx;
         }
     };
 
@@ -442,23 +468,25 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs p) {
             for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
 
     const int mi = lane >> 3, l7 = lane & 7;
-    long long ch = blockIdx.z;
-    if (ch < chunks) load(ch);
-    int st = 0;
-    for (; ch < chunks; ch += gridDim.z, st ^= 1) {
-        store(st);
+    for (int s0 = 0; s0 < WST - 1; ++s0) issue(s0);
+    for (long long i = 0; i < mine; ++i) {
+        const int st = (int)(i % WST);
+        asm volatile("cp.async.wait_group %0;" ::"n"(WST - 2) : "memory");
+        transform(i);
         __syncthreads();
-        if (ch + gridDim.z < chunks) load(ch + gridDim.z);
+        issue(i + WST - 1);
         if (warp_on) {
 #pragma unroll
-            for (int rs = 0; rs < BR; rs += 16) {
+            for (int rs = 0; rs < WBR; rs += 16) {
                 uint32_t af[4][4], bfr[2][4];
 #pragma unroll
                 for (int mf = 0; mf < 4; ++mf)
-                    ldsm_x4_trans(af[mf], smem_u32(&sD[st][rs + (mi >> 1) * 8 + l7][wn2 * 64 + mf * 16 + (mi & 1) * 8]));
+                    ldsm_x4_trans(af[mf], smem_u32(&sD[(st * WBR + rs + (mi >> 1) * 8 + l7) * SLD + wn2 * 64 + mf * 16 +
+                                                       (mi & 1) * 8]));
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb)
-                    ldsm_x4_trans(bfr[nb], smem_u32(&sX[st][rs + (mi & 1) * 8 + l7][wk * 32 + nb * 16 + (mi >> 1) * 8]));
+                    ldsm_x4_trans(bfr[nb], smem_u32(&sX[(st * WBR + rs + (mi & 1) * 8 + l7) * SLD + wk * 32 + nb * 16 +
+                                                        (mi >> 1) * 8]));
 #pragma unroll
                 for (int mf = 0; mf < 4; ++mf) {
                     if (n0 + wn2 * 64 + mf * 16 < p.n) {
@@ -469,8 +497,6 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const WgradArgs p) {
                 }
             }
         }
-        // the buffer written at the next iteration (st^1) was last read one iteration ago; the
-        // barrier above orders those reads before these writes
     }
     if (warp_on) {
         const int g = lane >> 2, t4 = lane & 3;
@@ -680,15 +706,23 @@ extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, con
     a.in_scale = in_scale; a.in_shift = in_shift;
     a.dw = dw; a.dw_ld = dw_ld;
     const int gx = (n + TN - 1) / TN, gy = (kp + TK - 1) / TK;
-    const long long chunks = (rows + BR - 1) / BR;
-    long long gz = (2 * 148) / (gx * gy);
+    const long long chunks = (rows + WBR - 1) / WBR;
+    long long gz = 148 / (gx * gy);  // one CTA per SM (shared memory), all resident
     if (gz < 1) gz = 1;
     if (gz > chunks) gz = chunks;
     dim3 grid(gx, gy, (unsigned)gz);
+    static bool configured = false;
+    if (!configured) {
+        PN2_CHECK(cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem),
+                  "wgrad: cudaFuncSetAttribute");
+        PN2_CHECK(cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem),
+                  "wgrad: cudaFuncSetAttribute");
+        configured = true;
+    }
     if (in_scale)
-        wgrad_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        wgrad_kernel<true><<<grid, kThreads, kWgradSmem, (cudaStream_t)stream>>>(a);
     else
-        wgrad_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        wgrad_kernel<false><<<grid, kThreads, kWgradSmem, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("wgrad_kernel");
     return 0;
 }

@@ -168,71 +168,94 @@ struct PoolArgs {
     float* sums;          // [2][C]
 };
 
-// grid (ceil(S/32), B); a warp owns groups s0+warp, +8, +16, +24; lanes own channel pairs of a 64-wide chunk
+// grid (s-tile slots, 64-channel chunks, B).  A CTA walks s-tiles of GT groups (stride gridDim.x); a warp
+// owns groups s0+warp, +8, ...; lanes own channel pairs of the chunk.  GT = 8 when there are few groups
+// (group-all, the 21 joints) so that the work still spreads over >= 256 CTAs.
+template <int GT>
 __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
-    __shared__ float tile[32][65];
+    __shared__ float tile[GT][65];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y, s0 = blockIdx.x * 32;
-    for (int c0 = 0; c0 < a.c; c0 += 64) {
-        const int ch = c0 + lane * 2;
-        const bool ok = ch < a.c;  // c is even (multiple of 8)
-        float sc0 = 0.f, sc1 = 0.f, sh0 = 0.f, sh1 = 0.f;
-        if (ok) { sc0 = a.scale[ch]; sc1 = a.scale[ch + 1]; sh0 = a.shift[ch]; sh1 = a.shift[ch + 1]; }
-        for (int gi = warp; gi < 32; gi += 8) {
+    const int b = blockIdx.z, c0 = blockIdx.y * 64;
+    const int ch = c0 + lane * 2;
+    const bool ok = ch < a.c;  // c is even (multiple of 8)
+    float sc0 = 0.f, sc1 = 0.f, sh0 = 0.f, sh1 = 0.f;
+    if (ok) { sc0 = a.scale[ch]; sc1 = a.scale[ch + 1]; sh0 = a.shift[ch]; sh1 = a.shift[ch + 1]; }
+    float csum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csum[j] = 0.f;
+    const int s_tiles = (a.s + GT - 1) / GT;
+    for (int t = blockIdx.x; t < s_tiles; t += gridDim.x) {
+        const int s0 = t * GT;
+        for (int gi = warp; gi < GT; gi += 8) {
             const int s = s0 + gi;
             float m0 = -1.f, m1 = -1.f;  // below every ReLU output: the first row always wins
             int i0 = 0, i1 = 0;
             if (ok && s < a.s) {
                 const act_t* yr = a.y + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch;
+#pragma unroll 4
                 for (int kk = 0; kk < a.k; ++kk) {
                     const float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
                     const float r0 = fmaxf(fmaf(v.x, sc0, sh0), 0.f), r1 = fmaxf(fmaf(v.y, sc1, sh1), 0.f);
                     if (r0 > m0) { m0 = r0; i0 = kk; }
                     if (r1 > m1) { m1 = r1; i1 = kk; }
                 }
-                const size_t g = (size_t)b * a.s + s;
-                if (a.argmax) *reinterpret_cast<int2*>(a.argmax + g * a.c + ch) = make_int2(i0, i1);
+                if (a.argmax) *reinterpret_cast<int2*>(a.argmax + ((size_t)b * a.s + s) * a.c + ch) = make_int2(i0, i1);
             }
             tile[gi][lane * 2] = m0;
             tile[gi][lane * 2 + 1] = m1;
         }
         __syncthreads();
-        for (int cc = warp; cc < 64; cc += 8) {
-            const int chn = c0 + cc, s = s0 + lane;
-            const bool okw = chn < a.c && s < a.s;
-            const float v = okw ? tile[lane][cc] : 0.f;
-            if (okw) a.out_cm[((size_t)b * a.c + chn) * a.s + s] = v;
-            if (a.chan_sums) {
-                float t = v;
+        if (lane < GT) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
-                if (lane == 0 && chn < a.c) atomicAdd(a.chan_sums + chn, t);
+            for (int j = 0; j < 8; ++j) {
+                const int cc = warp + j * 8, chn = c0 + cc, s = s0 + lane;
+                if (chn < a.c && s < a.s) {
+                    const float v = tile[lane][cc];
+                    a.out_cm[((size_t)b * a.c + chn) * a.s + s] = v;
+                    csum[j] += v;
+                }
             }
         }
         __syncthreads();
     }
+    if (a.chan_sums) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = csum[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+            const int chn = c0 + warp + j * 8;
+            if (lane == 0 && chn < a.c) atomicAdd(a.chan_sums + chn, t);
+        }
+    }
 }
 
+template <int GT>
 __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
-    __shared__ float tile[32][65];
+    __shared__ float tile[GT][65];
     __shared__ float red[8][2][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y, s0 = blockIdx.x * 32;
-    for (int c0 = 0; c0 < a.c; c0 += 64) {
-        for (int cc = warp; cc < 64; cc += 8) {
-            const int chn = c0 + cc, s = s0 + lane;
-            tile[lane][cc] = (chn < a.c && s < a.s) ? a.dout_cm[((size_t)b * a.c + chn) * a.s + s] : 0.f;
+    const int b = blockIdx.z, c0 = blockIdx.y * 64;
+    const int ch = c0 + lane * 2;
+    const bool ok = ch < a.c;
+    float sc0 = 0.f, sc1 = 0.f, sh0 = 0.f, sh1 = 0.f, mu0 = 0.f, mu1 = 0.f, rs0 = 0.f, rs1 = 0.f;
+    if (ok) {
+        sc0 = a.scale[ch]; sc1 = a.scale[ch + 1]; sh0 = a.shift[ch]; sh1 = a.shift[ch + 1];
+        mu0 = a.mean[ch]; mu1 = a.mean[ch + 1]; rs0 = a.rstd[ch]; rs1 = a.rstd[ch + 1];
+    }
+    float p1a = 0.f, p1b = 0.f, p2a = 0.f, p2b = 0.f;
+    const int s_tiles = (a.s + GT - 1) / GT;
+    for (int t = blockIdx.x; t < s_tiles; t += gridDim.x) {
+        const int s0 = t * GT;
+        if (lane < GT) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int cc = warp + j * 8, chn = c0 + cc, s = s0 + lane;
+                tile[lane][cc] = (chn < a.c && s < a.s) ? a.dout_cm[((size_t)b * a.c + chn) * a.s + s] : 0.f;
+            }
         }
         __syncthreads();
-        const int ch = c0 + lane * 2;
-        const bool ok = ch < a.c;
-        float sc0 = 0.f, sc1 = 0.f, sh0 = 0.f, sh1 = 0.f, mu0 = 0.f, mu1 = 0.f, rs0 = 0.f, rs1 = 0.f;
-        if (ok) {
-            sc0 = a.scale[ch]; sc1 = a.scale[ch + 1]; sh0 = a.shift[ch]; sh1 = a.shift[ch + 1];
-            mu0 = a.mean[ch]; mu1 = a.mean[ch + 1]; rs0 = a.rstd[ch]; rs1 = a.rstd[ch + 1];
-        }
-        float p1a = 0.f, p1b = 0.f, p2a = 0.f, p2b = 0.f;
-        for (int gi = warp; gi < 32; gi += 8) {
+        for (int gi = warp; gi < GT; gi += 8) {
             const int s = s0 + gi;
             if (!(ok && s < a.s)) continue;
             const size_t g = (size_t)b * a.s + s;
@@ -251,20 +274,26 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
                 *reinterpret_cast<uint32_t*>(dr + (size_t)kk * a.dz_ld) = f2_to_bf2(d0, d1);
             }
         }
-        red[warp][0][lane * 2] = p1a; red[warp][0][lane * 2 + 1] = p1b;
-        red[warp][1][lane * 2] = p2a; red[warp][1][lane * 2 + 1] = p2b;
-        __syncthreads();
-        if (threadIdx.x < 128) {
-            const int which = threadIdx.x >> 6, cc = threadIdx.x & 63;
-            if (c0 + cc < a.c) {
-                float t = 0.f;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) t += red[w][which][cc];
-                if (t != 0.f) atomicAdd(a.sums + (size_t)which * a.c + c0 + cc, t);
-            }
-        }
         __syncthreads();
     }
+    red[warp][0][lane * 2] = p1a; red[warp][0][lane * 2 + 1] = p1b;
+    red[warp][1][lane * 2] = p2a; red[warp][1][lane * 2 + 1] = p2b;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, cc = threadIdx.x & 63;
+        if (c0 + cc < a.c) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][which][cc];
+            if (t != 0.f) atomicAdd(a.sums + (size_t)which * a.c + c0 + cc, t);
+        }
+    }
+}
+
+template <int GT>
+void pool_grid(const PoolArgs& a, dim3& grid) {
+    const int s_tiles = (a.s + GT - 1) / GT;
+    grid = dim3(a.k == 1 ? (s_tiles < 8 ? s_tiles : 8) : s_tiles, (a.c + 63) / 64, a.b);
 }
 
 // ------------------------------------------------------------------ rows backward -----------
@@ -410,8 +439,14 @@ extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld,
     PoolArgs a{};
     a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
     a.out_cm = out_cm; a.chan_sums = chan_sums; a.argmax = argmax;
-    dim3 grid((s + 31) / 32, b);
-    pool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    dim3 grid;
+    if (k > 1 && s <= 64) {
+        pool_grid<8>(a, grid);
+        pool_fwd_kernel<8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        pool_grid<32>(a, grid);
+        pool_fwd_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    }
     PN2_CHECK_LAUNCH("pool_fwd_kernel");
     return 0;
 }
@@ -427,8 +462,14 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
     PoolArgs a{};
     a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
     a.mean = mean; a.rstd = rstd; a.argmax = const_cast<int*>(argmax); a.dout_cm = dout_cm; a.dz = (bf16*)dz; a.dz_ld = dz_ld; a.sums = sums;
-    dim3 grid((s + 31) / 32, b);
-    pool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    dim3 grid;
+    if (k > 1 && s <= 64) {
+        pool_grid<8>(a, grid);
+        pool_bwd_kernel<8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        pool_grid<32>(a, grid);
+        pool_bwd_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    }
     PN2_CHECK_LAUNCH("pool_bwd_kernel");
     return 0;
 }

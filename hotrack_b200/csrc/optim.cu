@@ -18,6 +18,8 @@ namespace {
 
 struct AdamArgs {
     float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, weight_decay, grad_scale;
+    float lr;
+    const int* step_dev;  // device-resident step counter (CUDA-graph replays): t = *step_dev + 1
 };
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a) {
@@ -28,9 +30,16 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
     p -= a.lr_over_bc1 * (m / denom);
 }
 
+__global__ void adam_advance_kernel(int* step_dev) { *step_dev += 1; }
+
 __global__ void __launch_bounds__(256)
 adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, AdamArgs a) {
+    if (a.step_dev) {  // bias corrections from the device-side counter (same for every thread)
+        const float t = (float)(*a.step_dev + 1);
+        a.lr_over_bc1 = a.lr / (1.f - powf(a.beta1, t));
+        a.inv_sqrt_bc2 = rsqrtf(1.f - powf(a.beta2, t));
+    }
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -56,23 +65,30 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
 
 extern "C" int pn2_adam_step(long long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                             float grad_scale, pn2_stream_t stream) {
+                             int* step_dev, float grad_scale, pn2_stream_t stream) {
     using namespace pn2;
-    if (n < 0 || step < 1) return fail_arg("pn2_adam_step", "n < 0 or step < 1");
+    if (n < 0 || (!step_dev && step < 1)) return fail_arg("pn2_adam_step", "n < 0 or step < 1");
     if (n == 0) return 0;
     if (!params || !grads || !exp_avg || !exp_avg_sq) return fail_arg("pn2_adam_step", "null pointer");
     if ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
          reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
         return fail_arg("pn2_adam_step", "buffers must be 16-byte aligned");
     AdamArgs a;
-    const double bc1 = 1.0 - std::pow((double)beta1, step), bc2 = 1.0 - std::pow((double)beta2, step);
+    const int t = step < 1 ? 1 : step;
+    const double bc1 = 1.0 - std::pow((double)beta1, t), bc2 = 1.0 - std::pow((double)beta2, t);
     a.lr_over_bc1 = (float)(lr / bc1);
     a.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+    a.lr = lr;
+    a.step_dev = step_dev;
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
     long long blocks = ((n >> 2) + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
     adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, a);
     PN2_CHECK_LAUNCH("adam_kernel");
+    if (step_dev) {
+        adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+        PN2_CHECK_LAUNCH("adam_advance_kernel");
+    }
     return 0;
 }

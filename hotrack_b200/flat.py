@@ -67,7 +67,12 @@ class FlatAdam:
         self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
         self.exp_avg = torch.zeros_like(flat.data)
         self.exp_avg_sq = torch.zeros_like(flat.data)
-        self.t = 0
+        # the step number lives on the device so that a captured step can be replayed (CUDA graphs)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=flat.data.device)
+
+    @property
+    def t(self):
+        return int(self.step_dev.item())
 
     def step(self, grad_scale=1.0):
         from . import _lib
@@ -75,10 +80,9 @@ class FlatAdam:
         f = self.flat
         if not f.data.is_cuda:
             raise RuntimeError("FlatAdam runs on CUDA tensors only (hotrack_b200 has no CPU path)")
-        self.t += 1
         _lib.call("pn2_adam_step", f.numel, f.data.data_ptr(), f.grad.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                  self.t, float(grad_scale), torch.cuda.current_stream().cuda_stream)
+                  0, self.step_dev.data_ptr(), float(grad_scale), torch.cuda.current_stream().cuda_stream)
 
 
 def shard_batch(n_items, rank, world):

@@ -101,9 +101,11 @@ int pn2_gather_points_grad(int b, int c, int n, int npoints, const float* grad_o
 /* Flat-buffer Adam step; replaces the torch.optim.Adam the reference trains with
  * (network/trainer.py:66-73).  All four buffers hold n fp32 values, 16-byte aligned.
  * Update rule = torch.optim.Adam with L2 weight decay; `step` counts from 1; the gradient is
- * multiplied by grad_scale first (1/world_size after a SUM all-reduce). */
+ * multiplied by grad_scale first (1/world_size after a SUM all-reduce).  step_dev != NULL: the step
+ * number lives on the device (t = *step_dev + 1, incremented after the update), so the call can be
+ * captured once in a CUDA graph and replayed; `step` is then ignored. */
 int pn2_adam_step(long long n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                  float beta1, float beta2, float eps, float weight_decay, int step, int* step_dev, float grad_scale,
                   pn2_stream_t stream);
 
 #ifdef __cplusplus
