@@ -600,7 +600,7 @@ __global__ void bn_eval_affine_kernel(int n, const float* __restrict__ gamma, co
 __global__ void bn_bwd_coefs_kernel(int n, float inv_rows, const float* __restrict__ sums,
                                     const float* __restrict__ gamma, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, float* cA, float* cB, float* cC, float* dgamma,
-                                    float* dbeta) {
+                                    float* dbeta, int accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const float s1 = sums[c], s2 = sums[n + c];
@@ -609,8 +609,13 @@ __global__ void bn_bwd_coefs_kernel(int n, float inv_rows, const float* __restri
     cA[c] = gr;
     cB[c] = -gr * m2 * rstd[c];
     cC[c] = gr * (m2 * rstd[c] * mean[c] - m1);
-    dgamma[c] = s2;
-    dbeta[c] = s1;
+    if (accumulate) {  // straight into the parameters' .grad (autograd's "+=" without an extra kernel)
+        dgamma[c] += s2;
+        dbeta[c] += s1;
+    } else {
+        dgamma[c] = s2;
+        dbeta[c] = s1;
+    }
 }
 
 __global__ void prep_weights_kernel(int n, int k_true, int kp, const float* __restrict__ w, act_t* __restrict__ wh,
@@ -755,12 +760,12 @@ extern "C" int pn2_bn_eval_affine(int n, const float* gamma, const float* beta, 
 
 extern "C" int pn2_bn_bwd_coefs(int n, long long rows, const float* sums, const float* gamma, const float* mean,
                                 const float* rstd, float* cA, float* cB, float* cC, float* dgamma, float* dbeta,
-                                pn2_stream_t stream) {
+                                int accumulate, pn2_stream_t stream) {
     if (n <= 0 || rows <= 0) return fail_arg("pn2_bn_bwd_coefs", "non-positive size");
     if (!sums || !gamma || !mean || !rstd || !cA || !cB || !cC || !dgamma || !dbeta)
         return fail_arg("pn2_bn_bwd_coefs", "null pointer");
     bn_bwd_coefs_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, (float)(1.0 / (double)rows), sums, gamma,
-                                                                          mean, rstd, cA, cB, cC, dgamma, dbeta);
+                                                                          mean, rstd, cA, cB, cC, dgamma, dbeta, accumulate);
     PN2_CHECK_LAUNCH("bn_bwd_coefs_kernel");
     return 0;
 }

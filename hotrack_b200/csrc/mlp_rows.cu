@@ -290,6 +290,110 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
     }
 }
 
+// ---- K == 1 (FP layers, head): BatchNorm+ReLU and rows -> channel-major transpose, wide accesses.
+// A CTA owns tiles of 32 consecutive rows x all C channels.  blockDim is a multiple of the C/8 16-byte
+// pieces of a row, so thread t always handles piece t % pieces (its 8 channels' constants and partial
+// sums live in registers) of rows t / pieces, + blockDim / pieces, ...: row reads/writes are fully
+// coalesced.  The shared tile is [32 rows][C + 1] with the column of channel ch permuted to
+// (ch % 8) * pieces + ch / 8, which makes both the piece-wise side and the channel-major side
+// (128-byte runs of 32 points per channel) bank-conflict free.
+constexpr int kRowTile = 32;
+
+__global__ void __launch_bounds__(kThreads) rows_to_cm_kernel(const PoolArgs a) {
+    extern __shared__ __align__(16) float tile_dyn[];  // [32][C + 1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.y;
+    const int pieces = a.c >> 3, ldt = a.c + 1;
+    const int pc = tid % pieces, r0 = tid / pieces, rstep = blockDim.x / pieces;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = a.scale[pc * 8 + e]; sh[e] = a.shift[pc * 8 + e]; }
+    const int s_tiles = (a.s + kRowTile - 1) / kRowTile;
+    for (int t = blockIdx.x; t < s_tiles; t += gridDim.x) {
+        const int s0 = t * kRowTile;
+        for (int r = r0; r < kRowTile; r += rstep) {
+            if (s0 + r < a.s) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.y + ((size_t)b * a.s + s0 + r) * a.y_ld + pc * 8));
+                const uint32_t* v = reinterpret_cast<const uint32_t*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = h2_to_f2(v[e]);
+                    tile_dyn[r * ldt + (2 * e) * pieces + pc] = fmaxf(fmaf(f.x, sc[2 * e], sh[2 * e]), 0.f);
+                    tile_dyn[r * ldt + (2 * e + 1) * pieces + pc] = fmaxf(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]), 0.f);
+                }
+            }
+        }
+        __syncthreads();
+        for (int ch = warp; ch < a.c; ch += nwarps)
+            if (s0 + lane < a.s)
+                a.out_cm[((size_t)b * a.c + ch) * a.s + s0 + lane] = tile_dyn[lane * ldt + (ch & 7) * pieces + (ch >> 3)];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) cm_to_rows_bwd_kernel(const PoolArgs a) {
+    extern __shared__ __align__(16) float tile_dyn[];  // [32][C + 1] dout tile
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.y;
+    const int pieces = a.c >> 3, ldt = a.c + 1;
+    const int pc = tid % pieces, r0 = tid / pieces, rstep = blockDim.x / pieces;
+    float sc[8], sh[8], mu[8], rs[8], p1[8], p2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int ch = pc * 8 + e;
+        sc[e] = a.scale[ch]; sh[e] = a.shift[ch]; mu[e] = a.mean[ch]; rs[e] = a.rstd[ch];
+        p1[e] = p2[e] = 0.f;
+    }
+    const int s_tiles = (a.s + kRowTile - 1) / kRowTile;
+    for (int t = blockIdx.x; t < s_tiles; t += gridDim.x) {
+        const int s0 = t * kRowTile;
+        // channel-major side: 8 independent 128-byte runs in flight per warp (c is a multiple of 8)
+        for (int ch0 = warp * 8; ch0 < a.c; ch0 += nwarps * 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (s0 + lane < a.s) ? __ldg(a.dout_cm + ((size_t)b * a.c + ch0 + j) * a.s + s0 + lane) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tile_dyn[lane * ldt + j * pieces + (ch0 >> 3)] = v[j];
+        }
+        __syncthreads();
+        for (int r = r0; r < kRowTile; r += rstep) {
+            if (s0 + r < a.s) {
+                const size_t row = (size_t)b * a.s + s0 + r;
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.y + row * a.y_ld + pc * 8));
+                const uint32_t* v = reinterpret_cast<const uint32_t*>(&q);
+                uint4 o;
+                uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = h2_to_f2(v[e]);
+                    float d0 = tile_dyn[r * ldt + (2 * e) * pieces + pc], d1 = tile_dyn[r * ldt + (2 * e + 1) * pieces + pc];
+                    d0 = fmaf(f.x, sc[2 * e], sh[2 * e]) > 0.f ? d0 : 0.f;
+                    d1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]) > 0.f ? d1 : 0.f;
+                    p1[2 * e] += d0; p1[2 * e + 1] += d1;
+                    p2[2 * e] = fmaf(d0, (f.x - mu[2 * e]) * rs[2 * e], p2[2 * e]);
+                    p2[2 * e + 1] = fmaf(d1, (f.y - mu[2 * e + 1]) * rs[2 * e + 1], p2[2 * e + 1]);
+                    ov[e] = f2_to_bf2(d0, d1);
+                }
+                *reinterpret_cast<uint4*>(a.dz + row * a.dz_ld + pc * 8) = o;
+            }
+        }
+        __syncthreads();
+    }
+    // rstep threads share a piece: combine them through shared memory, then one atomic per channel per CTA
+    float* red = tile_dyn;  // [rstep][2][C]
+    for (int e = 0; e < 8; ++e) {
+        red[(r0 * 2 + 0) * a.c + pc * 8 + e] = p1[e];
+        red[(r0 * 2 + 1) * a.c + pc * 8 + e] = p2[e];
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * a.c; i += blockDim.x) {
+        float tsum = 0.f;
+        for (int j = 0; j < rstep; ++j) tsum += red[j * 2 * a.c + i];
+        if (tsum != 0.f) atomicAdd(a.sums + i, tsum);
+    }
+}
+
 template <int GT>
 void pool_grid(const PoolArgs& a, dim3& grid) {
     const int s_tiles = (a.s + GT - 1) / GT;
@@ -440,7 +544,21 @@ extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld,
     a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
     a.out_cm = out_cm; a.chan_sums = chan_sums; a.argmax = argmax;
     dim3 grid;
-    if (k > 1 && s <= 64) {
+    if (k == 1 && !chan_sums && c <= 1024) {
+        const int s_tiles = (s + kRowTile - 1) / kRowTile;
+        const size_t smem = (size_t)kRowTile * (c + 1) * sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            PN2_CHECK(cudaFuncSetAttribute(rows_to_cm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kRowTile * 1025 * 4),
+                      "rows_to_cm: cudaFuncSetAttribute");
+            configured = true;
+        }
+        const int pieces = c / 8;
+        const int threads = pieces >= kThreads ? pieces : (kThreads / pieces) * pieces;  // multiple of pieces
+        grid = dim3(s_tiles < 32 ? s_tiles : 32, b);
+        rows_to_cm_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    } else if (k > 1 && s <= 64) {
         pool_grid<8>(a, grid);
         pool_fwd_kernel<8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
     } else {
@@ -463,7 +581,22 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
     a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
     a.mean = mean; a.rstd = rstd; a.argmax = const_cast<int*>(argmax); a.dout_cm = dout_cm; a.dz = (bf16*)dz; a.dz_ld = dz_ld; a.sums = sums;
     dim3 grid;
-    if (k > 1 && s <= 64) {
+    if (k == 1 && c <= 1024) {
+        const int s_tiles = (s + kRowTile - 1) / kRowTile;
+        const size_t smem = (size_t)kRowTile * (c + 1) * sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            PN2_CHECK(cudaFuncSetAttribute(cm_to_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kRowTile * 1025 * 4),
+                      "cm_to_rows_bwd: cudaFuncSetAttribute");
+            configured = true;
+        }
+        const int pieces = c / 8;
+        const int threads = pieces >= kThreads ? pieces : (kThreads / pieces) * pieces;
+        const size_t red = (size_t)2 * threads * 8 * sizeof(float);  // the final [rstep][2][C] reduction reuses the tile
+        grid = dim3(s_tiles < 32 ? s_tiles : 32, b);
+        cm_to_rows_bwd_kernel<<<grid, threads, smem > red ? smem : red, (cudaStream_t)stream>>>(a);
+    } else if (k > 1 && s <= 64) {
         pool_grid<8>(a, grid);
         pool_bwd_kernel<8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
     } else {

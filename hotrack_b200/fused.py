@@ -98,7 +98,7 @@ class _MlpStack(Function):
        kind 'dense' : a = x (B,C,N)                                                  -> (B,Cout,N)"""
 
     @staticmethod
-    def forward(ctx, kind, meta, bns, training, a, b, *params):
+    def forward(ctx, kind, meta, bns, pobjs, training, a, b, *params):
         dev = params[0].device
         st = _stream()
         nl = len(params) // 4
@@ -165,6 +165,10 @@ class _MlpStack(Function):
                 if in_off is None:
                     in_off = torch.zeros(kp, dtype=torch.float32, device=dev)
                 in_off[start:start + r.c] = r.offset
+        # one zero-filled arena for every accumulator of the forward pass (one memset per stack)
+        widths = [params[4 * l].shape[0] for l in range(nl)]
+        arena = torch.zeros(2 * sum(widths) + widths[-1], dtype=torch.float32, device=dev)
+        a_off = 0
         for l in range(nl):
             w, bias, gamma, beta = params[4 * l: 4 * l + 4]
             bn = bns[l]
@@ -181,7 +185,8 @@ class _MlpStack(Function):
             _lib.call("pn2_mlp_center", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
                       _p(in_off) if l == 0 else 0, cen.data_ptr(), cen_true.data_ptr(), st)
             if training:
-                stats = torch.zeros(2, L.cout, dtype=torch.float32, device=dev)
+                stats = arena[a_off:a_off + 2 * L.cout]
+                a_off += 2 * L.cout
                 _lib.call("pn2_mlp_gemm_fwd", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
                           cen.data_ptr(), L.y.data_ptr(), L.cout, stats.data_ptr(), st)
                 track = bn.track_running_stats and bn.running_mean is not None
@@ -204,7 +209,7 @@ class _MlpStack(Function):
         out = torch.empty(B, C, groups, dtype=torch.float32, device=dev)
         chan_sums = argmax = None
         if pool_k > 1:
-            chan_sums = torch.zeros(C, dtype=torch.float32, device=dev)
+            chan_sums = arena[2 * sum(widths):]
             argmax = torch.empty(B, groups, C, dtype=torch.int32, device=dev) if training else None
         _lib.call("pn2_pool_fwd", B, groups, pool_k, C, last.y.data_ptr(), C, last.scale.data_ptr(),
                   last.shift.data_ptr(), out.data_ptr(), _p(chan_sums), _p(argmax), st)
@@ -223,6 +228,7 @@ class _MlpStack(Function):
         ctx.a_shape = None if a is None else tuple(a.shape)
         ctx.b_shape = None if b is None else tuple(b.shape)
         ctx.gammas = [params[4 * l + 2] for l in range(nl)]
+        ctx.pobjs = pobjs
         ctx.set_materialize_grads(False)
         return out
 
@@ -231,7 +237,7 @@ class _MlpStack(Function):
         nl = len(ctx.layers)
         none_params = [None] * (4 * nl)
         if dout is None:
-            return (None, None, None, None, None, None, *none_params)
+            return (None, None, None, None, None, None, None, *none_params)
         if not ctx.training:
             raise NotImplementedError("fused engine: backward through eval-mode BatchNorm is not implemented; "
                                       "use engine 'ops' for that")
@@ -243,37 +249,51 @@ class _MlpStack(Function):
         last = layers[-1]
         C = last.cout
         dz = torch.empty(R, C, dtype=_BF16, device=dev)
-        sums = torch.zeros(2, C, dtype=torch.float32, device=dev)
+        # one zero-filled arena for the BatchNorm-backward sums of every layer
+        arena = torch.zeros(2 * sum(L.cout for L in layers), dtype=torch.float32, device=dev)
+        a_off = 2 * C
+        sums = arena[:a_off]
         _lib.call("pn2_pool_bwd", B, groups, pool_k, C, dout.data_ptr(), last.y.data_ptr(), C, last.scale.data_ptr(),
                   last.shift.data_ptr(), last.mean.data_ptr(), last.rstd.data_ptr(), _p(ctx.argmax), dz.data_ptr(), C,
                   sums.data_ptr(), st)
-        need_a = ctx.needs_input_grad[4] and ctx.a_shape is not None
-        need_b = ctx.needs_input_grad[5] and ctx.b_shape is not None
+        need_a = ctx.needs_input_grad[5] and ctx.a_shape is not None
+        need_b = ctx.needs_input_grad[6] and ctx.b_shape is not None
         grads = [None] * (4 * nl)
         dx0 = None
         for l in range(nl - 1, -1, -1):
             L = layers[l]
+            # Parameter gradients go STRAIGHT into the parameters' .grad when those exist as plain fp32 buffers
+            # (FlatParams keeps them so): autograd's per-parameter "+=" kernels disappear.  Otherwise they
+            # are returned to autograd the usual way.
+            pw, pb, pg, pbt = ctx.pobjs[4 * l: 4 * l + 4]
+            direct = all(q.grad is not None and q.grad.is_contiguous() and q.grad.dtype == torch.float32
+                         for q in (pw, pg, pbt))
             coefs = torch.empty(5, L.cout, dtype=torch.float32, device=dev)
             _lib.call("pn2_bn_bwd_coefs", L.cout, R, sums.data_ptr(), ctx.gammas[l].data_ptr(), L.mean.data_ptr(),
                       L.rstd.data_ptr(), coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(),
-                      coefs[3].data_ptr(), coefs[4].data_ptr(), st)
+                      pg.grad.data_ptr() if direct else coefs[3].data_ptr(),
+                      pbt.grad.data_ptr() if direct else coefs[4].data_ptr(), 1 if direct else 0, st)
             if l > 0:
                 P = layers[l - 1]
                 x, x_ld, xs, xh = P.y, P.cout, P.scale, P.shift
             else:
                 x, x_ld, xs, xh = ctx.in0
-            dw = torch.zeros(L.cout, L.cin, dtype=torch.float32, device=dev)
+            dw = None if direct else torch.zeros(L.cout, L.cin, dtype=torch.float32, device=dev)
             _lib.call("pn2_mlp_gemm_wgrad", R, L.cout, L.kp, L.cin, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
                       coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), x.data_ptr(), x_ld, _p(xs), _p(xh),
-                      dw.data_ptr(), L.cin, st)
-            grads[4 * l] = dw
-            grads[4 * l + 1] = torch.zeros(L.cout, dtype=torch.float32, device=dev)  # bias: cancelled by BN
-            grads[4 * l + 2] = coefs[3]
-            grads[4 * l + 3] = coefs[4]
+                      pw.grad.data_ptr() if direct else dw.data_ptr(), L.cin, st)
+            if not direct:
+                grads[4 * l] = dw
+                grads[4 * l + 2] = coefs[3]
+                grads[4 * l + 3] = coefs[4]
+            if not direct or pb.grad is None:
+                # conv bias: cancelled by train-mode BatchNorm, gradient exactly zero
+                grads[4 * l + 1] = torch.zeros(L.cout, dtype=torch.float32, device=dev)
             if l > 0:
                 P = layers[l - 1]
                 dzp = torch.empty(R, P.cout, dtype=_BF16, device=dev)
-                sums_p = torch.zeros(2, P.cout, dtype=torch.float32, device=dev)
+                sums_p = arena[a_off:a_off + 2 * P.cout]
+                a_off += 2 * P.cout
                 _lib.call("pn2_mlp_gemm_dgrad", R, L.cout, P.cout, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
                           coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), L.wt.data_ptr(),
                           P.y.data_ptr(), P.cout, P.scale.data_ptr(), P.shift.data_ptr(), P.mean.data_ptr(),
@@ -315,7 +335,7 @@ class _MlpStack(Function):
             else:
                 Bc, Cc, Nc = ctx.a_shape
                 da = dx0.view(Bc, Nc, -1)[:, :, :Cc].transpose(1, 2).float().contiguous()
-        return (None, None, None, None, da, db, *grads)
+        return (None, None, None, None, None, da, db, *grads)
 
 
 def _params(convs, bns):
@@ -337,7 +357,7 @@ def _run(kind, meta, convs, bns, training, a, b):
     views = []
     for i, p in enumerate(ps):
         views.append(p.view(p.shape[0], -1) if i % 4 == 0 else p)  # conv weight (Cout,Cin,1[,1]) -> (Cout,Cin)
-    out = _MlpStack.apply(kind, meta, list(bns), bool(training), a, b, *views)
+    out = _MlpStack.apply(kind, meta, list(bns), ps, bool(training), a, b, *views)
     rows, _MlpStack.last_rows = _MlpStack.last_rows, None  # set by forward (single-threaded hand-over)
     return attach_rows(out, rows) if rows is not None else out
 

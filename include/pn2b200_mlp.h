@@ -83,9 +83,10 @@ int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const void* y
                  const float* shift, const float* mean, const float* rstd, const int* argmax, void* dz, int dz_ld,
                  float* sums, pn2_stream_t stream);
 
-/* BatchNorm-backward per-channel coefficients: dY = cA*dz + cB*y + cC; dgamma = sums[c..2c), dbeta = sums[0..c). */
+/* BatchNorm-backward per-channel coefficients: dY = cA*dz + cB*y + cC; dgamma = sums[c..2c), dbeta = sums[0..c)
+ * (accumulate != 0: added to the existing contents -- the parameters' .grad buffers). */
 int pn2_bn_bwd_coefs(int n, long long rows, const float* sums, const float* gamma, const float* mean,
-                     const float* rstd, float* cA, float* cB, float* cC, float* dgamma, float* dbeta,
+                     const float* rstd, float* cA, float* cB, float* cC, float* dgamma, float* dbeta, int accumulate,
                      pn2_stream_t stream);
 
 /* dz_prev[rows][k_out] = dY[rows][n_red] * wt[k_out][n_red]^T with dY = cA*dz + cB*y + cC.  y_prev != NULL:

@@ -247,12 +247,19 @@ def test_whole_path_fused_vs_ops(cuda, train):
     for e in outs:
         sum(v.square().mean() for v in outs[e][:3]).backward()
     # The backward pass is as ill-conditioned as the forward one (BatchNorm-backward subtracts batch means of
-    # nearly identical clouds): the whole gradient must agree to a few percent, single tensors deep in the
-    # network (SA1's 96 first-layer weights) only in direction.
-    ga = torch.cat([p.grad.flatten() for n, p in models["ops"].named_parameters() if not (n.endswith(".bias") and "conv" in n)])
-    gb = torch.cat([p.grad.flatten() for n, p in models["fused"].named_parameters() if not (n.endswith(".bias") and "conv" in n)])
-    assert _rel(gb, ga) < 0.08, "whole-gradient rel %.3g" % _rel(gb, ga)
-    _grads_close(models["ops"], models["fused"], 0.6)
+    # nearly identical clouds) and errors grow towards the input: the typical tensor agrees to a few percent,
+    # the deepest one (SA1's 96 first-layer weights, the end of a 28-layer backward chain) only in direction.
+    errs = {}
+    for (n1, p1), (n2, p2) in zip(models["ops"].named_parameters(), models["fused"].named_parameters()):
+        if n1.endswith(".bias") and "conv" in n1:
+            continue
+        errs[n1] = _rel(p2.grad, p1.grad)
+    v = sorted(errs.values())
+    assert v[len(v) // 2] < 0.05, "median parameter-gradient rel error %.3g" % v[len(v) // 2]
+    assert v[-1] < 0.6, "worst parameter gradient: %s" % max(errs.items(), key=lambda kv: kv[1])
+    cos = torch.nn.functional.cosine_similarity(models["ops"].bhand.sa1.conv_blocks[0][0].weight.grad.flatten(),
+                                                models["fused"].bhand.sa1.conv_blocks[0][0].weight.grad.flatten(), dim=0)
+    assert cos > 0.85
     for (n1, b1), (n2, b2) in zip(models["ops"].named_buffers(), models["fused"].named_buffers()):
         if b1.dtype.is_floating_point:
             assert _rel(b2, b1) < 2e-2, n1
