@@ -38,11 +38,8 @@
 namespace pn2 {
 namespace {
 
-constexpr int BM = 128, BK = 32, LDS = BK + 8;
+constexpr int BM = 128;
 constexpr int kThreads = 256;
-// cp.async ring depth: forward GEMMs run 2 CTAs per SM with 3 stages, the backward ones (two A matrices
-// per chunk) 1 CTA per SM with 4 stages -- either way >= 32 KB of operand loads in flight per SM
-__host__ __device__ constexpr int nst_of(int amode) { return amode == 2 ? 4 : 3; }
 
 enum { A_PLAIN = 0, A_AFFINE = 1, A_BNBWD = 2 };
 
@@ -58,37 +55,75 @@ struct GemmArgs {
     float* sums;
     const uint16_t* yp; int yp_ld;   // MASK: previous layer's y (fp16)
     const float *p_scale, *p_shift, *p_mean, *p_rstd;
+    int nst, bres;                   // set by the launcher
 };
 
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-template <int BN, int AMODE, bool MASK>
-__global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_kernel(const GemmArgs p) {
-    constexpr int WN = BN / 32, WM = 8 / WN, MF = BM / WM / 16;
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_ring(int nst) {  // all but the nst-2 most recent groups
+    switch (nst) {
+        case 2: cp_async_wait<0>(); break;
+        case 3: cp_async_wait<1>(); break;
+        case 4: cp_async_wait<2>(); break;
+        case 5: cp_async_wait<3>(); break;
+        default: cp_async_wait<4>(); break;
+    }
+}
+
+// BKT = K-chunk width (32 or 64 elements: 64 / 128 bytes of every row per chunk).  p.nst = ring depth and
+// p.bres = "B slab resident in shared memory" are chosen by the launcher from the shared-memory budget.
+// 16 warps per CTA (8 for the 32-column tile): the kernel is one CTA per SM (shared-memory ring), so the
+// warp count is what hides instruction and shared-memory latency.
+__host__ __device__ constexpr int gemm_threads(int bn) { return bn == 32 ? 256 : 512; }
+
+template <int BN, int BKT, int AMODE, bool MASK>
+__global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_rows_kernel(const GemmArgs p) {
+    constexpr int kThreads = gemm_threads(BN);
+    constexpr int NW = kThreads / 32;
+    constexpr int WN = BN / 32, WM = NW / WN, MF = BM / WM / 16;
+    static_assert(MF >= 1, "warp tile must hold at least one 16-row fragment");
     constexpr int CLD = BN + 8;
     constexpr int CPR = BN / 8;
     constexpr int RPP = kThreads / CPR;
     constexpr int PASSES = BM / RPP;
     constexpr int NCOEF = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
     constexpr bool FWD = AMODE != A_BNBWD;  // forward GEMMs compute and store fp16, backward ones bf16
-    constexpr int NST = nst_of(AMODE);
+    constexpr int LDK = BKT + 8;            // shared-memory row stride of a chunk (odd multiple of 16 bytes)
+    constexpr int PPR = BKT / 8;            // 16-byte pieces per row per chunk
+    constexpr int APT = BM * PPR / kThreads;
+    constexpr int ASZ = BM * LDK, BSZ = BN * LDK;
+
+    const int nst = p.nst;
+    const bool bres = p.bres != 0;
+    const int ldb = bres ? p.kdim + 8 : LDK;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint16_t* sA = reinterpret_cast<uint16_t*>(smem_raw);          // [NST][BM][LDS]
-    uint16_t* sA1 = sA + NST * BM * LDS;                            // [NST][BM][LDS], BNBWD only
-    uint16_t* sB = sA1 + (AMODE == A_BNBWD ? NST * BM * LDS : 0);   // [NST][BN][LDS]
-    uint16_t* sC = sB + NST * BN * LDS;
+    uint16_t* sA = reinterpret_cast<uint16_t*>(smem_raw);               // [nst][BM][LDK]
+    uint16_t* sA1 = sA + nst * ASZ;                                      // [nst][BM][LDK], BNBWD only
+    uint16_t* sB = sA1 + (AMODE == A_BNBWD ? nst * ASZ : 0);             // [nst][BN][LDK] or [BN][kdim+8]
+    uint16_t* sC = sB + (bres ? BN * (p.kdim + 8) : nst * BSZ);          // [BM][CLD]
     float* sCoef = reinterpret_cast<float*>(sC + BM * CLD);
-    float* sPrev = sCoef + NCOEF * p.kdim;  // [4][BN], MASK only
+    float* sPrev = sCoef + NCOEF * p.kdim;      // [4][BN], MASK only
     float* sCen = sPrev + (MASK ? 4 * BN : 0);  // [BN]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t4 = lane & 3;
     const int n0 = blockIdx.y * BN;
-    const int KT = p.kdim / BK;
+    const int KT = p.kdim / BKT;
     const long long tiles = (p.rows + BM - 1) / BM;
 
+    if (bres) {  // the whole weight slab of this column tile, once per CTA (oldest cp.async group)
+        const int ppr = p.kdim >> 3;
+        for (int i = tid; i < BN * ppr; i += kThreads) {
+            const int r = i / ppr, ch = i - r * ppr;
+            const bool ok = n0 + r < p.n;
+            cp_async16(&sB[r * ldb + ch * 8], p.b + (size_t)(ok ? n0 + r : 0) * p.kdim + ch * 8, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    }
     for (int i = tid; i < NCOEF * p.kdim; i += kThreads) {
         const int which = i / p.kdim, c = i - which * p.kdim;
         const float* src = which == 0 ? p.c0 : (which == 1 ? p.c1 : p.c2);
@@ -104,69 +139,81 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
     }
     __syncthreads();
 
-    // ---- operand pipeline: NST-deep ring of raw chunks filled by cp.async (deep enough to cover HBM
-    // latency with one CTA of 8 warps), A chunks transformed IN PLACE by the thread that copied them
-    const int a_row = tid >> 2, a_col = (tid & 3) * 8;
+    // ---- operand pipeline: ring of raw chunks filled by cp.async, deep enough to keep >= 50 KB of HBM
+    // loads in flight per SM; A chunks are transformed IN PLACE by the thread that copied them
     const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long total = my_tiles * KT;
 
-    auto issue = [&](long long it) {
-        if (it < total) {
-            const long long tile = blockIdx.x + (it / KT) * gridDim.x;
-            const int kc = (int)(it % KT), st = (int)(it % NST);
+    // issue-side cursor (chunk index, tile, K chunk, ring slot), advanced incrementally: no divisions in the loop
+    long long is_it = 0, is_tile = blockIdx.x;
+    int is_kc = 0, is_st = 0;
+    auto issue = [&]() {
+        if (is_it < total) {
+            const long long tile = is_tile;
+            const int kc = is_kc, st = is_st;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int r = a_row + j * 64;
+            for (int j = 0; j < APT; ++j) {
+                const int q = tid + j * kThreads;
+                const int r = q / PPR, col = (q % PPR) * 8;
                 const long long row = tile * BM + r;
                 const bool ok = row < p.rows;
                 const long long rr = ok ? row : 0;
-                cp_async16(&sA[(st * BM + r) * LDS + a_col], p.a0 + rr * p.a0_ld + kc * BK + a_col, ok ? 16 : 0);
+                cp_async16(&sA[st * ASZ + r * LDK + col], p.a0 + rr * p.a0_ld + kc * BKT + col, ok ? 16 : 0);
                 if (AMODE == A_BNBWD)
-                    cp_async16(&sA1[(st * BM + r) * LDS + a_col], p.a1 + rr * p.a1_ld + kc * BK + a_col, ok ? 16 : 0);
+                    cp_async16(&sA1[st * ASZ + r * LDK + col], p.a1 + rr * p.a1_ld + kc * BKT + col, ok ? 16 : 0);
             }
-            for (int i = tid; i < BN * 4; i += kThreads) {
-                const int r = i >> 2, ch = i & 3;
-                const int nrow = n0 + r;
-                const bool ok = nrow < p.n;
-                const uint16_t* src = p.b + (size_t)(ok ? nrow : 0) * p.kdim + kc * BK + ch * 8;
-                cp_async16(&sB[(st * BN + r) * LDS + ch * 8], src, ok ? 16 : 0);
+            if (!bres) {
+                for (int i = tid; i < BN * PPR; i += kThreads) {
+                    const int r = i / PPR, ch = i % PPR;
+                    const bool ok = n0 + r < p.n;
+                    cp_async16(&sB[st * BSZ + r * LDK + ch * 8],
+                               p.b + (size_t)(ok ? n0 + r : 0) * p.kdim + kc * BKT + ch * 8, ok ? 16 : 0);
+                }
             }
+            ++is_it;
+            if (++is_kc == KT) { is_kc = 0; is_tile += gridDim.x; }
+            if (++is_st == nst) is_st = 0;
         }
         cp_async_commit();  // always: keeps the group count in step with the iteration count
     };
-    auto transform_A = [&](long long it) {
+    auto transform_A = [&](long long tile, int kc, int st) {
         if (AMODE == A_PLAIN) return;
-        const long long tile = blockIdx.x + (it / KT) * gridDim.x;
-        const int kc = (int)(it % KT), st = (int)(it % NST);
-        const int c = kc * BK + a_col;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int r = a_row + j * 64;
-            uint4* slot = reinterpret_cast<uint4*>(&sA[(st * BM + r) * LDS + a_col]);
+        for (int j = 0; j < APT; ++j) {
+            const int q = tid + j * kThreads;
+            const int r = q / PPR, col = (q % PPR) * 8;
+            const int c = kc * BKT + col;
+            uint4* slot = reinterpret_cast<uint4*>(&sA[st * ASZ + r * LDK + col]);
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (tile * BM + r < p.rows) {
                 const uint4 q0 = *slot;
                 const uint32_t* x0 = reinterpret_cast<const uint32_t*>(&q0);
                 uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+                const float4 ka0 = *reinterpret_cast<const float4*>(&sCoef[c]);
+                const float4 ka1 = *reinterpret_cast<const float4*>(&sCoef[c + 4]);
+                const float4 kb0 = *reinterpret_cast<const float4*>(&sCoef[p.kdim + c]);
+                const float4 kb1 = *reinterpret_cast<const float4*>(&sCoef[p.kdim + c + 4]);
+                const float k0[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
+                const float k1[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
                 if (AMODE == A_AFFINE) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float2 k0 = *reinterpret_cast<const float2*>(&sCoef[c + 2 * e]);
-                        const float2 k1 = *reinterpret_cast<const float2*>(&sCoef[p.kdim + c + 2 * e]);
                         const float2 a = h2_to_f2(x0[e]);
-                        o[e] = f2_to_h2(fmaxf(fmaf(a.x, k0.x, k1.x), 0.f), fmaxf(fmaf(a.y, k0.y, k1.y), 0.f));
+                        o[e] = f2_to_h2(fmaxf(fmaf(a.x, k0[2 * e], k1[2 * e]), 0.f),
+                                        fmaxf(fmaf(a.y, k0[2 * e + 1], k1[2 * e + 1]), 0.f));
                     }
                 } else {
-                    const uint4 q1 = *reinterpret_cast<const uint4*>(&sA1[(st * BM + r) * LDS + a_col]);
+                    const uint4 q1 = *reinterpret_cast<const uint4*>(&sA1[st * ASZ + r * LDK + col]);
                     const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&q1);
+                    const float4 kc0 = *reinterpret_cast<const float4*>(&sCoef[2 * p.kdim + c]);
+                    const float4 kc1 = *reinterpret_cast<const float4*>(&sCoef[2 * p.kdim + c + 4]);
+                    const float k2[8] = {kc0.x, kc0.y, kc0.z, kc0.w, kc1.x, kc1.y, kc1.z, kc1.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float2 k0 = *reinterpret_cast<const float2*>(&sCoef[c + 2 * e]);
-                        const float2 k1 = *reinterpret_cast<const float2*>(&sCoef[p.kdim + c + 2 * e]);
-                        const float2 k2 = *reinterpret_cast<const float2*>(&sCoef[2 * p.kdim + c + 2 * e]);
                         const float2 a = bf2_to_f2(x0[e]);
                         const float2 y = h2_to_f2(x1[e]);
-                        o[e] = f2_to_bf2(fmaf(k0.x, a.x, fmaf(k1.x, y.x, k2.x)), fmaf(k0.y, a.y, fmaf(k1.y, y.y, k2.y)));
+                        o[e] = f2_to_bf2(fmaf(k0[2 * e], a.x, fmaf(k1[2 * e], y.x, k2[2 * e])),
+                                         fmaf(k0[2 * e + 1], a.y, fmaf(k1[2 * e + 1], y.y, k2[2 * e + 1])));
                     }
                 }
             }
@@ -178,16 +225,18 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
     float s1[8], s2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+    const int chunk = tid % CPR;
+    const int col0 = n0 + chunk * 8;
+    uint4 yq[MASK ? PASSES : 1];  // the previous layer's y pieces this thread masks with, fetched at tile start
 
-    for (int s0 = 0; s0 < NST - 1; ++s0) issue(s0);
+    for (int s0 = 0; s0 < nst - 1; ++s0) issue();
+    long long tile = blockIdx.x;
+    int kc = 0, st = 0;
     for (long long it = 0; it < total; ++it) {
-        const long long tile = blockIdx.x + (it / KT) * gridDim.x;
-        const int kc = (int)(it % KT);
-        const int st = (int)(it % NST);
-        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");  // this thread's copies of chunk `it` landed
-        transform_A(it);
+        cp_async_wait_ring(nst);  // this thread's copies of chunk `it` (and the resident B slab) have landed
+        transform_A(tile, kc, st);
         __syncthreads();  // chunk `it` complete for everyone; everyone is done reading chunk it-1
-        issue(it + NST - 1);  // refills the buffer chunk it-1 used
+        issue();          // chunk it+nst-1 refills the buffer chunk it-1 used
         if (kc == 0) {
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf)
@@ -195,18 +244,26 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
                 for (int nf = 0; nf < 4; ++nf)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc[mf][nf][e] = 0.f;
-        }
+            if (MASK && col0 < p.n) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    const long long grow = tile * BM + tid / CPR + ps * RPP;
+                    if (grow < p.rows) yq[ps] = ldg128(p.yp + grow * p.yp_ld + col0);
+                }
+            }
+        }
+        const uint16_t* aBase = sA + st * ASZ;
+        const uint16_t* bBase = bres ? sB + kc * BKT : sB + st * BSZ;
+#pragma unroll
+        for (int ks = 0; ks < BKT / 16; ++ks) {
             uint32_t af[MF][4], bfr[2][4];
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf)
-                ldsm_x4(af[mf], smem_u32(&sA[(st * BM + wm * (MF * 16) + mf * 16 + (lane & 15)) * LDS + ks * 16 +
-                                             (lane >> 4) * 8]));
+                ldsm_x4(af[mf], smem_u32(&aBase[(wm * (MF * 16) + mf * 16 + (lane & 15)) * LDK + ks * 16 + (lane >> 4) * 8]));
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb)
-                ldsm_x4(bfr[nb], smem_u32(&sB[(st * BN + wn * 32 + nb * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS +
-                                              ks * 16 + ((lane >> 3) & 1) * 8]));
+                ldsm_x4(bfr[nb], smem_u32(&bBase[(wn * 32 + nb * 16 + (lane & 7) + ((lane >> 4) << 3)) * ldb + ks * 16 +
+                                                 ((lane >> 3) & 1) * 8]));
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
@@ -218,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
                 }
         }
         if (kc == KT - 1) {
-            // ---- epilogue: fp32 accumulators -> bf16 tile in shared memory -> coalesced stores + column sums
+            // ---- epilogue: fp32 accumulators -> 16-bit tile in shared memory -> coalesced stores + column sums
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
@@ -231,9 +288,21 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
                     *reinterpret_cast<uint32_t*>(&sC[(r + 8) * CLD + c]) = FWD ? f2_to_h2(v2, v3) : f2_to_bf2(v2, v3);
                 }
             __syncthreads();
-            const int chunk = tid % CPR;
-            const int col0 = n0 + chunk * 8;
             if (col0 < p.n) {
+                float ps_[8], ph_[8], pm_[8], pr_[8];
+                if (MASK) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(&sPrev[chunk * 8 + 4 * h]);
+                        const float4 b4 = *reinterpret_cast<const float4*>(&sPrev[BN + chunk * 8 + 4 * h]);
+                        const float4 c4 = *reinterpret_cast<const float4*>(&sPrev[2 * BN + chunk * 8 + 4 * h]);
+                        const float4 d4 = *reinterpret_cast<const float4*>(&sPrev[3 * BN + chunk * 8 + 4 * h]);
+                        ps_[4 * h] = a4.x; ps_[4 * h + 1] = a4.y; ps_[4 * h + 2] = a4.z; ps_[4 * h + 3] = a4.w;
+                        ph_[4 * h] = b4.x; ph_[4 * h + 1] = b4.y; ph_[4 * h + 2] = b4.z; ph_[4 * h + 3] = b4.w;
+                        pm_[4 * h] = c4.x; pm_[4 * h + 1] = c4.y; pm_[4 * h + 2] = c4.z; pm_[4 * h + 3] = c4.w;
+                        pr_[4 * h] = d4.x; pr_[4 * h + 1] = d4.y; pr_[4 * h + 2] = d4.z; pr_[4 * h + 3] = d4.w;
+                    }
+                }
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
                     const int r = tid / CPR + ps * RPP;
@@ -242,19 +311,17 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
                         uint4 v = *reinterpret_cast<const uint4*>(&sC[r * CLD + chunk * 8]);
                         uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
                         if (MASK) {
-                            const uint4 yq = ldg128(p.yp + grow * p.yp_ld + col0);
-                            const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yq);
+                            const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yq[ps]);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 float2 d = bf2_to_f2(vv[e]);  // MASK is a backward epilogue: bf16 tile
                                 const float2 y = h2_to_f2(yy[e]);
-                                const int c = chunk * 8 + 2 * e;
-                                const float a0 = fmaf(y.x, sPrev[c], sPrev[BN + c]);
-                                const float a1 = fmaf(y.y, sPrev[c + 1], sPrev[BN + c + 1]);
+                                const float a0 = fmaf(y.x, ps_[2 * e], ph_[2 * e]);
+                                const float a1 = fmaf(y.y, ps_[2 * e + 1], ph_[2 * e + 1]);
                                 d.x = a0 > 0.f ? d.x : 0.f;
                                 d.y = a1 > 0.f ? d.y : 0.f;
-                                const float h0 = (y.x - sPrev[2 * BN + c]) * sPrev[3 * BN + c];
-                                const float h1 = (y.y - sPrev[2 * BN + c + 1]) * sPrev[3 * BN + c + 1];
+                                const float h0 = (y.x - pm_[2 * e]) * pr_[2 * e];
+                                const float h1 = (y.y - pm_[2 * e + 1]) * pr_[2 * e + 1];
                                 s1[2 * e] += d.x; s1[2 * e + 1] += d.y;
                                 s2[2 * e] = fmaf(d.x, h0, s2[2 * e]);
                                 s2[2 * e + 1] = fmaf(d.y, h1, s2[2 * e + 1]);
@@ -275,12 +342,15 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
             }
             // sC is next written after the main-loop barrier of the following iteration
         }
+        if (++kc == KT) { kc = 0; tile += gridDim.x; }
+        if (++st == nst) st = 0;
     }
+    cp_async_wait<0>();
 
     if (p.sums) {
         // column sums: lanes sharing a chunk within the warp, then the 8 warps through shared memory
         __syncthreads();
-        float* red = reinterpret_cast<float*>(sC);  // [8 warps][2][BN]
+        float* red = reinterpret_cast<float*>(sC);  // [NW warps][2][BN]
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
 #pragma unroll
@@ -290,7 +360,6 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
             }
         }
         if (CPR >= 32 || lane < CPR) {
-            const int chunk = tid % CPR;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 red[(warp * 2 + 0) * BN + chunk * 8 + e] = s1[e];
@@ -303,50 +372,66 @@ __global__ void __launch_bounds__(kThreads, AMODE == A_BNBWD ? 1 : 2) gemm_rows_
             if (n0 + c < p.n) {
                 float s = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) s += red[(w * 2 + which) * BN + c];
+                for (int w = 0; w < NW; ++w) s += red[(w * 2 + which) * BN + c];
                 atomicAdd(p.sums + (size_t)which * p.n + n0 + c, s);
             }
         }
     }
 }
 
-template <int BN, int AMODE, bool MASK>
-int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+template <int BN, int BKT, int AMODE, bool MASK>
+int launch_gemm(GemmArgs a, cudaStream_t stream) {
     constexpr int NCOEF = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
-    constexpr int NST = nst_of(AMODE);
-    const size_t smem = (size_t)(NST * BM * LDS * (AMODE == A_BNBWD ? 2 : 1) + NST * BN * LDS + BM * (BN + 8)) *
-                            sizeof(uint16_t) +
-                        (size_t)(NCOEF * a.kdim + (MASK ? 4 * BN : 0) + BN) * sizeof(float);
-    constexpr size_t kMaxSmem = 200 * 1024;
-    if (smem > kMaxSmem) return fail_arg("pn2_mlp_gemm", "reduction dimension too large for shared memory");
+    constexpr size_t kMaxSmem = 220 * 1024;
+    constexpr int LDK = BKT + 8;
+    const size_t fixed = (size_t)BM * (BN + 8) * 2 + (size_t)(NCOEF * a.kdim + BN + (MASK ? 4 * BN : 0)) * 4;
+    const size_t bres_bytes = (size_t)BN * (a.kdim + 8) * 2;
+    const size_t a_stage = (size_t)BM * LDK * 2 * (AMODE == A_BNBWD ? 2 : 1);
+    const size_t b_stage = (size_t)BN * LDK * 2;
+    // keep the weight slab resident when that still leaves room for >= 3 operand stages
+    a.bres = (bres_bytes <= 72 * 1024 && fixed + bres_bytes + 3 * a_stage <= kMaxSmem) ? 1 : 0;
+    const size_t stage = a_stage + (a.bres ? 0 : b_stage);
+    const size_t avail = kMaxSmem - fixed - (a.bres ? bres_bytes : 0);
+    if (fixed + (a.bres ? bres_bytes : 0) > kMaxSmem || avail < 2 * stage)
+        return fail_arg("pn2_mlp_gemm", "reduction dimension too large for shared memory");
+    long long nst = (long long)(avail / stage);
+    if (nst > 6) nst = 6;
+    a.nst = (int)nst;
+    const size_t smem = fixed + (a.bres ? bres_bytes : 0) + nst * stage;
     static bool configured = false;
     if (!configured) {
-        PN2_CHECK(cudaFuncSetAttribute(gemm_rows_kernel<BN, AMODE, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PN2_CHECK(cudaFuncSetAttribute(gemm_rows_kernel<BN, BKT, AMODE, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kMaxSmem),
                   "gemm: cudaFuncSetAttribute");
         configured = true;
     }
     const long long tiles = (a.rows + BM - 1) / BM;
     const int ny = (a.n + BN - 1) / BN;
-    int occ = 1, sms = 148;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_rows_kernel<BN, AMODE, MASK>, kThreads, smem);
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (occ < 1) occ = 1;
-    long long gx = ((long long)occ * sms) / ny;  // persistent: every CTA resident, tiles dealt round-robin
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    long long gx = sms / ny;  // persistent, one CTA per SM: every CTA resident, tiles dealt round-robin
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
     dim3 grid((unsigned)gx, ny);
-    gemm_rows_kernel<BN, AMODE, MASK><<<grid, kThreads, smem, stream>>>(a);
+    gemm_rows_kernel<BN, BKT, AMODE, MASK><<<grid, gemm_threads(BN), smem, stream>>>(a);
     PN2_CHECK_LAUNCH("gemm_rows_kernel");
     return 0;
 }
 
 template <int AMODE, bool MASK>
 int dispatch_bn(const GemmArgs& a, cudaStream_t stream) {
-    if (a.n <= 32) return launch_gemm<32, AMODE, MASK>(a, stream);
-    if (a.n <= 64) return launch_gemm<64, AMODE, MASK>(a, stream);
-    return launch_gemm<128, AMODE, MASK>(a, stream);
+    if (a.kdim % 64 == 0) {
+        if (a.n <= 32) return launch_gemm<32, 64, AMODE, MASK>(a, stream);
+        if (a.n <= 64) return launch_gemm<64, 64, AMODE, MASK>(a, stream);
+        return launch_gemm<128, 64, AMODE, MASK>(a, stream);
+    }
+    if (a.n <= 32) return launch_gemm<32, 32, AMODE, MASK>(a, stream);
+    if (a.n <= 64) return launch_gemm<64, 32, AMODE, MASK>(a, stream);
+    return launch_gemm<128, 32, AMODE, MASK>(a, stream);
 }
 
 int check_common(const char* who, long long rows, int kdim, int n) {
@@ -375,8 +460,11 @@ struct WgradArgs {
 constexpr int WBR = 64, WST = 3;
 constexpr int kWgradSmem = WST * 3 * WBR * SLD * 2 + 5 * 128 * 4;
 
+constexpr int kWgradThreads = 512;  // 16 warps: 4 (Cout) x 4 (Cin) warp tiles of 32 x 32
+
 template <bool AFFINE>
-__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs p) {
+__global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const WgradArgs p) {
+    constexpr int kThreads = kWgradThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t* sD = reinterpret_cast<uint16_t*>(smem_raw);  // [WST][WBR][SLD] dz -> dY (bf16)
     uint16_t* sY = sD + WST * WBR * SLD;                   // [WST][WBR][SLD] y (fp16)
@@ -399,16 +487,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs p) {
 
     const long long chunks = (p.rows + WBR - 1) / WBR;
     const long long mine = blockIdx.z < chunks ? (chunks - blockIdx.z + gridDim.z - 1) / gridDim.z : 0;
-    const int p_row = tid >> 4, p_col = (tid & 15) * 8;  // 4 pieces per matrix per thread: rows p_row + 16*j
+    const int p_row = tid >> 4, p_col = (tid & 15) * 8;  // 2 pieces per matrix per thread: rows p_row + 32*j
     const bool ncol_ok = n0 + p_col < p.n, kcol_ok = k0 + p_col < p.kp;
 
-    auto issue = [&](long long i) {
-        if (i < mine) {
-            const long long ch = blockIdx.z + i * gridDim.z;
-            const int st = (int)(i % WST);
+    long long is_i = 0, is_ch = blockIdx.z;
+    int is_st = 0;
+    auto issue = [&]() {
+        if (is_i < mine) {
+            const long long ch = is_ch;
+            const int st = is_st;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = p_row + j * 16;
+            for (int j = 0; j < 2; ++j) {
+                const int r = p_row + j * 32;
                 const long long row = ch * WBR + r;
                 const bool ok = row < p.rows;
                 const long long rr = ok ? row : 0;
@@ -417,15 +507,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs p) {
                 cp_async16(&sY[off], p.y + rr * p.y_ld + (ncol_ok ? n0 + p_col : 0), ok && ncol_ok ? 16 : 0);
                 cp_async16(&sX[off], p.x + rr * p.x_ld + (kcol_ok ? k0 + p_col : 0), ok && kcol_ok ? 16 : 0);
             }
+            ++is_i;
+            is_ch += gridDim.z;
+            if (++is_st == WST) is_st = 0;
         }
         cp_async_commit();
     };
-    auto transform = [&](long long i) {
-        const long long ch = blockIdx.z + i * gridDim.z;
-        const int st = (int)(i % WST);
+    auto transform = [&](long long ch, int st) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = p_row + j * 16;
+        for (int j = 0; j < 2; ++j) {
+            const int r = p_row + j * 32;
             const bool ok = ch * WBR + r < p.rows;
             const int off = (st * WBR + r) * SLD + p_col;
             uint4 vd = make_uint4(0u, 0u, 0u, 0u), vx = make_uint4(0u, 0u, 0u, 0u);
@@ -457,39 +548,40 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs p) {
         }
     };
 
-    const int wn2 = warp >> 2, wk = warp & 3;
-    const bool warp_on = (n0 + wn2 * 64 < p.n) && (k0 + wk * 32 < p.kp);
-    float acc[4][4][4];
+    const int wn2 = warp >> 2, wk = warp & 3;  // 4 x 4 warps
+    const bool warp_on = (n0 + wn2 * 32 < p.n) && (k0 + wk * 32 < p.kp);
+    float acc[2][4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
 
     const int mi = lane >> 3, l7 = lane & 7;
-    for (int s0 = 0; s0 < WST - 1; ++s0) issue(s0);
-    for (long long i = 0; i < mine; ++i) {
-        const int st = (int)(i % WST);
+    for (int s0 = 0; s0 < WST - 1; ++s0) issue();
+    long long ch = blockIdx.z;
+    int st = 0;
+    for (long long i = 0; i < mine; ++i, ch += gridDim.z, st = (st + 1 == WST ? 0 : st + 1)) {
         asm volatile("cp.async.wait_group %0;" ::"n"(WST - 2) : "memory");
-        transform(i);
+        transform(ch, st);
         __syncthreads();
-        issue(i + WST - 1);
+        issue();
         if (warp_on) {
 #pragma unroll
             for (int rs = 0; rs < WBR; rs += 16) {
-                uint32_t af[4][4], bfr[2][4];
+                uint32_t af[2][4], bfr[2][4];
 #pragma unroll
-                for (int mf = 0; mf < 4; ++mf)
-                    ldsm_x4_trans(af[mf], smem_u32(&sD[(st * WBR + rs + (mi >> 1) * 8 + l7) * SLD + wn2 * 64 + mf * 16 +
+                for (int mf = 0; mf < 2; ++mf)
+                    ldsm_x4_trans(af[mf], smem_u32(&sD[(st * WBR + rs + (mi >> 1) * 8 + l7) * SLD + wn2 * 32 + mf * 16 +
                                                        (mi & 1) * 8]));
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb)
                     ldsm_x4_trans(bfr[nb], smem_u32(&sX[(st * WBR + rs + (mi & 1) * 8 + l7) * SLD + wk * 32 + nb * 16 +
                                                         (mi >> 1) * 8]));
 #pragma unroll
-                for (int mf = 0; mf < 4; ++mf) {
-                    if (n0 + wn2 * 64 + mf * 16 < p.n) {
+                for (int mf = 0; mf < 2; ++mf) {
+                    if (n0 + wn2 * 32 + mf * 16 < p.n) {
 #pragma unroll
                         for (int nf = 0; nf < 4; ++nf)
                             mma_bf16_16816(acc[mf][nf], af[mf], bfr[nf >> 1][(nf & 1) * 2], bfr[nf >> 1][(nf & 1) * 2 + 1]);
@@ -501,12 +593,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs p) {
     if (warp_on) {
         const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
-        for (int mf = 0; mf < 4; ++mf)
+        for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
             for (int nf = 0; nf < 4; ++nf)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int n = n0 + wn2 * 64 + mf * 16 + g + (e >> 1) * 8;
+                    const int n = n0 + wn2 * 32 + mf * 16 + g + (e >> 1) * 8;
                     const int k = k0 + wk * 32 + nf * 8 + t4 * 2 + (e & 1);
                     if (n < p.n && k < p.k_true) atomicAdd(p.dw + (size_t)n * p.dw_ld + k, acc[mf][nf][e]);
                 }
@@ -517,6 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const WgradArgs p) {
 // c[n] = sum_k w[n][k] * mean_j act(x[row_j][k]) over <= 16 rows spread evenly over the matrix;
 // c_true[n] = c[n] + sum_k w[n][k] * in_offset[k]: the input rows may themselves be stored centred
 // (x_true = x + in_offset per channel), which the GEMM output inherits as a per-channel constant.
+// One warp per output column (8 columns per CTA) so that even 512 columns spread over 64 CTAs.
 __global__ void __launch_bounds__(256) center_kernel(long long rows, int kdim, int n, const act_t* __restrict__ x,
                                                       int x_ld, const float* __restrict__ sc,
                                                       const float* __restrict__ sh, const act_t* __restrict__ w,
@@ -527,35 +620,36 @@ __global__ void __launch_bounds__(256) center_kernel(long long rows, int kdim, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ns = rows < 16 ? (int)rows : 16;
     const long long step = rows / ns;
+    const float inv = 1.f / (float)ns;
     for (int k = tid; k < kdim; k += 256) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = j < ns ? h_to_f(x[(size_t)(j * step) * x_ld + k]) : 0.f;
         float m = 0.f;
-        for (int j = 0; j < ns; ++j) {
-            float v = h_to_f(x[(size_t)(j * step) * x_ld + k]);
-            if (sc) v = fmaxf(fmaf(v, sc[k], sh[k]), 0.f);
-            m += v;
-        }
-        sM[k] = m / (float)ns;
+        const float a = sc ? sc[k] : 1.f, b = sc ? sh[k] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < ns) m += sc ? fmaxf(fmaf(v[j], a, b), 0.f) : v[j];
+        sM[k] = m * inv;
         sO[k] = in_offset ? in_offset[k] : 0.f;
     }
     __syncthreads();
-    for (int j = 0; j < 4; ++j) {
-        const int col = blockIdx.x * 32 + warp * 4 + j;
-        if (col >= n) break;
-        float acc = 0.f, acc2 = 0.f;
-        for (int k = lane; k < kdim; k += 32) {
-            const float wv = h_to_f(w[(size_t)col * kdim + k]);
-            acc = fmaf(wv, sM[k], acc);
-            acc2 = fmaf(wv, sO[k], acc2);
-        }
+    const int col = blockIdx.x * 8 + warp;
+    if (col >= n) return;
+    float acc = 0.f, acc2 = 0.f;
+    for (int k = lane * 2; k < kdim; k += 64) {  // kdim is a multiple of 32: pairs never straddle the end
+        const float2 wv = h2_to_f2(*reinterpret_cast<const uint32_t*>(w + (size_t)col * kdim + k));
+        acc = fmaf(wv.x, sM[k], fmaf(wv.y, sM[k + 1], acc));
+        acc2 = fmaf(wv.x, sO[k], fmaf(wv.y, sO[k + 1], acc2));
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc += __shfl_xor_sync(kFull, acc, o);
-            acc2 += __shfl_xor_sync(kFull, acc2, o);
-        }
-        if (lane == 0) {
-            c[col] = acc;
-            c_true[col] = acc + acc2;
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(kFull, acc, o);
+        acc2 += __shfl_xor_sync(kFull, acc2, o);
+    }
+    if (lane == 0) {
+        c[col] = acc;
+        c_true[col] = acc + acc2;
     }
 }
 
@@ -640,7 +734,7 @@ extern "C" int pn2_mlp_center(long long rows, int kdim, int n, const void* x, in
     if (rows == 0) return 0;
     if (kdim > 1024) return fail_arg("pn2_mlp_center", "kdim > 1024");
     if (!x || !w || !center || !center_true) return fail_arg("pn2_mlp_center", "null pointer");
-    center_kernel<<<(n + 31) / 32, 256, 0, (cudaStream_t)stream>>>(rows, kdim, n, (const act_t*)x, x_ld, in_scale, in_shift,
+    center_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rows, kdim, n, (const act_t*)x, x_ld, in_scale, in_shift,
                                                                   (const act_t*)w, in_offset, center, center_true);
     PN2_CHECK_LAUNCH("center_kernel");
     return 0;
@@ -725,9 +819,9 @@ extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, con
         configured = true;
     }
     if (in_scale)
-        wgrad_kernel<true><<<grid, kThreads, kWgradSmem, (cudaStream_t)stream>>>(a);
+        wgrad_kernel<true><<<grid, kWgradThreads, kWgradSmem, (cudaStream_t)stream>>>(a);
     else
-        wgrad_kernel<false><<<grid, kThreads, kWgradSmem, (cudaStream_t)stream>>>(a);
+        wgrad_kernel<false><<<grid, kWgradThreads, kWgradSmem, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("wgrad_kernel");
     return 0;
 }

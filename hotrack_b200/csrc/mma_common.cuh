@@ -70,9 +70,9 @@ __device__ __forceinline__ float bf_to_f(bf16 v) { return __bfloat162float(v); }
 
 __device__ __forceinline__ float2 h2_to_f2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 __device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
-    // saturate instead of overflowing to inf: a finite fp16 keeps BatchNorm statistics finite
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    // plain round-to-nearest: the values stored in fp16 are centred pre-BatchNorm outputs and post-ReLU
+    // activations, orders of magnitude below 65504 (an overflow would surface as inf/NaN in the BatchNorm
+    // statistics, which the tests check for)
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }

@@ -37,8 +37,9 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
-def _pad32(c):
-    return (c + 31) // 32 * 32
+def _padk(c):
+    """GEMM reduction-dimension padding: one 32-wide chunk, else whole 64-wide (128-byte) chunks."""
+    return 32 if c <= 32 else (c + 63) // 64 * 64
 
 
 class Rows:
@@ -117,7 +118,7 @@ class _MlpStack(Function):
             cc = rb.c if rb is not None else 0
             cin = fc + 3 + cc
             R, groups, pool_k = B * S * K, S, K
-            x0 = torch.empty(R, _pad32(cin), dtype=_F16, device=dev)
+            x0 = torch.empty(R, _padk(cin), dtype=_F16, device=dev)
             _lib.call("pn2_sa_build_rows", B, N, S, K, xyz.data_ptr(), _p(new_xyz), _p(idx),
                       _p(ra.y) if ra else 0, fc, ra.ld if ra else 0, _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0,
                       _p(rb.y) if rb else 0, cc, rb.ld if rb else 0, _p(rb.scale) if rb else 0, _p(rb.shift) if rb else 0,
@@ -128,7 +129,7 @@ class _MlpStack(Function):
             sc = ra.c if ra is not None else 0
             cin = sc + rb.c
             R, groups, pool_k = B * N, N, 1
-            x0 = torch.empty(R, _pad32(cin), dtype=_F16, device=dev)
+            x0 = torch.empty(R, _padk(cin), dtype=_F16, device=dev)
             _lib.call("pn2_fp_build_rows", B, N, S, _p(ra.y) if ra else 0, sc, ra.ld if ra else 0,
                       _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0, rb.y.data_ptr(), rb.c, rb.ld, _p(rb.scale),
                       _p(rb.shift), _p(idx), _p(dist2), x0.data_ptr(), x0.shape[1], st)
@@ -142,10 +143,10 @@ class _MlpStack(Function):
         if x0 is not None:
             x, x_ld, xs, xh, kp = x0, x0.shape[1], None, None, x0.shape[1]
         else:
-            if ra.ld % 32 == 0:
+            if ra.ld == _padk(ra.c):
                 x, x_ld, xs, xh, kp = ra.y, ra.ld, ra.scale, ra.shift, ra.ld
-            else:  # re-pad the row form to the GEMM's 32-column granularity
-                kp = _pad32(ra.c)
+            else:  # re-pad the row form to the GEMM's chunk granularity
+                kp = _padk(ra.c)
                 x = torch.zeros(R, kp, dtype=_F16, device=dev)
                 x[:, :ra.c] = ra.y[:, :ra.c]
                 x_ld, xs, xh = kp, ra.scale, ra.shift
