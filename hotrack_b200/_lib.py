@@ -41,12 +41,12 @@ SIGNATURES = {
     "pn2_bn_finalize": [_i, _ll, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "pn2_bn_eval_affine": [_i, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p],
     "pn2_pool_fwd": [_i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p],
-    "pn2_pool_bwd": [_i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p],
+    "pn2_pool_bwd": [_i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p],
     "pn2_bn_bwd_coefs": [_i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "pn2_mlp_gemm_dgrad": [_ll, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p],
     "pn2_mlp_gemm_wgrad": [_ll, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p],
     "pn2_mlp_prep_weights": [_i, _i, _i, _p, _p, _p, _p],
-    "pn2_sa_rows_bwd": [_i, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p],
+    "pn2_sa_rows_bwd": [_i, _i, _i, _i, _p, _p, _i, _i, _p, _i, _i, _p, _i, _p],
     "pn2_fp_rows_bwd": [_i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _p, _p],
 }
 
@@ -79,6 +79,9 @@ def call(name, *args):
         return
     import torch
 
+    # drain the stream first: with work still queued, the start event would fire while earlier kernels run and
+    # the pair would time the queue, not this launch
+    torch.cuda.current_stream().synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     check(getattr(lib, name)(*args), name)

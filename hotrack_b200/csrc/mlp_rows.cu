@@ -163,7 +163,8 @@ struct PoolArgs {
     float* out_cm;        // (B,C,S)
     float* chan_sums;     // [C] += sum over (b,s) of the output (nullable)
     int* argmax;          // (B,S,C)
-    const float* dout_cm; // backward
+    const float* dout_cm; // backward (nullable when extra_rows carries the whole gradient)
+    const float* extra_rows;  // backward, k == 1: additional output gradient in row form [B*S][C] (nullable)
     bf16* dz; int dz_ld;
     float* sums;          // [2][C]
 };
@@ -348,13 +349,15 @@ __global__ void __launch_bounds__(kThreads) cm_to_rows_bwd_kernel(const PoolArgs
     for (int t = blockIdx.x; t < s_tiles; t += gridDim.x) {
         const int s0 = t * kRowTile;
         // channel-major side: 8 independent 128-byte runs in flight per warp (c is a multiple of 8)
-        for (int ch0 = warp * 8; ch0 < a.c; ch0 += nwarps * 8) {
-            float v[8];
+        if (a.dout_cm) {
+            for (int ch0 = warp * 8; ch0 < a.c; ch0 += nwarps * 8) {
+                float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                v[j] = (s0 + lane < a.s) ? __ldg(a.dout_cm + ((size_t)b * a.c + ch0 + j) * a.s + s0 + lane) : 0.f;
+                for (int j = 0; j < 8; ++j)
+                    v[j] = (s0 + lane < a.s) ? __ldg(a.dout_cm + ((size_t)b * a.c + ch0 + j) * a.s + s0 + lane) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tile_dyn[lane * ldt + j * pieces + (ch0 >> 3)] = v[j];
+                for (int j = 0; j < 8; ++j) tile_dyn[lane * ldt + j * pieces + (ch0 >> 3)] = v[j];
+            }
         }
         __syncthreads();
         for (int r = r0; r < kRowTile; r += rstep) {
@@ -362,12 +365,23 @@ __global__ void __launch_bounds__(kThreads) cm_to_rows_bwd_kernel(const PoolArgs
                 const size_t row = (size_t)b * a.s + s0 + r;
                 const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.y + row * a.y_ld + pc * 8));
                 const uint32_t* v = reinterpret_cast<const uint32_t*>(&q);
+                float ex[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (a.extra_rows) {  // gradient contributions consumers delivered in row form (sparse gathers)
+                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(a.extra_rows + row * a.c + pc * 8));
+                    const float4 e1 = __ldg(reinterpret_cast<const float4*>(a.extra_rows + row * a.c + pc * 8 + 4));
+                    ex[0] = e0.x; ex[1] = e0.y; ex[2] = e0.z; ex[3] = e0.w;
+                    ex[4] = e1.x; ex[5] = e1.y; ex[6] = e1.z; ex[7] = e1.w;
+                }
                 uint4 o;
                 uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 f = h2_to_f2(v[e]);
-                    float d0 = tile_dyn[r * ldt + (2 * e) * pieces + pc], d1 = tile_dyn[r * ldt + (2 * e + 1) * pieces + pc];
+                    float d0 = ex[2 * e], d1 = ex[2 * e + 1];
+                    if (a.dout_cm) {
+                        d0 += tile_dyn[r * ldt + (2 * e) * pieces + pc];
+                        d1 += tile_dyn[r * ldt + (2 * e + 1) * pieces + pc];
+                    }
                     d0 = fmaf(f.x, sc[2 * e], sh[2 * e]) > 0.f ? d0 : 0.f;
                     d1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]) > 0.f ? d1 : 0.f;
                     p1[2 * e] += d0; p1[2 * e + 1] += d1;
@@ -405,7 +419,8 @@ struct SaBwdArgs {
     int b, n, s, k;
     const int* idx;
     const bf16* dx; int dx_ld;
-    int feat_c; float* dfeat_cm;   // (B,feat_c,N) zeroed, atomics
+    int feat_c; float* dfeat_cm;   // (B,feat_c,N) zeroed, atomics -- or, feat_rows_major, [B*N][feat_c]
+    int feat_rows_major;
     int cen_c; float* dcen_cm;     // (B,cen_c,S)  zeroed, atomics
     int xyz_first;
 };
@@ -421,9 +436,17 @@ __global__ void __launch_bounds__(kThreads) sa_rows_bwd_kernel(const SaBwdArgs a
     const int fc = a.dfeat_cm ? a.feat_c : 0, cc = a.dcen_cm ? a.cen_c : 0;
     const int f0 = a.xyz_first ? 3 : 0, c0 = a.feat_c + 3;
     const bf16* d = a.dx + (size_t)row * a.dx_ld;
-    for (int col = lane; col < fc; col += 32) {
-        const float v = bf_to_f(d[f0 + col]);
-        if (v != 0.f) atomicAdd(a.dfeat_cm + ((size_t)b * a.feat_c + col) * a.n + j, v);
+    if (a.feat_rows_major) {  // lanes along the contiguous channel dimension: coalesced reductions
+        float* dst = a.dfeat_cm + ((size_t)b * a.n + j) * a.feat_c;
+        for (int col = lane; col < fc; col += 32) {
+            const float v = bf_to_f(d[f0 + col]);
+            if (v != 0.f) atomicAdd(dst + col, v);
+        }
+    } else {
+        for (int col = lane; col < fc; col += 32) {
+            const float v = bf_to_f(d[f0 + col]);
+            if (v != 0.f) atomicAdd(a.dfeat_cm + ((size_t)b * a.feat_c + col) * a.n + j, v);
+        }
     }
     for (int col = lane; col < cc; col += 32) {
         const float v = bf_to_f(d[c0 + col]);
@@ -569,17 +592,20 @@ extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld,
     return 0;
 }
 
-extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const void* y, int y_ld,
-                            const float* scale, const float* shift, const float* mean, const float* rstd,
+extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* extra_rows, const void* y,
+                            int y_ld, const float* scale, const float* shift, const float* mean, const float* rstd,
                             const int* argmax, void* dz, int dz_ld, float* sums, pn2_stream_t stream) {
     if (b < 0 || s <= 0 || k <= 0 || c <= 0 || c % 8) return fail_arg("pn2_pool_bwd", "bad size");
     if (b == 0) return 0;
     if (b > 65535) return fail_arg("pn2_pool_bwd", "b > 65535");
-    if (!dout_cm || !y || !scale || !shift || !mean || !rstd || !dz || !sums) return fail_arg("pn2_pool_bwd", "null pointer");
+    if ((!dout_cm && !extra_rows) || !y || !scale || !shift || !mean || !rstd || !dz || !sums)
+        return fail_arg("pn2_pool_bwd", "null pointer");
     if (k > 1 && !argmax) return fail_arg("pn2_pool_bwd", "argmax required when k > 1");
+    if (extra_rows && !(k == 1 && c <= 1024)) return fail_arg("pn2_pool_bwd", "extra_rows needs k == 1 and c <= 1024");
     PoolArgs a{};
     a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
-    a.mean = mean; a.rstd = rstd; a.argmax = const_cast<int*>(argmax); a.dout_cm = dout_cm; a.dz = (bf16*)dz; a.dz_ld = dz_ld; a.sums = sums;
+    a.mean = mean; a.rstd = rstd; a.argmax = const_cast<int*>(argmax); a.dout_cm = dout_cm; a.extra_rows = extra_rows;
+    a.dz = (bf16*)dz; a.dz_ld = dz_ld; a.sums = sums;
     dim3 grid;
     if (k == 1 && c <= 1024) {
         const int s_tiles = (s + kRowTile - 1) / kRowTile;
@@ -608,13 +634,15 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
 }
 
 extern "C" int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const void* dx, int dx_ld, int feat_c,
-                               float* dfeat_cm, int cen_c, float* dcen_cm, int xyz_first, pn2_stream_t stream) {
+                               float* dfeat_cm, int feat_rows_major, int cen_c, float* dcen_cm, int xyz_first,
+                               pn2_stream_t stream) {
     if (b < 0 || n <= 0 || s <= 0 || k <= 0) return fail_arg("pn2_sa_rows_bwd", "bad size");
     if (b == 0 || (!dfeat_cm && !dcen_cm)) return 0;
     if (!dx) return fail_arg("pn2_sa_rows_bwd", "null pointer");
     SaBwdArgs a;
     a.b = b; a.n = n; a.s = s; a.k = k; a.idx = idx; a.dx = (const bf16*)dx; a.dx_ld = dx_ld;
-    a.feat_c = feat_c; a.dfeat_cm = dfeat_cm; a.cen_c = cen_c; a.dcen_cm = dcen_cm; a.xyz_first = xyz_first;
+    a.feat_c = feat_c; a.dfeat_cm = dfeat_cm; a.feat_rows_major = feat_rows_major;
+    a.cen_c = cen_c; a.dcen_cm = dcen_cm; a.xyz_first = xyz_first;
     sa_rows_bwd_kernel<<<warp_blocks((long long)b * s * k), kThreads, 0, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("sa_rows_bwd_kernel");
     return 0;

@@ -42,15 +42,39 @@ def _padk(c):
     return 32 if c <= 32 else (c + 63) // 64 * 64
 
 
+# Row-form gradient hand-over ("sink").  A consumer that GATHERS rows of a fused K=1 stack's output (the q
+# modules gathering 21 x 80 neighbours per cloud from the (B,384,N) backbone output) has a sparse gradient
+# w.r.t. that output.  Through autograd it must be returned dense and channel-major: a 201 MB memset, an
+# uncoalesced atomic scatter and a 600 MB-traffic add kernel per consumer.  With the sink enabled the consumer
+# instead accumulates its rows (coalesced atomics) into ONE fp32 row buffer owned by the producer and returns
+# None; the producer's backward -- which autograd runs after all of its consumers -- adds that buffer while it
+# builds dz.  Opt-in (TrainStep enables it): code that asks autograd for d(consumer)/d(producer output)
+# directly (torch.autograd.grad on intermediate tensors) must leave it off.
+SPARSE_GRAD_SINK = False
+
+
+def set_sparse_grad_sink(on):
+    global SPARSE_GRAD_SINK
+    SPARSE_GRAD_SINK = bool(on)
+
+
+class _Sink:
+    __slots__ = ("rows", "c", "buf")
+
+    def __init__(self, rows, c):
+        self.rows, self.c, self.buf = rows, c, None
+
+
 class Rows:
     """fp16 row matrix [rows][ld] with c valid channels; scale/shift (fp32, length >= c) mean the
     consumer must read relu(y*scale + shift) -- the producer's BatchNorm+ReLU applied on the fly."""
 
-    __slots__ = ("y", "c", "ld", "scale", "shift", "offset", "numel", "version")
+    __slots__ = ("y", "c", "ld", "scale", "shift", "offset", "sink", "numel", "version")
 
-    def __init__(self, y, c, ld, scale=None, shift=None, offset=None):
+    def __init__(self, y, c, ld, scale=None, shift=None, offset=None, sink=None):
         # offset (fp32 [c]): the rows are stored CENTRED, true value = y + offset (pooled features)
         self.y, self.c, self.ld, self.scale, self.shift, self.offset = y, c, ld, scale, shift, offset
+        self.sink = sink  # _Sink of the producing K=1 stack (row-form gradient hand-over), or None
         self.numel = self.version = None
 
 
@@ -220,8 +244,13 @@ class _MlpStack(Function):
             out_rows = torch.empty(B * groups, C, dtype=_F16, device=dev)
             _lib.call("pn2_to_rows", B, C, groups, out.data_ptr(), chan_sums.data_ptr(), inv, out_rows.data_ptr(), C, st)
             _MlpStack.last_rows = Rows(out_rows, C, C, offset=chan_sums * inv)
+            ctx.out_sink = None
         else:
-            _MlpStack.last_rows = Rows(last.y, C, C, last.scale, last.shift)
+            ctx.out_sink = _Sink(R, C) if (training and C <= 1024) else None
+            _MlpStack.last_rows = Rows(last.y, C, C, last.scale, last.shift, sink=ctx.out_sink)
+        # gather-type consumer of a producer that offers a sink: deliver the feature gradient in row form
+        ctx.feat_sink = ra.sink if (kind == "sa" and SPARSE_GRAD_SINK and training and ra is not None
+                                    and ra.sink is not None and a is not None and a.requires_grad) else None
 
         ctx.kind, ctx.meta, ctx.training = kind, meta, training
         ctx.dims = (B, groups, pool_k, R, cin)
@@ -237,16 +266,20 @@ class _MlpStack(Function):
     def backward(ctx, dout):
         nl = len(ctx.layers)
         none_params = [None] * (4 * nl)
-        if dout is None:
+        extra = ctx.out_sink.buf if ctx.out_sink is not None else None
+        if ctx.out_sink is not None:
+            ctx.out_sink.buf = None
+        if dout is None and extra is None:
             return (None, None, None, None, None, None, None, *none_params)
         if not ctx.training:
             raise NotImplementedError("fused engine: backward through eval-mode BatchNorm is not implemented; "
                                       "use engine 'ops' for that")
         st = _stream()
-        dev = dout.device
+        dev = ctx.layers[0].y.device
         B, groups, pool_k, R, cin = ctx.dims
         layers = ctx.layers
-        dout = dout.contiguous().float()
+        if dout is not None:
+            dout = dout.contiguous().float()
         last = layers[-1]
         C = last.cout
         dz = torch.empty(R, C, dtype=_BF16, device=dev)
@@ -254,7 +287,7 @@ class _MlpStack(Function):
         arena = torch.zeros(2 * sum(L.cout for L in layers), dtype=torch.float32, device=dev)
         a_off = 2 * C
         sums = arena[:a_off]
-        _lib.call("pn2_pool_bwd", B, groups, pool_k, C, dout.data_ptr(), last.y.data_ptr(), C, last.scale.data_ptr(),
+        _lib.call("pn2_pool_bwd", B, groups, pool_k, C, _p(dout), _p(extra), last.y.data_ptr(), C, last.scale.data_ptr(),
                   last.shift.data_ptr(), last.mean.data_ptr(), last.rstd.data_ptr(), _p(ctx.argmax), dz.data_ptr(), C,
                   sums.data_ptr(), st)
         need_a = ctx.needs_input_grad[5] and ctx.a_shape is not None
@@ -316,12 +349,20 @@ class _MlpStack(Function):
                 S, K = (idx.shape[1], idx.shape[2]) if idx is not None else (1, N)
                 fc = ctx.a_shape[1] if ctx.a_shape is not None else 0
                 cc = ctx.b_shape[1] if ctx.b_shape is not None else 0
-                if need_a:
+                sink = ctx.feat_sink if need_a else None
+                if sink is not None:
+                    if sink.buf is None:
+                        sink.buf = torch.zeros(sink.rows, sink.c, dtype=torch.float32, device=dev)
+                    dfeat, rows_major = sink.buf, 1  # da stays None: the producer's backward picks the buffer up
+                elif need_a:
                     da = torch.zeros(ctx.a_shape, dtype=torch.float32, device=dev)
+                    dfeat, rows_major = da, 0
+                else:
+                    dfeat, rows_major = None, 0
                 if need_b:
                     db = torch.zeros(ctx.b_shape, dtype=torch.float32, device=dev)
-                _lib.call("pn2_sa_rows_bwd", B, N, S, K, _p(idx), dx0.data_ptr(), dx0.shape[1], fc, _p(da), cc, _p(db),
-                          1 if xyz_first else 0, st)
+                _lib.call("pn2_sa_rows_bwd", B, N, S, K, _p(idx), dx0.data_ptr(), dx0.shape[1], fc, _p(dfeat), rows_major,
+                          cc, _p(db), 1 if xyz_first else 0, st)
             elif ctx.kind == "fp":
                 idx, dist2, N, S = ctx.meta
                 sc = ctx.a_shape[1] if ctx.a_shape is not None else 0

@@ -15,6 +15,8 @@ from .flat import FlatAdam, FlatParams
 class TrainStep:
     def __init__(self, model, loss_fn, lr=1e-4, weight_decay=1e-4, graph=True):
         self.model, self.loss_fn = model, loss_fn
+        from . import fused
+        fused.set_sparse_grad_sink(True)  # whole-step backward: gather gradients travel in row form
         self.flat = FlatParams(model)
         self.flat.broadcast(0)
         self.opt = FlatAdam(self.flat, lr=lr, weight_decay=weight_decay)

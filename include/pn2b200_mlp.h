@@ -78,8 +78,11 @@ int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld, const floa
                  float* out_cm, float* chan_sums, int* argmax, pn2_stream_t stream);
 
 /* Backward of pool_fwd: dz[rows][c] = dout at the arg-max row where the ReLU is active, else 0; sums[0..c) +=
- * sum(dz), sums[c..2c) += sum(dz * xhat)  (zeroed by the caller). */
-int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const void* y, int y_ld, const float* scale,
+ * sum(dz), sums[c..2c) += sum(dz * xhat)  (zeroed by the caller).  k == 1 only: extra_rows [B*S][c] fp32
+ * (nullable) is a second output-gradient term in row form (what consumers that GATHER from this output
+ * deliver, see pn2_sa_rows_bwd); dout_cm may then be NULL. */
+int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* extra_rows, const void* y, int y_ld,
+                 const float* scale,
                  const float* shift, const float* mean, const float* rstd, const int* argmax, void* dz, int dz_ld,
                  float* sums, pn2_stream_t stream);
 
@@ -105,10 +108,12 @@ int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, const void* dz
 /* fp32 conv weight [n][k_true] -> bf16 [n][kp] (zero padded) and, if wt != NULL, its transpose [kp][n]. */
 int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_bf16, void* wt_bf16, pn2_stream_t stream);
 
-/* Gradient of sa_build_rows' output rows scattered to the feature tensors (channel-major fp32, zeroed by the
- * caller, atomics): dfeat_cm (B,feat_c,N), dcen_cm (B,cen_c,S); either may be NULL. */
+/* Gradient of sa_build_rows' output rows scattered to the feature tensors (fp32, zeroed by the caller, atomics):
+ * dfeat_cm (B,feat_c,N) channel-major -- or, feat_rows_major != 0, rows [B*N][feat_c] (coalesced; the form
+ * pn2_pool_bwd's extra_rows takes) --, dcen_cm (B,cen_c,S); either may be NULL. */
 int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const void* dx, int dx_ld, int feat_c,
-                    float* dfeat_cm, int cen_c, float* dcen_cm, int xyz_first, pn2_stream_t stream);
+                    float* dfeat_cm, int feat_rows_major, int cen_c, float* dcen_cm, int xyz_first,
+                    pn2_stream_t stream);
 
 /* Gradient of fp_build_rows' output rows: dskip_cm (B,skip_c,N) plain stores; dcoarse_rows (B*S, coarse_c) fp32
  * rows, zeroed by the caller, atomics; either may be NULL. */

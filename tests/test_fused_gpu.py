@@ -292,3 +292,45 @@ def test_train_step_graph_replay_matches_eager(cuda):
     # same number of optimiser steps on the same data; atomics make the two runs differ in the last bits only
     assert _rel(finals[1][0], finals[0][0]) < 5e-2
     assert abs(finals[1][1] - finals[0][1]) < 5e-2 * abs(finals[0][1])
+
+
+def test_sparse_grad_sink_matches_dense_autograd_path(cuda):
+    """Row-form gradient hand-over (fused.SPARSE_GRAD_SINK): a K=1 producer stack whose output is gathered by a
+    given-centres SA module must receive the same gradient through the sink as through autograd's dense path,
+    with and without an additional dense consumer of the producer's output."""
+    import torch.nn as nn
+    from hotrack_b200 import fused, pointnet_utils as pu
+
+    torch.manual_seed(0)
+    B, N = 3, 1024
+    xyz = torch.from_numpy(clouds.ball(B, N, seed=8)).to(cuda).transpose(1, 2).contiguous()
+    cen = torch.from_numpy(clouds.keypoints(B, 21, seed=8)).to(cuda).transpose(1, 2).contiguous()
+    x0 = torch.randn(B, 64, N, device=cuda)
+    convs = nn.ModuleList([nn.Conv1d(64, 128, 1)]).to(cuda)
+    bns = nn.ModuleList([nn.BatchNorm1d(128)]).to(cuda)
+    pu.set_engine("fused")
+    q = pu.PointNetSetAbstractionMsg_GivenCenterPoints([0.2, 0.2], [16, 32], [[32, 64], [32, 64]], 128 + 3, knn=True).to(cuda)
+    pu.set_engine("ops")
+    params = list(convs.parameters()) + list(bns.parameters()) + list(q.parameters())
+    try:
+        for with_dense_term in (False, True):
+            res = []
+            for sink in (False, True):
+                fused.set_sparse_grad_sink(sink)
+                for p_ in params:
+                    p_.grad = None
+                x = x0.clone().requires_grad_(True)
+                feats = fused.dense_stack(x, convs, bns, True)
+                out = q(xyz, feats, cen, None)
+                loss = out.square().sum()
+                if with_dense_term:
+                    loss = loss + feats.square().sum() * 1e-2
+                loss.backward()
+                res.append([x.grad.clone()] + [p_.grad.clone() for p_ in params if p_.grad is not None and p_.dim() > 0])
+            assert len(res[0]) == len(res[1])
+            for a, b in zip(res[0], res[1]):
+                if a.abs().max() < 1e-3:
+                    continue  # conv biases in front of BatchNorm
+                assert _rel(b, a) < 1e-2, (with_dense_term, tuple(a.shape), _rel(b, a))
+    finally:
+        fused.set_sparse_grad_sink(False)
