@@ -80,9 +80,15 @@ def test_config2_path_forward_backward_matches_reference(ref, cuda, train):
     lt = sum(v.square().mean() for v in t[:3])
     lo.backward()
     lt.backward()
+    gmax = max(p.grad.abs().max().item() for p in theirs.parameters() if p.grad is not None)
     for (n1, p1), (n2, p2) in zip(ours.named_parameters(), theirs.named_parameters()):
         assert n1 == n2
         if p2.grad is None:
+            continue
+        if p2.grad.abs().max().item() < 1e-6 * gmax:
+            # mathematically zero gradients (e.g. SA3's last BatchNorm bias: FP3's train-mode BatchNorm cancels
+            # any per-channel constant of the broadcast global feature): both sides hold fp32 rounding noise
+            assert p1.grad.abs().max().item() < 1e-5 * gmax, n1
             continue
         if n1.endswith(".bias") and ("conv" in n1):
             # a conv bias in front of train-mode BatchNorm has an exactly-zero gradient in real

@@ -225,3 +225,26 @@ def test_bad_arguments_raise(ops, cuda):
                        torch.zeros(1, 8, 5000, dtype=torch.int32, device=cuda))
     with pytest.raises(ValueError):
         pc.three_nn_wrapper(1, 8, 8, x.cpu(), x, x, x)
+
+
+def test_data_loader_fps_matches_reference_semantics(cuda):
+    """datasets/data_utils.farthest_point_sample (B=1, <= 5*npoint points, npoint=512) and the
+    batched variant; checked against the oracle on the points the function actually samples from."""
+    from hotrack_b200 import data_utils
+
+    rng = np.random.RandomState(0)
+    small = clouds.ball(1, 2000, seed=31)[0]          # <= 5*512: used as is
+    big = clouds.shell(1, 9000, seed=32)[0]           # > 5*512: random 2560-subset first
+    np.random.seed(5)
+    got = data_utils.farthest_point_sample(small, 512, cuda)
+    np.testing.assert_array_equal(got, orc.furthest_point_sample(small[None], 512)[0])
+    np.random.seed(5)
+    got = data_utils.farthest_point_sample(big, 512, cuda)
+    np.random.seed(5)
+    sub = np.random.permutation(len(big))[:2560]
+    np.testing.assert_array_equal(got, sub[orc.furthest_point_sample(big[sub][None], 512)[0]])
+    # batched: ragged clouds in one launch == one call per cloud
+    cl = [clouds.ball(1, n, seed=40 + n)[0] for n in (700, 2560, 1500)]
+    batch = data_utils.sample_batch(cl, 512, cuda)
+    for c, b in zip(cl, batch):
+        np.testing.assert_array_equal(b, orc.furthest_point_sample(c[None], 512)[0])

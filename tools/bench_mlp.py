@@ -107,6 +107,16 @@ def main():
         nb = fused.alg_bytes("pn2_pool_bwd", args[1:])
         out.append(dict(kernel="pool_bwd", case=name, us=round(t, 1), GBs=round(nb / t / 1e3, 1)))
         print(out[-1], flush=True)
+    for name, (B, C, N) in {"to_rows_q": (32, 192, 21), "to_rows_sa1": (32, 64, 256)}.items():
+        if flt and flt not in name:
+            continue
+        src = torch.randn(B, C, N, device=dev)
+        sums = torch.randn(C, device=dev)
+        dst = torch.empty(B * N, C, dtype=HF, device=dev)
+        args = ("pn2_to_rows", B, C, N, src.data_ptr(), sums.data_ptr(), 0.01, dst.data_ptr(), C, st())
+        t = timeit(lambda: _lib.call(*args))
+        out.append(dict(kernel="to_rows", case=name, us=round(t, 1)))
+        print(out[-1], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bench_mlp.json"), "w"), indent=1)
 
