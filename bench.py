@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="ours: dispatch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=8, help="clouds in the cpu_baseline sample")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu: skip the e2e leg, the per-kernel probe pass and the cpu baseline (the printed "
+                         "line is then NOT a bench value)")
     return ap.parse_args()
 
 
@@ -337,14 +340,14 @@ def main():
     if sampler:
         sampler.start()
     ms_dev = timed(K, from_host=False)
-    ms_e2e = timed(K, from_host=True)
+    ms_e2e = ms_dev if args.profile_mode else timed(K, from_host=True)
     clocks = sampler.stop() if sampler else None
 
     # Per-kernel device times of OUR kernels, CUDA events around every C-ABI call.  A replayed CUDA graph
     # cannot be bracketed kernel by kernel, so this pass dispatches the same step eagerly (same kernels, same
     # shapes, same process, right after the timed region); the launch count per step comes from it too.
     probe, launches = None, 0
-    if _lib:  # every rank steps (the gradient all-reduce needs all of them), rank 0 records
+    if _lib and not args.profile_mode:  # every rank steps (the gradient all-reduce needs all of them), rank 0 records
         n_probe = 3
         train.use_graph, was = False, train.use_graph
         step(xyz_d, kps_d)
@@ -384,6 +387,8 @@ def main():
         "gpu_launches": int(launches),  # kernels of libpn2b200.so inside the K timed steps (all ranks), counted by the library
         "clocks": clocks,
     }
+    if args.profile_mode:
+        line["invalid"] = "profile mode: e2e/probe/cpu legs skipped, not a bench value"
     if args.impl == "reference":
         line["impl"] = "reference"
         line["cpu_baseline"] = {"value": line["value"], "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
@@ -426,7 +431,7 @@ def main():
                             "timing": "CUDA events around each launch, eager probe pass after the timed region"}
         line["roofline"] = best
         line["kernel_shares"] = shares[:12]
-        if not ddp and not args.no_cpu_baseline:  # rank 0 at N=1 only
+        if not ddp and not args.no_cpu_baseline and not args.profile_mode:  # rank 0 at N=1 only
             try:
                 line["cpu_baseline"] = cpu_reference(args.cpu_sample, N, steps=3, warmup=1)
             except Exception as ex:  # oracle/_ref not staged

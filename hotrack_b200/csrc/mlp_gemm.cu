@@ -33,30 +33,13 @@
 // L2-resident) streams through cp.async; mma.sync.m16n8k16 bf16 with fp32 accumulation.  Every layer
 // of this network is far below the tensor roofline (K <= 800, N <= 512): the bound is the HBM
 // traffic of the row matrices, which is what the design minimises.
-#include "mma_common.cuh"
+#include "mlp_gemm.cuh"
 
 namespace pn2 {
 namespace {
 
 constexpr int BM = 128;
 constexpr int kThreads = 256;
-
-enum { A_PLAIN = 0, A_AFFINE = 1, A_BNBWD = 2 };
-
-struct GemmArgs {
-    long long rows;
-    int kdim, n;
-    const uint16_t* a0; int a0_ld;   // forward: x (fp16);  BNBWD: dz (bf16)
-    const uint16_t* a1; int a1_ld;   // BNBWD: y (fp16)
-    const float *c0, *c1, *c2;
-    const uint16_t* b;               // forward: w (fp16);  BNBWD: wt (bf16)
-    const float* center;  // [n] subtracted from the accumulators before bf16 rounding (nullable)
-    uint16_t* out; int out_ld;       // forward: y (fp16);  BNBWD: dz_prev (bf16)
-    float* sums;
-    const uint16_t* yp; int yp_ld;   // MASK: previous layer's y (fp16)
-    const float *p_scale, *p_shift, *p_mean, *p_rstd;
-    int nst, bres;                   // set by the launcher
-};
 
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
@@ -755,6 +738,7 @@ extern "C" int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, 
     a.center = center;
     a.out = (uint16_t*)y; a.out_ld = y_ld;
     a.sums = stats;
+    if (gemm_use_tc()) return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
     if (in_scale) return dispatch_bn<A_AFFINE, false>(a, (cudaStream_t)stream);
     return dispatch_bn<A_PLAIN, false>(a, (cudaStream_t)stream);
 }
@@ -782,9 +766,11 @@ extern "C" int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const vo
         a.sums = sums_prev;
         a.yp = (const uint16_t*)y_prev; a.yp_ld = y_prev_ld;
         a.p_scale = prev_scale; a.p_shift = prev_shift; a.p_mean = prev_mean; a.p_rstd = prev_rstd;
+        if (gemm_use_tc()) return launch_gemm_tc(a, A_BNBWD, true, (cudaStream_t)stream);
         return dispatch_bn<A_BNBWD, true>(a, (cudaStream_t)stream);
     }
     a.sums = nullptr;
+    if (gemm_use_tc()) return launch_gemm_tc(a, A_BNBWD, false, (cudaStream_t)stream);
     return dispatch_bn<A_BNBWD, false>(a, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,31 @@
+// mlp_gemm.cuh -- argument block shared by the two implementations of the row-matrix GEMM
+// (mlp_gemm_tc.cu: tcgen05 / TMEM, the production path; mlp_gemm.cu: warp-level mma.sync, kept as the
+// cross-check the tests and tools/dev/gemm_tc_check.cu compare against, PN2_GEMM_IMPL=mma).
+#pragma once
+#include "mma_common.cuh"
+
+namespace pn2 {
+
+enum { A_PLAIN = 0, A_AFFINE = 1, A_BNBWD = 2 };
+
+struct GemmArgs {
+    long long rows;
+    int kdim, n;
+    const uint16_t* a0; int a0_ld;   // forward: x (fp16);  BNBWD: dz (bf16)
+    const uint16_t* a1; int a1_ld;   // BNBWD: y (fp16)
+    const float *c0, *c1, *c2;
+    const uint16_t* b;               // forward: w (fp16);  BNBWD: wt (bf16)
+    const float* center;  // [n] subtracted from the accumulators before 16-bit rounding (nullable)
+    uint16_t* out; int out_ld;       // forward: y (fp16);  BNBWD: dz_prev (bf16)
+    float* sums;
+    const uint16_t* yp; int yp_ld;   // MASK: previous layer's y (fp16)
+    const float *p_scale, *p_shift, *p_mean, *p_rstd;
+    int nst, bres;                   // set by the mma.sync launcher
+};
+
+// tcgen05 implementation (mlp_gemm_tc.cu).  amode: A_PLAIN / A_AFFINE / A_BNBWD; mask: ReLU-mask epilogue.
+int launch_gemm_tc(const GemmArgs& a, int amode, bool mask, cudaStream_t stream);
+// which implementation pn2_mlp_gemm_fwd / pn2_mlp_gemm_dgrad dispatch to (env PN2_GEMM_IMPL = tc | mma, default tc)
+bool gemm_use_tc();
+
+}  // namespace pn2

@@ -1,0 +1,513 @@
+// mlp_gemm_tc.cu -- the row-matrix GEMM of the grouped per-point MLP on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM), sm_100a.  Same contract as mlp_gemm.cu's gemm_rows_kernel:
+//
+//     C[R][n] = A'[R][k] * B[n][k]^T          A' = A | relu(A*scale+shift) | cA*dZ + cB*Y + cC
+//     epilogue: - centre[n], 16-bit rounding, column sums (BatchNorm statistics) or, with MASK,
+//               ReLU mask of the previous layer + the two BatchNorm-backward sums
+//
+// replacing the conv1x1 -> BatchNorm -> ReLU launches of reference pointnet_utils.py:399-403,458-460,
+// 505-507,577-580 and backbones.py:131-132 (and their backward).
+//
+// Why not TMA for A: the A operand is never the matrix in memory -- BatchNorm+ReLU of the producing
+// layer (forward) or the BatchNorm-backward combination of two matrices (backward) is applied on the
+// way in, so a thread has to touch every element between HBM and the tensor core.  The kernel is
+// therefore warp-specialised around that:
+//
+//   8 producer warps  cp.async 16-byte pieces of the A (and B) chunk straight into the UMMA canonical
+//                     K-major SWIZZLE_128B layout (row pitch 128 B, piece index XOR row%8), D chunks
+//                     in flight per thread; when a chunk has landed each thread transforms ITS pieces in
+//                     place (fp32 math, one rounding), fence.proxy.async, arrives on the stage's mbarrier
+//   1 MMA warp        one elected lane: waits the stage, issues 4 x tcgen05.mma (M=128, N=BN, K=16) per
+//                     64-wide chunk, tcgen05.commit -> frees the stage / publishes the accumulator
+//   4 epilogue warps  tcgen05.ld 32 lanes x 32 columns -> - centre -> 16-bit tile in shared memory ->
+//                     16-byte coalesced row stores + per-thread column sums (same scheme as the
+//                     mma.sync kernel), two TMEM accumulator stages so tile i+1 is multiplied while
+//                     tile i is written out
+//
+// Bound: HBM traffic of the row matrices (rows*(k+n)*2 bytes, + the masks backward); per 128x128 output
+// tile the tensor pipe needs ~0.1 us, the producers ~0.4 us of issue slots, the epilogue ~0.35 us.
+#include "mlp_gemm.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace pn2 {
+namespace {
+
+constexpr int TM = 128;          // rows per tile = UMMA M
+constexpr int TK = 64;           // K chunk: 64 x 16-bit = one 128-byte swizzle row
+constexpr int kEpiWarps = 4;     // warps 0..3: TMEM lane quarter = warp index
+constexpr int kMmaWarp = 4;
+constexpr int kProdWarps = 8;    // warps 5..12
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kTcThreads = (kEpiWarps + 1 + kProdWarps) * 32;
+constexpr int kMaxK = 1024;
+constexpr int kSmemBudget = 225 * 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16/bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// UMMA shared-memory descriptor of a K-major SWIZZLE_128B operand tile (rows x 64 16-bit elements, 128-byte row
+// pitch, 1024-byte aligned): start address >> 4 in [0,14), LBO (ignored for swizzled K-major) = 1 in [16,30),
+// SBO = 1024 B (one 8-row group) >> 4 in [32,46), descriptor version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// stage = [A0 16 KB][A1 16 KB, BNBWD only][B BN*128 B]
+template <int BN, int AMODE>
+struct TcCfg {
+    static constexpr int kABytes = TM * 128;
+    static constexpr int kNA = AMODE == A_BNBWD ? 2 : 1;
+    static constexpr int kStage = kABytes * kNA + BN * 128;
+    static constexpr int kEpiBN = BN < 128 ? BN : 128;         // columns per epilogue pass
+    static constexpr int kCLD = kEpiBN + 8;                    // 16-bit elements per sC row
+    static constexpr int kSC = TM * kCLD * 2;
+    static constexpr int kNCoef = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
+    static constexpr int kFixed = kSC + kNCoef * kMaxK * 4 + 5 * BN * 4 + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int kNstRaw = (kSmemBudget - kFixed) / kStage;
+    static constexpr int kNst = kNstRaw > 6 ? 6 : kNstRaw;
+    static constexpr int kDist = kNst - 1;                     // chunks in flight per producer thread
+    static_assert(kNst >= 2, "not enough shared memory for a two-stage ring");
+};
+
+template <int BN, int AMODE, bool MASK>
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p) {
+    using Cfg = TcCfg<BN, AMODE>;
+    constexpr int NST = Cfg::kNst, D = Cfg::kDist;
+    constexpr int EBN = Cfg::kEpiBN, CLD = Cfg::kCLD, NH = BN / EBN;
+    constexpr int CPR = EBN / 8;          // 16-byte pieces per sC row
+    constexpr int RPP = 128 / CPR;        // rows per epilogue pass
+    constexpr int PASSES = TM / RPP;
+    constexpr bool FWD = AMODE != A_BNBWD;
+    constexpr int NCOEF = Cfg::kNCoef;
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    unsigned char* base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // SWIZZLE_128B tiles: 1024-byte aligned
+    unsigned char* sStage = base;
+    uint16_t* sC = reinterpret_cast<uint16_t*>(base + NST * Cfg::kStage);
+    float* sCoef = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sC) + Cfg::kSC);
+    const int kpad = (p.kdim + TK - 1) / TK * TK;
+    float* sPrev = sCoef + NCOEF * kpad;        // [4][BN], MASK only
+    float* sCen = sPrev + 4 * BN;               // [BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sCen + BN);  // 8-byte aligned: every size above is a multiple of 8
+    uint64_t* full = bars;                      // [NST] producers -> MMA
+    uint64_t* empty = bars + NST;               // [NST] MMA -> producers
+    uint64_t* tfull = bars + 2 * NST;           // [2]   MMA -> epilogue
+    uint64_t* tempty = bars + 2 * NST + 2;      // [2]   epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.y * BN;
+    const int KT = kpad / TK;
+    const long long tiles = (p.rows + TM - 1) / TM;
+    const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    // ---- one-time setup
+    for (int i = tid; i < NCOEF * kpad; i += kTcThreads) {
+        const int which = i / kpad, c = i - which * kpad;
+        const float* src = which == 0 ? p.c0 : (which == 1 ? p.c1 : p.c2);
+        sCoef[i] = c < p.kdim ? src[c] : 0.f;
+    }
+    for (int i = tid; i < BN; i += kTcThreads) sCen[i] = (p.center && n0 + i < p.n) ? p.center[n0 + i] : 0.f;
+    if (MASK) {
+        for (int i = tid; i < 4 * BN; i += kTcThreads) {
+            const int which = i / BN, c = n0 + (i - which * BN);
+            const float* src = which == 0 ? p.p_scale : (which == 1 ? p.p_shift : (which == 2 ? p.p_mean : p.p_rstd));
+            sPrev[i] = c < p.n ? src[c] : 0.f;
+        }
+    }
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&full[i], kProdThreads);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], kEpiWarps * 32);
+        }
+        mbar_fence_init();
+    }
+    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two: BN in {32,64,128,256}
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp > kMmaWarp) {
+        // ================================ producers ================================
+        const int pt = tid - (kMmaWarp + 1) * 32;  // 0..255
+        const int pj = pt & 7;                      // 16-byte piece of the 128-byte row
+        const int pr = pt >> 3;                     // rows pr + 32*i
+        const long long total = my_tiles * KT;
+        long long i_tile = blockIdx.x, p_tile = blockIdx.x;
+        int i_kc = 0, i_slot = 0, p_kc = 0, p_slot = 0;
+        uint32_t i_phase = 0;
+        for (long long c = 0; c < total + D; ++c) {
+            if (c < total) {
+                mbar_wait(&empty[i_slot], i_phase ^ 1);  // the MMAs that read this slot NST chunks ago have completed
+                unsigned char* st = sStage + i_slot * Cfg::kStage;
+                const int kcol = i_kc * TK + pj * 8;
+                const bool kok = kcol < p.kdim;
+#pragma unroll
+                for (int i = 0; i < TM / 32; ++i) {
+                    const int r = pr + 32 * i;
+                    const long long row = i_tile * TM + r;
+                    const bool ok = kok && row < p.rows;
+                    const uint32_t off = r * 128 + ((pj ^ (r & 7)) << 4);
+                    cp_async16(st + off, p.a0 + (ok ? row * p.a0_ld + kcol : 0), ok ? 16 : 0);
+                    if (AMODE == A_BNBWD)
+                        cp_async16(st + Cfg::kABytes + off, p.a1 + (ok ? row * p.a1_ld + kcol : 0), ok ? 16 : 0);
+                }
+                unsigned char* sb = st + Cfg::kABytes * Cfg::kNA;
+#pragma unroll
+                for (int i = 0; i < BN / 32; ++i) {
+                    const int r = pr + 32 * i;
+                    const bool ok = kok && n0 + r < p.n;
+                    cp_async16(sb + r * 128 + ((pj ^ (r & 7)) << 4), p.b + (ok ? (size_t)(n0 + r) * p.kdim + kcol : 0),
+                               ok ? 16 : 0);
+                }
+                if (++i_kc == KT) { i_kc = 0; i_tile += gridDim.x; }
+                if (++i_slot == NST) { i_slot = 0; i_phase ^= 1; }
+            }
+            cp_async_commit();  // always: the group count stays in step with c
+            if (c >= D) {
+                cp_wait<D>();   // this thread's pieces of chunk c - D have landed
+                if (AMODE != A_PLAIN) {
+                    unsigned char* st = sStage + p_slot * Cfg::kStage;
+                    const int cc = p_kc * TK + pj * 8;
+                    const float4 ka0 = *reinterpret_cast<const float4*>(&sCoef[cc]);
+                    const float4 ka1 = *reinterpret_cast<const float4*>(&sCoef[cc + 4]);
+                    const float4 kb0 = *reinterpret_cast<const float4*>(&sCoef[kpad + cc]);
+                    const float4 kb1 = *reinterpret_cast<const float4*>(&sCoef[kpad + cc + 4]);
+                    const float k0[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
+                    const float k1[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
+                    float k2[8];
+                    if (AMODE == A_BNBWD) {
+                        const float4 kc0 = *reinterpret_cast<const float4*>(&sCoef[2 * kpad + cc]);
+                        const float4 kc1 = *reinterpret_cast<const float4*>(&sCoef[2 * kpad + cc + 4]);
+                        k2[0] = kc0.x; k2[1] = kc0.y; k2[2] = kc0.z; k2[3] = kc0.w;
+                        k2[4] = kc1.x; k2[5] = kc1.y; k2[6] = kc1.z; k2[7] = kc1.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < TM / 32; ++i) {
+                        const int r = pr + 32 * i;
+                        const uint32_t off = r * 128 + ((pj ^ (r & 7)) << 4);
+                        uint4* slot = reinterpret_cast<uint4*>(st + off);
+                        const uint4 q0 = *slot;
+                        const uint32_t* x0 = reinterpret_cast<const uint32_t*>(&q0);
+                        uint4 v;
+                        uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+                        if (AMODE == A_AFFINE) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 a = h2_to_f2(x0[e]);
+                                o[e] = f2_to_h2(fmaxf(fmaf(a.x, k0[2 * e], k1[2 * e]), 0.f),
+                                                fmaxf(fmaf(a.y, k0[2 * e + 1], k1[2 * e + 1]), 0.f));
+                            }
+                        } else {
+                            const uint4 q1 = *reinterpret_cast<const uint4*>(st + Cfg::kABytes + off);
+                            const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&q1);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 a = bf2_to_f2(x0[e]);
+                                const float2 y = h2_to_f2(x1[e]);
+                                o[e] = f2_to_bf2(fmaf(k0[2 * e], a.x, fmaf(k1[2 * e], y.x, k2[2 * e])),
+                                                 fmaf(k0[2 * e + 1], a.y, fmaf(k1[2 * e + 1], y.y, k2[2 * e + 1])));
+                            }
+                        }
+                        *slot = v;
+                    }
+                }
+                fence_proxy_async();  // generic-proxy writes (cp.async + the in-place transform) -> visible to the tensor core
+                mbar_arrive(&full[p_slot]);
+                if (++p_kc == KT) { p_kc = 0; p_tile += gridDim.x; }
+                if (++p_slot == NST) p_slot = 0;
+            }
+        }
+        (void)p_tile;
+    } else if (warp == kMmaWarp) {
+        // ================================ MMA issuer ================================
+        // instruction descriptor: D fp32 [4,6)=1, A/B format [7,10)/[10,13) (0 fp16, 1 bf16), both K-major, N>>3 [17,23), M>>4 [24,29)
+        constexpr uint32_t fmt = FWD ? 0u : 1u;
+        constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        int slot = 0;
+        uint32_t phase = 0, as = 0, aphase = 0;
+        for (long long t = 0; t < my_tiles; ++t) {
+            mbar_wait(&tempty[as], aphase ^ 1);  // the epilogue has drained this accumulator stage
+            tc_fence_after();
+            for (int kc = 0; kc < KT; ++kc) {
+                mbar_wait(&full[slot], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(sStage + slot * Cfg::kStage);
+                    const uint64_t adesc = umma_desc_k128(sa);
+                    const uint64_t bdesc = umma_desc_k128(sa + Cfg::kABytes * Cfg::kNA);
+                    const int ksteps = min(TK / 16, (p.kdim - kc * TK + 15) / 16);
+                    for (int k4 = 0; k4 < ksteps; ++k4)  // +32 bytes (>>4 = 2) along K inside the swizzle atom
+                        umma_f16(tmem_base + as * BN, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kc | k4) != 0);
+                    tc_commit(&empty[slot]);               // arrives when the MMAs above have finished reading the stage
+                    if (kc == KT - 1) tc_commit(&tfull[as]);
+                }
+                __syncwarp();
+                if (++slot == NST) { slot = 0; phase ^= 1; }
+            }
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int chunk = tid % CPR, r0 = tid / CPR;
+        float s1[NH][8], s2[NH][8];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s1[h][e] = s2[h][e] = 0.f;
+        uint32_t as = 0, aphase = 0;
+        long long tile = blockIdx.x;
+        for (long long t = 0; t < my_tiles; ++t, tile += gridDim.x) {
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                const int col0 = n0 + h * EBN + chunk * 8;  // first of this thread's 8 output columns (pass 2)
+                uint4 yq[MASK ? PASSES : 1];
+                if (MASK && col0 < p.n) {
+#pragma unroll
+                    for (int ps = 0; ps < PASSES; ++ps) {
+                        const long long grow = tile * TM + r0 + ps * RPP;
+                        if (grow < p.rows) yq[ps] = __ldg(reinterpret_cast<const uint4*>(p.yp + grow * p.yp_ld + col0));
+                    }
+                }
+                // pass 1: TMEM -> registers -> 16-bit tile in shared memory (thread = row, 32 columns at a time)
+#pragma unroll
+                for (int c32 = 0; c32 < EBN; c32 += 32) {
+                    if (n0 + h * EBN + c32 < p.n) {  // warp-uniform
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + h * EBN + c32, v);
+                        const int r = warp * 32 + lane;
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            uint4 q;
+                            uint32_t* qq = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = h * EBN + c32 + g8 * 8 + 2 * e;
+                                const float a = __uint_as_float(v[g8 * 8 + 2 * e]) - sCen[c];
+                                const float b = __uint_as_float(v[g8 * 8 + 2 * e + 1]) - sCen[c + 1];
+                                qq[e] = FWD ? f2_to_h2(a, b) : f2_to_bf2(a, b);
+                            }
+                            *reinterpret_cast<uint4*>(&sC[r * CLD + c32 + g8 * 8]) = q;
+                        }
+                    }
+                }
+                if (h == NH - 1) {  // every tcgen05.ld of this accumulator stage has completed
+                    tc_fence_before();
+                    mbar_arrive(&tempty[as]);
+                }
+                epi_bar();
+                // pass 2: 16-byte pieces, coalesced stores, column sums in registers
+                if (col0 < p.n) {
+                    float ps_[8], ph_[8], pm_[8], pr_[8];
+                    if (MASK) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = h * EBN + chunk * 8 + e;
+                            ps_[e] = sPrev[c]; ph_[e] = sPrev[BN + c]; pm_[e] = sPrev[2 * BN + c]; pr_[e] = sPrev[3 * BN + c];
+                        }
+                    }
+#pragma unroll
+                    for (int ps = 0; ps < PASSES; ++ps) {
+                        const int r = r0 + ps * RPP;
+                        const long long grow = tile * TM + r;
+                        if (grow < p.rows) {
+                            uint4 v = *reinterpret_cast<const uint4*>(&sC[r * CLD + chunk * 8]);
+                            uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
+                            if (MASK) {
+                                const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yq[ps]);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 d = bf2_to_f2(vv[e]);  // MASK is a backward epilogue: bf16 tile
+                                    const float2 y = h2_to_f2(yy[e]);
+                                    const float a0 = fmaf(y.x, ps_[2 * e], ph_[2 * e]);
+                                    const float a1 = fmaf(y.y, ps_[2 * e + 1], ph_[2 * e + 1]);
+                                    d.x = a0 > 0.f ? d.x : 0.f;
+                                    d.y = a1 > 0.f ? d.y : 0.f;
+                                    const float h0 = (y.x - pm_[2 * e]) * pr_[2 * e];
+                                    const float h1 = (y.y - pm_[2 * e + 1]) * pr_[2 * e + 1];
+                                    s1[h][2 * e] += d.x; s1[h][2 * e + 1] += d.y;
+                                    s2[h][2 * e] = fmaf(d.x, h0, s2[h][2 * e]);
+                                    s2[h][2 * e + 1] = fmaf(d.y, h1, s2[h][2 * e + 1]);
+                                    vv[e] = f2_to_bf2(d.x, d.y);
+                                }
+                            } else if (p.sums) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 d = FWD ? h2_to_f2(vv[e]) : bf2_to_f2(vv[e]);
+                                    s1[h][2 * e] += d.x; s1[h][2 * e + 1] += d.y;
+                                    s2[h][2 * e] = fmaf(d.x, d.x, s2[h][2 * e]);
+                                    s2[h][2 * e + 1] = fmaf(d.y, d.y, s2[h][2 * e + 1]);
+                                }
+                            }
+                            *reinterpret_cast<uint4*>(p.out + grow * p.out_ld + col0) = v;
+                        }
+                    }
+                }
+                epi_bar();  // sC is rewritten by the next pass 1
+            }
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+        if (p.sums) {
+            // column sums: the RPP threads sharing a column piece combine through shared memory, one atomic per column
+            float* red = reinterpret_cast<float*>(sC);  // [RPP][2][EBN] floats <= TM*CLD*2 bytes
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    red[(r0 * 2 + 0) * EBN + chunk * 8 + e] = s1[h][e];
+                    red[(r0 * 2 + 1) * EBN + chunk * 8 + e] = s2[h][e];
+                }
+                epi_bar();
+                for (int i = tid; i < 2 * EBN; i += kEpiWarps * 32) {
+                    const int which = i / EBN, c = i - which * EBN;
+                    const int col = n0 + h * EBN + c;
+                    if (col < p.n) {
+                        float s = 0.f;
+#pragma unroll 8
+                        for (int j = 0; j < RPP; ++j) s += red[(j * 2 + which) * EBN + c];
+                        atomicAdd(p.sums + (size_t)which * p.n + col, s);
+                    }
+                }
+                epi_bar();
+            }
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int BN, int AMODE, bool MASK>
+int launch_tc(const GemmArgs& a, cudaStream_t stream) {
+    using Cfg = TcCfg<BN, AMODE>;
+    const int kpad = (a.kdim + TK - 1) / TK * TK;
+    const size_t smem = (size_t)Cfg::kNst * Cfg::kStage + Cfg::kSC + (size_t)Cfg::kNCoef * kpad * 4 + 5 * BN * 4 + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        PN2_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmemBudget),
+                  "gemm_tc: cudaFuncSetAttribute");
+        configured = true;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long tiles = (a.rows + TM - 1) / TM;
+    const int ny = (a.n + BN - 1) / BN;
+    long long gx = sms / ny;  // persistent: one CTA per SM (shared memory, TMEM), tiles dealt round-robin
+    if (gx < 1) gx = 1;
+    if (gx > tiles) gx = tiles;
+    gemm_tc_kernel<BN, AMODE, MASK><<<dim3((unsigned)gx, ny), kTcThreads, smem, stream>>>(a);
+    PN2_CHECK_LAUNCH("gemm_tc_kernel");
+    return 0;
+}
+
+// column-tile width: the widest of {256 (forward only), 128, 64, 32} that wastes the fewest padded columns
+int pick_bn(int n, bool fwd) {
+    int best = 32, best_waste = 1 << 30;
+    const int cands[4] = {fwd ? 256 : 128, 128, 64, 32};
+    for (int i = 0; i < 4; ++i) {
+        const int bn = cands[i];
+        const int waste = (n + bn - 1) / bn * bn - n;
+        if (waste < best_waste) { best = bn; best_waste = waste; }
+    }
+    return best;
+}
+
+template <int AMODE, bool MASK>
+int dispatch_tc(const GemmArgs& a, cudaStream_t stream) {
+    constexpr bool FWD = AMODE != A_BNBWD;
+    switch (pick_bn(a.n, FWD)) {
+        case 256:
+            if constexpr (FWD) return launch_tc<256, AMODE, MASK>(a, stream);
+            return launch_tc<128, AMODE, MASK>(a, stream);
+        case 128: return launch_tc<128, AMODE, MASK>(a, stream);
+        case 64: return launch_tc<64, AMODE, MASK>(a, stream);
+        default: return launch_tc<32, AMODE, MASK>(a, stream);
+    }
+}
+
+}  // namespace
+
+bool gemm_use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PN2_GEMM_IMPL");
+        v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
+int launch_gemm_tc(const GemmArgs& a, int amode, bool mask, cudaStream_t stream) {
+    if (a.kdim > kMaxK) return fail_arg("pn2_mlp_gemm", "reduction dimension > 1024");
+    if (amode == A_PLAIN) return dispatch_tc<A_PLAIN, false>(a, stream);
+    if (amode == A_AFFINE) return dispatch_tc<A_AFFINE, false>(a, stream);
+    if (mask) return dispatch_tc<A_BNBWD, true>(a, stream);
+    return dispatch_tc<A_BNBWD, false>(a, stream);
+}
+
+}  // namespace pn2

@@ -424,33 +424,73 @@ struct SaBwdArgs {
     int cen_c; float* dcen_cm;     // (B,cen_c,S)  zeroed, atomics
     int xyz_first;
 };
+// Vector reduction into global memory: one 16-byte red.global.add.v4.f32 (sm_90+) instead of four scalar atomics.
+__device__ __forceinline__ void red_add_v4(float* dst, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+// One CTA per group (b, s); warps walk the group's K rows.
+//   feature columns  -> scattered to the gathered point's gradient: row-form destination = coalesced 16-byte vector
+//                       reductions (lane = 4 channels); channel-major destination = scalar atomics
+//   centre columns   -> every row of the group adds into the SAME (b, :, s) column, so the K rows are summed in
+//                       registers first and the group issues one atomic per channel (not K same-address atomics)
 __global__ void __launch_bounds__(kThreads) sa_rows_bwd_kernel(const SaBwdArgs a) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const long long total = (long long)a.b * a.s * a.k;
-    if (row >= total) return;
-    const int kk = (int)(row % a.k);
-    const long long bs = row / a.k;
-    const int s = (int)(bs % a.s), b = (int)(bs / a.s);
-    const int j = a.idx ? a.idx[row] : kk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = blockIdx.x;  // b * s + s_idx
+    const int s = grp % a.s, b = grp / a.s;
     const int fc = a.dfeat_cm ? a.feat_c : 0, cc = a.dcen_cm ? a.cen_c : 0;
     const int f0 = a.xyz_first ? 3 : 0, c0 = a.feat_c + 3;
-    const bf16* d = a.dx + (size_t)row * a.dx_ld;
-    if (a.feat_rows_major) {  // lanes along the contiguous channel dimension: coalesced reductions
-        float* dst = a.dfeat_cm + ((size_t)b * a.n + j) * a.feat_c;
-        for (int col = lane; col < fc; col += 32) {
-            const float v = bf_to_f(d[f0 + col]);
-            if (v != 0.f) atomicAdd(dst + col, v);
-        }
-    } else {
-        for (int col = lane; col < fc; col += 32) {
-            const float v = bf_to_f(d[f0 + col]);
-            if (v != 0.f) atomicAdd(a.dfeat_cm + ((size_t)b * a.feat_c + col) * a.n + j, v);
+    const bf16* dgrp = a.dx + (size_t)grp * a.k * a.dx_ld;
+    // few groups (group-all): gridDim.y CTAs share a group's rows
+    const int kchunk = (a.k + gridDim.y - 1) / gridDim.y;
+    const int k_lo = blockIdx.y * kchunk, k_hi = min(a.k, k_lo + kchunk);
+    if (fc > 0) {
+        const bool vec = a.feat_rows_major && (fc & 3) == 0 && (f0 & 3) == 0 && (a.dx_ld & 3) == 0;
+        for (int kk = k_lo + warp; kk < k_hi; kk += kThreads / 32) {
+            const int j = a.idx ? __ldg(a.idx + (size_t)grp * a.k + kk) : kk;
+            const bf16* d = dgrp + (size_t)kk * a.dx_ld + f0;
+            if (vec) {
+                float* dst = a.dfeat_cm + ((size_t)b * a.n + j) * fc;
+                for (int col = lane * 4; col < fc; col += 128) {
+                    const uint2 q = __ldg(reinterpret_cast<const uint2*>(d + col));
+                    const float2 v0 = bf2_to_f2(q.x), v1 = bf2_to_f2(q.y);
+                    if (q.x | q.y) red_add_v4(dst + col, v0.x, v0.y, v1.x, v1.y);
+                }
+            } else if (a.feat_rows_major) {
+                float* dst = a.dfeat_cm + ((size_t)b * a.n + j) * fc;
+                for (int col = lane; col < fc; col += 32) {
+                    const float v = bf_to_f(d[col]);
+                    if (v != 0.f) atomicAdd(dst + col, v);
+                }
+            } else {
+                for (int col = lane; col < fc; col += 32) {
+                    const float v = bf_to_f(d[col]);
+                    if (v != 0.f) atomicAdd(a.dfeat_cm + ((size_t)b * fc + col) * a.n + j, v);
+                }
+            }
         }
     }
-    for (int col = lane; col < cc; col += 32) {
-        const float v = bf_to_f(d[c0 + col]);
-        if (v != 0.f) atomicAdd(a.dcen_cm + ((size_t)b * a.cen_c + col) * a.s + s, v);
+    if (cc > 0) {
+        const bf16* d = dgrp + c0;
+        if (((c0 | a.dx_ld | cc) & 1) == 0) {
+            for (int col = threadIdx.x * 2; col < cc; col += kThreads * 2) {
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll 8
+                for (int kk = k_lo; kk < k_hi; ++kk) {
+                    const float2 v = bf2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(d + (size_t)kk * a.dx_ld + col)));
+                    t0 += v.x; t1 += v.y;
+                }
+                if (t0 != 0.f) atomicAdd(a.dcen_cm + ((size_t)b * cc + col) * a.s + s, t0);
+                if (t1 != 0.f) atomicAdd(a.dcen_cm + ((size_t)b * cc + col + 1) * a.s + s, t1);
+            }
+        } else {
+            for (int col = threadIdx.x; col < cc; col += kThreads) {
+                float t = 0.f;
+#pragma unroll 8
+                for (int kk = k_lo; kk < k_hi; ++kk) t += bf_to_f(d[(size_t)kk * a.dx_ld + col]);
+                if (t != 0.f) atomicAdd(a.dcen_cm + ((size_t)b * cc + col) * a.s + s, t);
+            }
+        }
     }
 }
 
@@ -643,7 +683,10 @@ extern "C" int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const
     a.b = b; a.n = n; a.s = s; a.k = k; a.idx = idx; a.dx = (const bf16*)dx; a.dx_ld = dx_ld;
     a.feat_c = feat_c; a.dfeat_cm = dfeat_cm; a.feat_rows_major = feat_rows_major;
     a.cen_c = cen_c; a.dcen_cm = dcen_cm; a.xyz_first = xyz_first;
-    sa_rows_bwd_kernel<<<warp_blocks((long long)b * s * k), kThreads, 0, (cudaStream_t)stream>>>(a);
+    const long long groups = (long long)b * s;
+    long long gy = groups >= 296 ? 1 : (592 + groups - 1) / groups;
+    if (gy > (k + 7) / 8) gy = (k + 7) / 8;
+    sa_rows_bwd_kernel<<<dim3((unsigned)groups, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("sa_rows_bwd_kernel");
     return 0;
 }

@@ -1,0 +1,21 @@
+#!/bin/bash
+# One gpurun call: [GPU tests,] both bench arms, ncu launch list, ncu --set full of the hot kernels.
+# usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh <tag> [tests] [ref] [full]'
+tag=${1:-run}; shift
+out=gpurun_out/$tag
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/smi.txt 2>&1
+for what in "$@"; do case $what in
+tests) timeout 900 python -m pytest tests -m gpu -x -q > $out/tests.log 2>&1; echo "tests rc=$?" >> $out/tests.log; tail -3 $out/tests.log;;
+ref) timeout 300 python bench.py --impl reference --steps 10 --warmup 3 > $out/bench_ref.json 2> $out/bench_ref.err; cut -c1-300 $out/bench_ref.json;;
+bench) timeout 400 python bench.py > $out/bench_ours.json 2> $out/bench_ours.err; cut -c1-300 $out/bench_ours.json;;
+launches) timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches.csv \
+    python bench.py --steps 1 --warmup 3 --profile-mode > $out/b_ncu.log 2>&1;;
+full) timeout 600 ncu --set full --clock-control none --import-source on \
+    -k regex:'gemm_rows_kernel|wgrad_kernel|sa_rows_bwd|pool_bwd|cm_to_rows|fps_regs|ball_query|knn_kernel|three_nn' \
+    --launch-skip ${FULL_SKIP:-300} --launch-count ${FULL_COUNT:-50} -o $out/full -f \
+    python bench.py --steps 1 --warmup 3 --profile-mode --no-graph > $out/full_ncu.log 2>&1
+  ncu -i $out/full.ncu-rep --page raw --csv > $out/full_raw.csv 2>/dev/null
+  sz=$(stat -c %s $out/full.ncu-rep); if [ "$sz" -gt 30000000 ]; then rm -f $out/full.ncu-rep; echo "rep dropped ($sz bytes)"; fi;;
+esac; done
+ls -la $out; du -sh gpurun_out
