@@ -427,17 +427,6 @@ int check_common(const char* who, long long rows, int kdim, int n) {
 // ------------------------------------------------------------------ wgrad -------------------
 constexpr int TN = 128, TK = 128, SLD = 128 + 8;
 
-struct WgradArgs {
-    long long rows;
-    int n, kp, k_true;
-    const bf16* dz; int dz_ld;
-    const act_t* y; int y_ld;
-    const float *cA, *cB, *cC;
-    const act_t* x; int x_ld;
-    const float *in_scale, *in_shift;
-    float* dw; int dw_ld;
-};
-
 // Stage = WBR rows x 128 columns of dz, y (-> dY in place over dz) and x (-> X' in place), brought in
 // by cp.async WST stages deep; one CTA per SM, >= 100 KB of loads in flight.
 constexpr int WBR = 64, WST = 3;
@@ -804,6 +793,7 @@ extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, con
                   "wgrad: cudaFuncSetAttribute");
         configured = true;
     }
+    if (gemm_use_tc() && wgrad_tc_supported(a)) return launch_wgrad_tc(a, (cudaStream_t)stream);
     if (in_scale)
         wgrad_kernel<true><<<grid, kWgradThreads, kWgradSmem, (cudaStream_t)stream>>>(a);
     else

@@ -23,6 +23,21 @@ struct GemmArgs {
     int nst, bres;                   // set by the mma.sync launcher
 };
 
+struct WgradArgs {
+    long long rows;
+    int n, kp, k_true;
+    const bf16* dz; int dz_ld;
+    const act_t* y; int y_ld;
+    const float *cA, *cB, *cC;
+    const act_t* x; int x_ld;
+    const float *in_scale, *in_shift;
+    float* dw; int dw_ld;
+};
+
+// tcgen05 weight-gradient kernel (mlp_wgrad_tc.cu); supported when the whole output-channel range fits TMEM (n <= 512)
+bool wgrad_tc_supported(const WgradArgs& a);
+int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream);
+
 // tcgen05 implementation (mlp_gemm_tc.cu).  amode: A_PLAIN / A_AFFINE / A_BNBWD; mask: ReLU-mask epilogue.
 int launch_gemm_tc(const GemmArgs& a, int amode, bool mask, cudaStream_t stream);
 // which implementation pn2_mlp_gemm_fwd / pn2_mlp_gemm_dgrad dispatch to (env PN2_GEMM_IMPL = tc | mma, default tc)

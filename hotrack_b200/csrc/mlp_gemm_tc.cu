@@ -19,7 +19,7 @@
 //                     place (fp32 math, one rounding), fence.proxy.async, arrives on the stage's mbarrier
 //   1 MMA warp        one elected lane: waits the stage, issues 4 x tcgen05.mma (M=128, N=BN, K=16) per
 //                     64-wide chunk, tcgen05.commit -> frees the stage / publishes the accumulator
-//   4 epilogue warps  tcgen05.ld 32 lanes x 32 columns -> - centre -> 16-bit tile in shared memory ->
+//   8 epilogue warps  (two per 32-lane TMEM quarter, half the columns each) tcgen05.ld -> - centre -> 16-bit tile in shared memory ->
 //                     16-byte coalesced row stores + per-thread column sums (same scheme as the
 //                     mma.sync kernel), two TMEM accumulator stages so tile i+1 is multiplied while
 //                     tile i is written out
@@ -27,6 +27,7 @@
 // Bound: HBM traffic of the row matrices (rows*(k+n)*2 bytes, + the masks backward); per 128x128 output
 // tile the tensor pipe needs ~0.1 us, the producers ~0.4 us of issue slots, the epilogue ~0.35 us.
 #include "mlp_gemm.cuh"
+#include "tc_common.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -36,50 +37,16 @@ namespace {
 
 constexpr int TM = 128;          // rows per tile = UMMA M
 constexpr int TK = 64;           // K chunk: 64 x 16-bit = one 128-byte swizzle row
-constexpr int kEpiWarps = 4;     // warps 0..3: TMEM lane quarter = warp index
-constexpr int kMmaWarp = 4;
-constexpr int kProdWarps = 8;    // warps 5..12
+constexpr int kEpiWarps = 8;     // warps 0..7: TMEM lane quarter = warp % 4, column half = warp / 4
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMmaWarp = 8;
+constexpr int kProdWarps = 8;    // warps 9..16
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kTcThreads = (kEpiWarps + 1 + kProdWarps) * 32;
 constexpr int kMaxK = 1024;
 constexpr int kSmemBudget = 225 * 1024;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16/bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // UMMA shared-memory descriptor of a K-major SWIZZLE_128B operand tile (rows x 64 16-bit elements, 128-byte row
 // pitch, 1024-byte aligned): start address >> 4 in [0,14), LBO (ignored for swizzled K-major) = 1 in [16,30),
@@ -88,9 +55,6 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // stage = [A0 16 KB][A1 16 KB, BNBWD only][B BN*128 B]
 template <int BN, int AMODE>
@@ -115,7 +79,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     constexpr int NST = Cfg::kNst, D = Cfg::kDist;
     constexpr int EBN = Cfg::kEpiBN, CLD = Cfg::kCLD, NH = BN / EBN;
     constexpr int CPR = EBN / 8;          // 16-byte pieces per sC row
-    constexpr int RPP = 128 / CPR;        // rows per epilogue pass
+    constexpr int RPP = kEpiThreads / CPR;  // rows per epilogue pass
+    constexpr int WC = EBN / 2;           // columns of a pass-1 warp (two warps share a 32-lane quarter)
+    constexpr int LDW = WC < 32 ? WC : 32;  // columns per tcgen05.ld
     constexpr int PASSES = TM / RPP;
     constexpr bool FWD = AMODE != A_BNBWD;
     constexpr int NCOEF = Cfg::kNCoef;
@@ -163,7 +129,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], kEpiWarps * 32);
+            mbar_init(&tempty[i], kEpiThreads);
         }
         mbar_fence_init();
     }
@@ -184,6 +150,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
         const int pt = tid - (kMmaWarp + 1) * 32;  // 0..255
         const int pj = pt & 7;                      // 16-byte piece of the 128-byte row
         const int pr = pt >> 3;                     // rows pr + 32*i
+        // row r = pr + 32*i of a chunk lives at r*128 + ((pj ^ (r & 7)) << 4): r & 7 == pr & 7, so the 4 (8) pieces of a
+        // thread are 4096 bytes apart
+        const uint32_t poff = pr * 128 + ((pj ^ (pr & 7)) << 4);
+        const uint32_t stage0 = smem_u32(sStage);
+        const size_t a0_step = (size_t)32 * p.a0_ld, a1_step = (size_t)32 * p.a1_ld, b_step = (size_t)32 * p.kdim;
+        const int n_left = p.n - n0 - pr;           // B rows pr + 32*i < n_left are real
         const long long total = my_tiles * KT;
         long long i_tile = blockIdx.x, p_tile = blockIdx.x;
         int i_kc = 0, i_slot = 0, p_kc = 0, p_slot = 0;
@@ -191,26 +163,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
         for (long long c = 0; c < total + D; ++c) {
             if (c < total) {
                 mbar_wait(&empty[i_slot], i_phase ^ 1);  // the MMAs that read this slot NST chunks ago have completed
-                unsigned char* st = sStage + i_slot * Cfg::kStage;
+                const uint32_t st = stage0 + i_slot * Cfg::kStage;
                 const int kcol = i_kc * TK + pj * 8;
                 const bool kok = kcol < p.kdim;
+                const long long row0 = i_tile * TM + pr;
+                const int rows_left = (int)min((long long)TM, p.rows - i_tile * TM) - pr;  // rows pr + 32*i < rows_left are real
+                const uint16_t* a0p = p.a0 + row0 * p.a0_ld + kcol;
+                const uint16_t* a1p = AMODE == A_BNBWD ? p.a1 + row0 * p.a1_ld + kcol : nullptr;
 #pragma unroll
                 for (int i = 0; i < TM / 32; ++i) {
-                    const int r = pr + 32 * i;
-                    const long long row = i_tile * TM + r;
-                    const bool ok = kok && row < p.rows;
-                    const uint32_t off = r * 128 + ((pj ^ (r & 7)) << 4);
-                    cp_async16(st + off, p.a0 + (ok ? row * p.a0_ld + kcol : 0), ok ? 16 : 0);
+                    const bool ok = kok && 32 * i < rows_left;
+                    cp_async16_s(st + poff + i * 4096, ok ? a0p + (size_t)i * a0_step : p.a0, ok ? 16 : 0);
                     if (AMODE == A_BNBWD)
-                        cp_async16(st + Cfg::kABytes + off, p.a1 + (ok ? row * p.a1_ld + kcol : 0), ok ? 16 : 0);
+                        cp_async16_s(st + Cfg::kABytes + poff + i * 4096, ok ? a1p + (size_t)i * a1_step : p.a1, ok ? 16 : 0);
                 }
-                unsigned char* sb = st + Cfg::kABytes * Cfg::kNA;
+                const uint32_t sb = st + Cfg::kABytes * Cfg::kNA;
+                const uint16_t* bp = p.b + (size_t)(n0 + pr) * p.kdim + kcol;
 #pragma unroll
                 for (int i = 0; i < BN / 32; ++i) {
-                    const int r = pr + 32 * i;
-                    const bool ok = kok && n0 + r < p.n;
-                    cp_async16(sb + r * 128 + ((pj ^ (r & 7)) << 4), p.b + (ok ? (size_t)(n0 + r) * p.kdim + kcol : 0),
-                               ok ? 16 : 0);
+                    const bool ok = kok && 32 * i < n_left;
+                    cp_async16_s(sb + poff + i * 4096, ok ? bp + (size_t)i * b_step : p.b, ok ? 16 : 0);
                 }
                 if (++i_kc == KT) { i_kc = 0; i_tile += gridDim.x; }
                 if (++i_slot == NST) { i_slot = 0; i_phase ^= 1; }
@@ -219,7 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
             if (c >= D) {
                 cp_wait<D>();   // this thread's pieces of chunk c - D have landed
                 if (AMODE != A_PLAIN) {
-                    unsigned char* st = sStage + p_slot * Cfg::kStage;
+                    unsigned char* st = sStage + p_slot * Cfg::kStage + poff;
                     const int cc = p_kc * TK + pj * 8;
                     const float4 ka0 = *reinterpret_cast<const float4*>(&sCoef[cc]);
                     const float4 ka1 = *reinterpret_cast<const float4*>(&sCoef[cc + 4]);
@@ -236,8 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                     }
 #pragma unroll
                     for (int i = 0; i < TM / 32; ++i) {
-                        const int r = pr + 32 * i;
-                        const uint32_t off = r * 128 + ((pj ^ (r & 7)) << 4);
+                        const uint32_t off = i * 4096;
                         uint4* slot = reinterpret_cast<uint4*>(st + off);
                         const uint4 q0 = *slot;
                         const uint32_t* x0 = reinterpret_cast<const uint32_t*>(&q0);
@@ -324,25 +295,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                         if (grow < p.rows) yq[ps] = __ldg(reinterpret_cast<const uint4*>(p.yp + grow * p.yp_ld + col0));
                     }
                 }
-                // pass 1: TMEM -> registers -> 16-bit tile in shared memory (thread = row, 32 columns at a time)
+                // pass 1: TMEM -> registers -> 16-bit tile in shared memory (thread = row; warp = 32 rows x WC columns)
+                const int q4 = warp & 3, wc0 = (warp >> 2) * WC;
 #pragma unroll
-                for (int c32 = 0; c32 < EBN; c32 += 32) {
-                    if (n0 + h * EBN + c32 < p.n) {  // warp-uniform
+                for (int cw = 0; cw < WC; cw += LDW) {
+                    const int cb = wc0 + cw;  // first column (within this EBN-wide pass) of this load
+                    if (n0 + h * EBN + cb < p.n) {  // warp-uniform
                         uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN + h * EBN + c32, v);
-                        const int r = warp * 32 + lane;
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * BN + h * EBN + cb;
+                        if (LDW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                        const int r = q4 * 32 + lane;
 #pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
+                        for (int g8 = 0; g8 < LDW / 8; ++g8) {
+                            const float4 ce0 = *reinterpret_cast<const float4*>(&sCen[h * EBN + cb + g8 * 8]);
+                            const float4 ce1 = *reinterpret_cast<const float4*>(&sCen[h * EBN + cb + g8 * 8 + 4]);
                             uint4 q;
-                            uint32_t* qq = reinterpret_cast<uint32_t*>(&q);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int c = h * EBN + c32 + g8 * 8 + 2 * e;
-                                const float a = __uint_as_float(v[g8 * 8 + 2 * e]) - sCen[c];
-                                const float b = __uint_as_float(v[g8 * 8 + 2 * e + 1]) - sCen[c + 1];
-                                qq[e] = FWD ? f2_to_h2(a, b) : f2_to_bf2(a, b);
-                            }
-                            *reinterpret_cast<uint4*>(&sC[r * CLD + c32 + g8 * 8]) = q;
+                            q.x = FWD ? f2_to_h2(__uint_as_float(v[g8 * 8 + 0]) - ce0.x, __uint_as_float(v[g8 * 8 + 1]) - ce0.y)
+                                      : f2_to_bf2(__uint_as_float(v[g8 * 8 + 0]) - ce0.x, __uint_as_float(v[g8 * 8 + 1]) - ce0.y);
+                            q.y = FWD ? f2_to_h2(__uint_as_float(v[g8 * 8 + 2]) - ce0.z, __uint_as_float(v[g8 * 8 + 3]) - ce0.w)
+                                      : f2_to_bf2(__uint_as_float(v[g8 * 8 + 2]) - ce0.z, __uint_as_float(v[g8 * 8 + 3]) - ce0.w);
+                            q.z = FWD ? f2_to_h2(__uint_as_float(v[g8 * 8 + 4]) - ce1.x, __uint_as_float(v[g8 * 8 + 5]) - ce1.y)
+                                      : f2_to_bf2(__uint_as_float(v[g8 * 8 + 4]) - ce1.x, __uint_as_float(v[g8 * 8 + 5]) - ce1.y);
+                            q.w = FWD ? f2_to_h2(__uint_as_float(v[g8 * 8 + 6]) - ce1.z, __uint_as_float(v[g8 * 8 + 7]) - ce1.w)
+                                      : f2_to_bf2(__uint_as_float(v[g8 * 8 + 6]) - ce1.z, __uint_as_float(v[g8 * 8 + 7]) - ce1.w);
+                            *reinterpret_cast<uint4*>(&sC[r * CLD + cb + g8 * 8]) = q;
                         }
                     }
                 }
@@ -404,23 +380,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
             if (as == 0) aphase ^= 1;
         }
         if (p.sums) {
-            // column sums: the RPP threads sharing a column piece combine through shared memory, one atomic per column
-            float* red = reinterpret_cast<float*>(sC);  // [RPP][2][EBN] floats <= TM*CLD*2 bytes
+            // column sums: lanes sharing a column piece combine by shuffles, the 8 warps through shared memory,
+            // then one atomic per column
+            float* red = reinterpret_cast<float*>(sC);  // [8 warps][2][EBN] floats <= 8 KB <= TM*CLD*2 bytes
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    red[(r0 * 2 + 0) * EBN + chunk * 8 + e] = s1[h][e];
-                    red[(r0 * 2 + 1) * EBN + chunk * 8 + e] = s2[h][e];
+#pragma unroll
+                    for (int o = CPR; o < 32; o <<= 1) {
+                        s1[h][e] += __shfl_xor_sync(kFull, s1[h][e], o);
+                        s2[h][e] += __shfl_xor_sync(kFull, s2[h][e], o);
+                    }
+                }
+                if (lane < CPR) {  // CPR <= 16: lane == chunk for these lanes (CPR divides 32)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        red[(warp * 2 + 0) * EBN + lane * 8 + e] = s1[h][e];
+                        red[(warp * 2 + 1) * EBN + lane * 8 + e] = s2[h][e];
+                    }
                 }
                 epi_bar();
-                for (int i = tid; i < 2 * EBN; i += kEpiWarps * 32) {
+                for (int i = tid; i < 2 * EBN; i += kEpiThreads) {
                     const int which = i / EBN, c = i - which * EBN;
                     const int col = n0 + h * EBN + c;
                     if (col < p.n) {
                         float s = 0.f;
-#pragma unroll 8
-                        for (int j = 0; j < RPP; ++j) s += red[(j * 2 + which) * EBN + c];
+#pragma unroll
+                        for (int j = 0; j < kEpiWarps; ++j) s += red[(j * 2 + which) * EBN + c];
                         atomicAdd(p.sums + (size_t)which * p.n + col, s);
                     }
                 }

@@ -1,0 +1,306 @@
+// mlp_wgrad_tc.cu -- weight gradient of the grouped per-point MLP on tcgen05 tensor cores, sm_100a.
+//
+//     dW[n][k] += sum_r dY[r][n] * X'[r][k]      dY = cA*dZ + cB*Y + cC  (BatchNorm backward, bf16)
+//                                                X' = relu(X*scale+shift) | X   (the layer's input, bf16)
+//
+// (the conv1x1 weight gradient cuDNN computes for reference pointnet_utils.py:399-403,458-460,505-507,577-580
+// and backbones.py:131 in backward).  The reduction runs over ROWS, so both operands are "MN-major" for the
+// tensor core: memory rows are K slices.  Layout per pipeline stage (32 rows):
+//
+//     panel = [32 rows][64 columns] 16-bit, 128-byte row pitch, 16-byte pieces XOR-swizzled by row % 8
+//             (UMMA canonical MN-major SWIZZLE_128B: LBO = panel pitch 4096 B, SBO = 1024 B per 8 rows)
+//     stage = dZ panels (n_pad/64) | Y panels (n_pad/64, scratch) | X panels (kw_pad/64)
+//
+// A panel is exactly one 16-byte piece per producer thread, so a thread's pieces of a stage share the row and the
+// piece column and differ only by the panel: no per-piece index arithmetic.
+//
+//   8 producer warps  cp.async raw dZ / Y / X pieces, D stages in flight; when a stage has landed each thread turns
+//                     ITS dZ pieces into dY and its X pieces into X' in place, fence.proxy.async, mbarrier arrive
+//   1 MMA warp        one lane: per stage 2 (K = 16 rows each) x MT (128 output channels each) tcgen05.mma with
+//                     N = kw input channels, accumulating in TMEM over ALL stages of the CTA; tcgen05.commit
+//                     frees the stage; a final commit publishes the accumulators
+//   4 epilogue warps  wait for the final commit, tcgen05.ld, fp32 atomics into dW (the caller's .grad buffer)
+//
+// Grid: (row splits, input-channel tiles).  One CTA holds every output channel (n <= 512: MT <= 4 accumulators of
+// kw <= 512/MT columns), so X is read and transformed once per input-channel tile.
+// Bound: HBM reads rows*(2n + k)*2 bytes; the transforms are ~3 fp32 ops per element on the producers.
+#include "mlp_gemm.cuh"
+#include "tc_common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int WR = 32;            // rows per stage
+constexpr int kPanel = WR * 128;  // bytes
+constexpr int kWEpiWarps = 4, kWMmaWarp = 4, kWProdWarps = 8;
+constexpr int kWProdThreads = kWProdWarps * 32;
+constexpr int kWThreads = (kWEpiWarps + 1 + kWProdWarps) * 32;
+constexpr int kWSmem = 225 * 1024;
+
+struct WgTc {
+    WgradArgs a;
+    int mt;        // 128-wide output-channel tiles
+    int kw;        // input channels per CTA (multiple of 16, <= 256, mt*kw <= 512)
+    int npd, npx;  // dZ (= Y) panels, X panels per stage
+    int nst;       // ring depth
+    int tmem_cols; // power of two >= mt*kw
+};
+
+template <bool AFFINE>
+__global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
+    const WgradArgs& p = w.a;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    unsigned char* base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    const int stage_bytes = (2 * w.npd + w.npx) * kPanel;
+    unsigned char* sStage = base;
+    float* sCo = reinterpret_cast<float*>(base + w.nst * stage_bytes);  // [3][npd*64] cA cB cC, then [2][npx*64] scale shift
+    const int ncol = w.npd * 64, kcol_pad = w.npx * 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sCo + 3 * ncol + 2 * kcol_pad);
+    uint64_t* full = bars;            // [nst]
+    uint64_t* empty = bars + w.nst;   // [nst]
+    uint64_t* done = bars + 2 * w.nst;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * w.nst + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k0 = blockIdx.y * w.kw;                 // first input channel of this CTA
+    const int kw_here = min(w.kw, p.kp - k0);         // multiple of 16 (kp % 32 == 0, kw % 16 == 0)
+    const long long stages = (p.rows + WR - 1) / WR;
+    const long long mine = blockIdx.x < stages ? (stages - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    for (int i = tid; i < 3 * ncol; i += kWThreads) {
+        const int which = i / ncol, c = i - which * ncol;
+        sCo[i] = c < p.n ? (which == 0 ? p.cA : (which == 1 ? p.cB : p.cC))[c] : 0.f;
+    }
+    for (int i = tid; i < 2 * kcol_pad; i += kWThreads) {
+        const int which = i / kcol_pad, c = i - which * kcol_pad;
+        sCo[3 * ncol + i] = (AFFINE && k0 + c < p.kp) ? (which == 0 ? p.in_scale : p.in_shift)[k0 + c] : 0.f;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < w.nst; ++i) {
+            mbar_init(&full[i], kWProdThreads);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == kWMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)w.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp > kWMmaWarp) {
+        // ================================ producers ================================
+        const int pt = tid - (kWMmaWarp + 1) * 32;
+        const int pj = pt & 7, pr = pt >> 3;  // piece column, row of every panel
+        const uint32_t poff = pr * 128 + ((pj ^ (pr & 7)) << 4);
+        const uint32_t stage0 = smem_u32(sStage);
+        const int D = w.nst - 1;
+        long long i_s = blockIdx.x, p_s = blockIdx.x;
+        int i_slot = 0, p_slot = 0;
+        uint32_t i_phase = 0;
+        for (long long c = 0; c < mine + D; ++c) {
+            if (c < mine) {
+                mbar_wait(&empty[i_slot], i_phase ^ 1);
+                const uint32_t st = stage0 + i_slot * stage_bytes + poff;
+                const long long row = i_s * WR + pr;
+                const bool rok = row < p.rows;
+                const bf16* dzp = p.dz + row * p.dz_ld + pj * 8;
+                const act_t* yp = p.y + row * p.y_ld + pj * 8;
+                for (int P = 0; P < w.npd; ++P) {
+                    const bool ok = rok && P * 64 + pj * 8 < p.n;
+                    cp_async16_s(st + P * kPanel, ok ? (const void*)(dzp + P * 64) : (const void*)p.dz, ok ? 16 : 0);
+                    cp_async16_s(st + (w.npd + P) * kPanel, ok ? (const void*)(yp + P * 64) : (const void*)p.y, ok ? 16 : 0);
+                }
+                const act_t* xp = p.x + row * p.x_ld + k0 + pj * 8;
+                for (int P = 0; P < w.npx; ++P) {
+                    const bool ok = rok && P * 64 + pj * 8 < kw_here;
+                    cp_async16_s(st + (2 * w.npd + P) * kPanel, ok ? (const void*)(xp + P * 64) : (const void*)p.x, ok ? 16 : 0);
+                }
+                i_s += gridDim.x;
+                if (++i_slot == w.nst) { i_slot = 0; i_phase ^= 1; }
+            }
+            cp_async_commit();
+            if (c >= D) {
+                switch (D) {  // this thread's pieces of stage c - D have landed
+                    case 1: cp_wait<1>(); break;
+                    case 2: cp_wait<2>(); break;
+                    case 3: cp_wait<3>(); break;
+                    case 4: cp_wait<4>(); break;
+                    default: cp_wait<5>(); break;
+                }
+                unsigned char* st = sStage + p_slot * stage_bytes + poff;
+                const bool rok = p_s * WR + pr < p.rows;
+                for (int P = 0; P < w.npd; ++P) {
+                    uint4* slot = reinterpret_cast<uint4*>(st + P * kPanel);
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (rok) {
+                        const uint4 qd = *slot;
+                        const uint4 qy = *reinterpret_cast<const uint4*>(st + (w.npd + P) * kPanel);
+                        const uint32_t* d = reinterpret_cast<const uint32_t*>(&qd);
+                        const uint32_t* y = reinterpret_cast<const uint32_t*>(&qy);
+                        uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+                        const float* ca = sCo + P * 64 + pj * 8;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(ca + 4 * hh);
+                            const float4 b4 = *reinterpret_cast<const float4*>(ca + ncol + 4 * hh);
+                            const float4 c4 = *reinterpret_cast<const float4*>(ca + 2 * ncol + 4 * hh);
+                            const float2 d0 = bf2_to_f2(d[2 * hh]), d1 = bf2_to_f2(d[2 * hh + 1]);
+                            const float2 y0 = h2_to_f2(y[2 * hh]), y1 = h2_to_f2(y[2 * hh + 1]);
+                            o[2 * hh] = f2_to_bf2(fmaf(a4.x, d0.x, fmaf(b4.x, y0.x, c4.x)), fmaf(a4.y, d0.y, fmaf(b4.y, y0.y, c4.y)));
+                            o[2 * hh + 1] = f2_to_bf2(fmaf(a4.z, d1.x, fmaf(b4.z, y1.x, c4.z)), fmaf(a4.w, d1.y, fmaf(b4.w, y1.y, c4.w)));
+                        }
+                    }
+                    *slot = v;
+                }
+                for (int P = 0; P < w.npx; ++P) {
+                    uint4* slot = reinterpret_cast<uint4*>(st + (2 * w.npd + P) * kPanel);
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (rok) {
+                        const uint4 qx = *slot;
+                        const uint32_t* x = reinterpret_cast<const uint32_t*>(&qx);
+                        uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+                        if (AFFINE) {
+                            const float* cs = sCo + 3 * ncol + P * 64 + pj * 8;
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const float4 s4 = *reinterpret_cast<const float4*>(cs + 4 * hh);
+                                const float4 h4 = *reinterpret_cast<const float4*>(cs + kcol_pad + 4 * hh);
+                                const float2 x0 = h2_to_f2(x[2 * hh]), x1 = h2_to_f2(x[2 * hh + 1]);
+                                o[2 * hh] = f2_to_bf2(fmaxf(fmaf(x0.x, s4.x, h4.x), 0.f), fmaxf(fmaf(x0.y, s4.y, h4.y), 0.f));
+                                o[2 * hh + 1] = f2_to_bf2(fmaxf(fmaf(x1.x, s4.z, h4.z), 0.f), fmaxf(fmaf(x1.y, s4.w, h4.w), 0.f));
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 xv = h2_to_f2(x[e]);
+                                o[e] = f2_to_bf2(xv.x, xv.y);  // the gradient GEMM runs in bf16
+                            }
+                        }
+                    }
+                    *slot = v;
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[p_slot]);
+                p_s += gridDim.x;
+                if (++p_slot == w.nst) p_slot = 0;
+            }
+        }
+    } else if (warp == kWMmaWarp) {
+        // ================================ MMA issuer ================================
+        // A = dY^T (M = output channels), B = X'^T (N = input channels): both MN-major, bf16
+        const uint32_t idesc = umma_idesc(1u, true, true, 128, kw_here);
+        int slot = 0;
+        uint32_t phase = 0;
+        for (long long c = 0; c < mine; ++c) {
+            mbar_wait(&full[slot], phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(sStage + slot * stage_bytes);
+                const uint32_t sx = sa + 2 * w.npd * kPanel;
+#pragma unroll
+                for (int k16 = 0; k16 < WR / 16; ++k16) {
+                    const uint64_t bdesc = umma_desc_sw128(sx + k16 * 2048, kPanel, 1024);
+                    for (int m = 0; m < w.mt; ++m) {
+                        const uint64_t adesc = umma_desc_sw128(sa + 2 * m * kPanel + k16 * 2048, kPanel, 1024);
+                        umma_f16(tmem_base + m * w.kw, adesc, bdesc, idesc, (c | k16) != 0);
+                    }
+                }
+                tc_commit(&empty[slot]);
+                if (c == mine - 1) tc_commit(done);
+            }
+            __syncwarp();
+            if (++slot == w.nst) { slot = 0; phase ^= 1; }
+        }
+    } else if (mine > 0) {
+        // ================================ epilogue ================================
+        mbar_wait(done, 0);
+        tc_fence_after();
+        for (int m = 0; m < w.mt; ++m) {
+            const int n = m * 128 + warp * 32 + lane;  // output channel of this thread (TMEM lane)
+            for (int c16 = 0; c16 < kw_here; c16 += 16) {
+                if (m * 128 + warp * 32 < p.n) {  // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + m * w.kw + c16, v);
+                    if (n < p.n) {
+                        float* dst = p.dw + (size_t)n * p.dw_ld + k0 + c16;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float g = __uint_as_float(v[e]);
+                            if (k0 + c16 + e < p.k_true && g != 0.f) atomicAdd(dst + e, g);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWMmaWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)w.tmem_cols)
+                     : "memory");
+    }
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(const WgradArgs& a) { return a.n <= 512 && a.kp % 32 == 0 && a.n % 8 == 0; }
+
+int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
+    WgTc w;
+    w.a = a;
+    w.mt = (a.n + 127) / 128;
+    w.npd = w.mt * 2;
+    int kw_max = 512 / w.mt / 16 * 16;
+    if (kw_max > 256) kw_max = 256;
+    const int ky = (a.kp + kw_max - 1) / kw_max;
+    w.kw = ((a.kp + ky - 1) / ky + 31) / 32 * 32;  // even split, multiple of 32, <= kw_max (kw_max is a multiple of 32 or kp fits)
+    if (w.kw > kw_max) w.kw = kw_max;
+    w.npx = (w.kw + 63) / 64;
+    const int gy = (a.kp + w.kw - 1) / w.kw;
+    int cols = w.mt * w.kw;
+    w.tmem_cols = 32;
+    while (w.tmem_cols < cols) w.tmem_cols <<= 1;
+    const size_t stage = (size_t)(2 * w.npd + w.npx) * kPanel;
+    const size_t fixed = (size_t)(3 * w.npd * 64 + 2 * w.npx * 64) * 4 + 256 + 1024;
+    int nst = (int)((kWSmem - fixed) / stage);
+    if (nst > 6) nst = 6;
+    if (nst < 2) return fail_arg("pn2_mlp_gemm_wgrad", "stage does not fit shared memory");
+    w.nst = nst;
+    const size_t smem = fixed + nst * stage;
+    static bool configured = false;
+    if (!configured) {
+        PN2_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem),
+                  "wgrad_tc: cudaFuncSetAttribute");
+        PN2_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem),
+                  "wgrad_tc: cudaFuncSetAttribute");
+        configured = true;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long stages = (a.rows + WR - 1) / WR;
+    long long gx = sms / gy;
+    if (gx < 1) gx = 1;
+    if (gx > stages) gx = stages;
+    if (a.in_scale)
+        wgrad_tc_kernel<true><<<dim3((unsigned)gx, gy), kWThreads, smem, stream>>>(w);
+    else
+        wgrad_tc_kernel<false><<<dim3((unsigned)gx, gy), kWThreads, smem, stream>>>(w);
+    PN2_CHECK_LAUNCH("wgrad_tc_kernel");
+    return 0;
+}
+
+}  // namespace pn2

@@ -22,6 +22,13 @@ static float frand() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; retu
 static float h16(float v) { return __half2float(__float2half_rn(v)); }
 static float b16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+__global__ void flush_read_kernel(const float4* p, size_t n, float* sink) {
+    float acc = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { float4 v = p[i]; acc += v.x + v.y + v.z + v.w; }
+    if (acc == 123.456f) *sink = acc;
+}
+static void flush_l2(float* buf, int) { flush_read_kernel<<<1184, 256>>>((const float4*)buf, (size_t)(256 << 20) / 16, buf); }
+
 template <class T> T* dev(const std::vector<T>& h) { T* d; CK(cudaMalloc(&d, h.size() * sizeof(T) + 16)); CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); return d; }
 
 static int check_fwd(int R, int K, int N, bool affine) {
@@ -113,6 +120,65 @@ static int check_dgrad(int R, int NR, int KO, bool mask) {
     return ok ? 0 : 1;
 }
 
+static int check_wgrad(int R, int N, int KP, int KT, bool affine) {
+    std::vector<__nv_bfloat16> dz((size_t)R * N);
+    std::vector<__half> y((size_t)R * N), x((size_t)R * KP);
+    std::vector<float> dzf(dz.size()), yf(y.size()), xf(x.size()), cA(N), cB(N), cC(N), sc(KP), sh(KP);
+    for (size_t i = 0; i < dz.size(); ++i) { dzf[i] = b16(frand()); dz[i] = __float2bfloat16_rn(dzf[i]); yf[i] = h16(frand() * 2.f); y[i] = __float2half_rn(yf[i]); }
+    for (size_t i = 0; i < x.size(); ++i) { xf[i] = h16(frand() * 2.f); x[i] = __float2half_rn(xf[i]); }
+    for (int n = 0; n < N; ++n) { cA[n] = 0.5f + 0.4f * frand(); cB[n] = 0.1f * frand(); cC[n] = 0.05f * frand(); }
+    for (int k = 0; k < KP; ++k) { sc[k] = 0.5f + 0.4f * frand(); sh[k] = 0.2f * frand(); }
+    std::vector<float> dy(dz.size()), xa(x.size());
+    for (size_t i = 0; i < dy.size(); ++i) { int n = i % N; dy[i] = b16(fmaf(cA[n], dzf[i], fmaf(cB[n], yf[i], cC[n]))); }
+    for (size_t i = 0; i < xa.size(); ++i) { int k = i % KP; xa[i] = b16(affine ? fmaxf(fmaf(xf[i], sc[k], sh[k]), 0.f) : xf[i]); }
+    std::vector<double> ref((size_t)N * KT, 0.0);
+    for (int r = 0; r < R; ++r)
+        for (int n = 0; n < N; ++n) {
+            const double d = dy[(size_t)r * N + n];
+            for (int k = 0; k < KT; ++k) ref[(size_t)n * KT + k] += d * xa[(size_t)r * KP + k];
+        }
+    auto *ddz = dev(dz); auto *dy_ = dev(y), *dx = dev(x);
+    float *dA = dev(cA), *dB = dev(cB), *dC = dev(cC), *dsc = dev(sc), *dsh = dev(sh);
+    float* ddw; CK(cudaMalloc(&ddw, (size_t)N * KT * 4)); CK(cudaMemset(ddw, 0, (size_t)N * KT * 4));
+    int rc = pn2_mlp_gemm_wgrad(R, N, KP, KT, ddz, N, dy_, N, dA, dB, dC, dx, KP, affine ? dsc : nullptr, affine ? dsh : nullptr, ddw, KT, 0);
+    if (rc) { printf("wgrad R=%d N=%d KP=%d: launch failed rc=%d\n", R, N, KP, rc); return 1; }
+    CK(cudaDeviceSynchronize());
+    std::vector<float> dw((size_t)N * KT);
+    CK(cudaMemcpy(dw.data(), ddw, dw.size() * 4, cudaMemcpyDeviceToHost));
+    double scale = 0; for (double v : ref) scale = fmax(scale, fabs(v));
+    double maxerr = 0; size_t bad = 0;
+    for (size_t i = 0; i < dw.size(); ++i) {
+        double e = fabs(dw[i] - ref[i]) / (scale + 1e-9);
+        if (!(e < 2e-3)) { if (bad < 5) printf("   dw[%zu,%zu] = %f ref %f\n", i / KT, i % KT, dw[i], ref[i]); ++bad; }
+        if (e > maxerr) maxerr = e;
+    }
+    const bool ok = bad == 0;
+    printf("wgrad R=%6d N=%4d KP=%4d KT=%4d affine=%d  max err/scale %.2e (scale %.1f)  bad %zu  %s\n", R, N, KP, KT, affine, maxerr, scale, bad, ok ? "OK" : "FAIL");
+    cudaFree(ddz); cudaFree(dy_); cudaFree(dx); cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dsc); cudaFree(dsh); cudaFree(ddw);
+    return ok ? 0 : 1;
+}
+
+
+static void time_wgrad(long long R, int N, int KP, bool affine) {
+    void *dz, *y, *x; float *c, *dw, *flush;
+    CK(cudaMalloc(&dz, R * N * 2)); CK(cudaMalloc(&y, R * N * 2)); CK(cudaMalloc(&x, R * KP * 2));
+    CK(cudaMalloc(&c, 1024 * 4 * 8)); CK(cudaMalloc(&dw, (size_t)N * KP * 4)); CK(cudaMalloc(&flush, 256 << 20));
+    CK(cudaMemset(dz, 0, R * N * 2)); CK(cudaMemset(y, 0, R * N * 2)); CK(cudaMemset(x, 0, R * KP * 2)); CK(cudaMemset(c, 0, 1024 * 4 * 8)); CK(cudaMemset(dw, 0, (size_t)N * KP * 4));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e9, tot = 0; const int reps = 10;
+    for (int i = 0; i < reps + 2; ++i) {
+        flush_l2(flush, i);
+        cudaEventRecord(e0, 0);
+        pn2_mlp_gemm_wgrad(R, N, KP, KP, dz, N, y, N, c, c + 1024, c + 2048, x, KP, affine ? c + 3072 : nullptr, affine ? c + 4096 : nullptr, dw, KP, 0);
+        cudaEventRecord(e1, 0); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 2) { tot += ms; best = fminf(best, ms); }
+    }
+    const double bytes = (double)R * (2 * N + KP) * 2;
+    printf("time wgrad R=%lld N=%d KP=%d affine=%d: avg %.1f us best %.1f us  -> %.0f GB/s (alg %.1f MB)\n", R, N, KP, affine, tot / reps * 1e3, best * 1e3, bytes / (tot / reps * 1e-3) / 1e9, bytes / 1e6);
+    cudaFree(dz); cudaFree(y); cudaFree(x); cudaFree(c); cudaFree(dw); cudaFree(flush);
+}
+
 static void time_fwd(long long R, int K, int N, bool affine) {
     __half *x, *w, *y; float *sc, *sh, *cen, *st, *flush;
     CK(cudaMalloc(&x, R * K * 2)); CK(cudaMalloc(&w, (size_t)N * K * 2)); CK(cudaMalloc(&y, R * N * 2));
@@ -122,7 +188,7 @@ static void time_fwd(long long R, int K, int N, bool affine) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9, tot = 0; const int reps = 10;
     for (int i = 0; i < reps + 2; ++i) {
-        CK(cudaMemsetAsync(flush, i, 256 << 20, 0));
+        flush_l2(flush, i);
         cudaEventRecord(e0, 0);
         pn2_mlp_gemm_fwd(R, K, N, x, K, affine ? sc : nullptr, affine ? sh : nullptr, w, cen, y, N, st, 0);
         cudaEventRecord(e1, 0); CK(cudaEventSynchronize(e1));
@@ -142,7 +208,7 @@ static void time_dgrad(long long R, int NR, int KO, bool mask) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9, tot = 0; const int reps = 10;
     for (int i = 0; i < reps + 2; ++i) {
-        CK(cudaMemsetAsync(flush, i, 256 << 20, 0));
+        flush_l2(flush, i);
         cudaEventRecord(e0, 0);
         pn2_mlp_gemm_dgrad(R, NR, KO, dz, NR, y, NR, c, c + 1024, c + 2048, wt, mask ? yp : nullptr, KO, c + 3072, c + 4096, c + 5120, c + 6144, out, KO, sum, 0);
         cudaEventRecord(e1, 0); CK(cudaEventSynchronize(e1));
@@ -157,6 +223,12 @@ static void time_dgrad(long long R, int NR, int KO, bool mask) {
 int main(int argc, char** argv) {
     const char* impl = getenv("PN2_GEMM_IMPL");
     printf("PN2_GEMM_IMPL=%s\n", impl ? impl : "(default tc)");
+    if (argc > 1 && !strcmp(argv[1], "prof")) {  // the two conv1 GEMMs only (for ncu)
+        time_fwd(131072, 128, 384, true);
+        time_dgrad(131072, 384, 128, true);
+        time_wgrad(131072, 384, 128, true);
+        return 0;
+    }
     int fails = 0;
     fails += check_fwd(128, 64, 32, false);
     fails += check_fwd(128, 64, 128, false);
@@ -176,6 +248,15 @@ int main(int argc, char** argv) {
     fails += check_dgrad(700, 128, 832, false);
     fails += check_dgrad(2500, 384, 128, true);
     fails += check_dgrad(20000, 256, 256, true);
+    fails += check_wgrad(64, 128, 64, 64, false);
+    fails += check_wgrad(1000, 32, 32, 3, false);
+    fails += check_wgrad(5000, 64, 96, 67, false);
+    fails += check_wgrad(999, 128, 128, 128, true);
+    fails += check_wgrad(3000, 384, 128, 128, true);
+    fails += check_wgrad(2000, 128, 832, 771, false);
+    fails += check_wgrad(1500, 512, 128, 128, true);
+    fails += check_wgrad(1700, 256, 640, 640, false);
+    fails += check_wgrad(2100, 192, 128, 128, true);
     printf("%d failing case(s)\n", fails);
     if (argc > 1 && !strcmp(argv[1], "time")) {
         time_fwd(131072, 128, 384, true);   // conv1
@@ -190,6 +271,12 @@ int main(int argc, char** argv) {
         time_dgrad(131072, 128, 192, false);
         time_dgrad(43008, 128, 832, false);
         time_dgrad(262144, 64, 32, true);
+        time_wgrad(131072, 384, 128, true);   // conv1
+        time_wgrad(131072, 128, 128, true);   // fp1 layer 1
+        time_wgrad(131072, 128, 192, false);  // fp1 layer 0
+        time_wgrad(262144, 64, 32, true);     // sa1 layer 2
+        time_wgrad(43008, 128, 832, false);   // q2 K=64 layer 0
+        time_wgrad(43008, 192, 128, true);    // q2 K=64 layer 2
     }
     return fails ? 1 : 0;
 }
