@@ -14,7 +14,7 @@ OUT = os.path.join(HERE, "libpn2b200.so")
 OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", *os.environ.get("PN2_NVCC_EXTRA", "").split(),
     "-Xcompiler", "-fPIC",
 ]
 

@@ -69,8 +69,11 @@ struct TcCfg {
     static constexpr int kFixed = kSC + kNCoef * kMaxK * 4 + 5 * BN * 4 + 256 + 1024;  // + barriers + alignment slack
     static constexpr int kNstRaw = (kSmemBudget - kFixed) / kStage;
     static constexpr int kNst = kNstRaw > 6 ? 6 : kNstRaw;
-    static constexpr int kDist = kNst - 1;                     // chunks in flight per producer thread
-    static_assert(kNst >= 2, "not enough shared memory for a two-stage ring");
+    // chunks in flight per producer thread.  NST - 2, not NST - 1: refilling a slot waits for the MMAs of the chunk that
+    // used it NST chunks ago; with D = NST - 1 that chunk was published only one iteration earlier and the MMA round
+    // trip (mbarrier wake-up, tcgen05.mma, commit) would sit on the producers' critical path every iteration
+    static constexpr int kDist = kNst - 2;
+    static_assert(kNst >= 3, "not enough shared memory for a three-stage ring");
 };
 
 template <int BN, int AMODE, bool MASK>
@@ -235,7 +238,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                         *slot = v;
                     }
                 }
+#ifndef PN2_FENCE_CONSUMER
                 fence_proxy_async();  // generic-proxy writes (cp.async + the in-place transform) -> visible to the tensor core
+#endif
                 mbar_arrive(&full[p_slot]);
                 if (++p_kc == KT) { p_kc = 0; p_tile += gridDim.x; }
                 if (++p_slot == NST) p_slot = 0;
@@ -254,6 +259,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
             tc_fence_after();
             for (int kc = 0; kc < KT; ++kc) {
                 mbar_wait(&full[slot], phase);
+#ifdef PN2_FENCE_CONSUMER
+                fence_proxy_async();
+#endif
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(sStage + slot * Cfg::kStage);
@@ -453,16 +461,14 @@ int launch_tc(const GemmArgs& a, cudaStream_t stream) {
     return 0;
 }
 
-// column-tile width: the widest of {256 (forward only), 128, 64, 32} that wastes the fewest padded columns
+// column-tile width: the narrowest of {32, 64, 128, 256 (forward only)} that covers n, else the widest.  Every extra
+// column tile re-reads and re-transforms the whole A operand; padded columns only cost tensor-pipe time (the epilogue
+// skips them).
 int pick_bn(int n, bool fwd) {
-    int best = 32, best_waste = 1 << 30;
-    const int cands[4] = {fwd ? 256 : 128, 128, 64, 32};
-    for (int i = 0; i < 4; ++i) {
-        const int bn = cands[i];
-        const int waste = (n + bn - 1) / bn * bn - n;
-        if (waste < best_waste) { best = bn; best_waste = waste; }
-    }
-    return best;
+    const int widest = fwd ? 256 : 128;
+    for (int bn = 32; bn < widest; bn <<= 1)
+        if (n <= bn) return bn;
+    return widest;
 }
 
 template <int AMODE, bool MASK>

@@ -74,31 +74,82 @@ struct SaBuildArgs {
     int out_ld;
 };
 
+// 8 consecutive channels of a feature row as floats, BatchNorm+ReLU of the producer applied on the fly (16-byte load;
+// needs ch % 8 == 0 and ld % 8 == 0)
+__device__ __forceinline__ void row_vals8(const RowSrc& s, size_t row, int ch, float (&v)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(s.p + row * s.ld + ch));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = h2_to_f2(w[e]);
+        v[2 * e] = f.x; v[2 * e + 1] = f.y;
+    }
+    if (s.scale) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(s.scale + ch)), s1 = __ldg(reinterpret_cast<const float4*>(s.scale + ch + 4));
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(s.shift + ch)), h1 = __ldg(reinterpret_cast<const float4*>(s.shift + ch + 4));
+        v[0] = fmaxf(fmaf(v[0], s0.x, h0.x), 0.f); v[1] = fmaxf(fmaf(v[1], s0.y, h0.y), 0.f);
+        v[2] = fmaxf(fmaf(v[2], s0.z, h0.z), 0.f); v[3] = fmaxf(fmaf(v[3], s0.w, h0.w), 0.f);
+        v[4] = fmaxf(fmaf(v[4], s1.x, h1.x), 0.f); v[5] = fmaxf(fmaf(v[5], s1.y, h1.y), 0.f);
+        v[6] = fmaxf(fmaf(v[6], s1.z, h1.z), 0.f); v[7] = fmaxf(fmaf(v[7], s1.w, h1.w), 0.f);
+    }
+}
+
+// A lane owns one 16-byte piece (8 channels) of an output row: rows narrower than 32 pieces share a warp
+// (gpr = pieces per row, rpw = rows per warp), wider rows take several passes.  Pieces that lie entirely inside the
+// feature segment are one 16-byte gather; pieces straddling a segment boundary (the 3 coordinates shift the centre
+// segment off the 8-channel grid) are assembled element by element.
 __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildArgs a) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int gpr = a.out_ld >> 3;
+    const int rpw = gpr >= 32 ? 1 : 32 / gpr;
     const long long total = (long long)a.b * a.s * a.k;
-    if (row >= total) return;
+    const long long wrow = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * rpw;
+    const int sub = gpr >= 32 ? 0 : lane / gpr;
+    const long long row = wrow + sub;
+    if (row >= total || sub >= rpw) return;
     const int kk = (int)(row % a.k);
     const long long bs = row / a.k;
     const int s = (int)(bs % a.s), b = (int)(bs / a.s);
-    const int j = a.idx ? a.idx[row] : kk;
-    float rel[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const float cx = a.new_xyz ? __ldg(a.new_xyz + ((size_t)b * 3 + d) * a.s + s) : 0.f;
-        rel[d] = __ldg(a.xyz + ((size_t)b * 3 + d) * a.n + j) - cx;
-    }
+    const int j = a.idx ? __ldg(a.idx + row) : kk;
     const size_t frow = (size_t)b * a.n + j, crow = (size_t)b * a.s + s;
     const int fc = a.feat.p ? a.feat.c : 0, cc = a.cen.p ? a.cen.c : 0;
     const int f0 = a.xyz_first ? 3 : 0, x0 = a.xyz_first ? 0 : fc, c0 = fc + 3;
+    const bool fvec = fc > 0 && f0 == 0 && (fc & 7) == 0 && (a.feat.ld & 7) == 0;
+    float rel[3] = {0.f, 0.f, 0.f};
+    bool have_rel = false;
     act_t* o = a.out + (size_t)row * a.out_ld;
-    for (int col = lane; col < a.out_ld; col += 32) {
-        float v = 0.f;
-        if (col >= f0 && col < f0 + fc) v = row_val(a.feat, frow, col - f0);
-        else if (col >= x0 && col < x0 + 3) v = rel[col - x0];
-        else if (col >= c0 && col < c0 + cc) v = row_val(a.cen, crow, col - c0);
-        o[col] = f_to_h(v);
+    for (int g = gpr >= 32 ? lane : lane - sub * gpr; g < gpr; g += 32) {
+        const int col = g << 3;
+        float v[8];
+        if (fvec && col + 8 <= fc) {
+            row_vals8(a.feat, frow, col, v);
+        } else {
+            if (!have_rel && col < x0 + 3 && col + 8 > x0) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float cx = a.new_xyz ? __ldg(a.new_xyz + ((size_t)b * 3 + d) * a.s + s) : 0.f;
+                    rel[d] = __ldg(a.xyz + ((size_t)b * 3 + d) * a.n + j) - cx;
+                }
+                have_rel = true;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = col + e;
+                float t = 0.f;
+                if (c >= f0 && c < f0 + fc) t = row_val(a.feat, frow, c - f0);
+                else if (c >= x0 && c < x0 + 3) t = rel[c - x0];
+                else if (c >= c0 && c < c0 + cc) t = row_val(a.cen, crow, c - c0);
+                v[e] = t;
+            }
+        }
+        uint4 q;
+        uint32_t* qq = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float lo = fminf(fmaxf(v[2 * e], -65504.f), 65504.f), hi = fminf(fmaxf(v[2 * e + 1], -65504.f), 65504.f);
+            qq[e] = f2_to_h2(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(o + col) = q;
     }
 }
 
@@ -424,11 +475,6 @@ struct SaBwdArgs {
     int cen_c; float* dcen_cm;     // (B,cen_c,S)  zeroed, atomics
     int xyz_first;
 };
-// Vector reduction into global memory: one 16-byte red.global.add.v4.f32 (sm_90+) instead of four scalar atomics.
-__device__ __forceinline__ void red_add_v4(float* dst, float x, float y, float z, float w) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-
 // One CTA per group (b, s); warps walk the group's K rows.
 //   feature columns  -> scattered to the gathered point's gradient: row-form destination = coalesced 16-byte vector
 //                       reductions (lane = 4 channels); channel-major destination = scalar atomics
@@ -574,7 +620,8 @@ extern "C" int pn2_sa_build_rows(int b, int n, int s, int k, const float* xyz, c
     a.feat = mk_src(feat, feat_c, feat_ld, feat_scale, feat_shift);
     a.cen = mk_src(cen, cen_c, cen_ld, cen_scale, cen_shift);
     a.xyz_first = xyz_first; a.out = (act_t*)out; a.out_ld = out_ld;
-    sa_build_rows_kernel<<<warp_blocks((long long)b * s * k), kThreads, 0, (cudaStream_t)stream>>>(a);
+    const int gpr = out_ld >> 3, rpw = gpr >= 32 ? 1 : 32 / gpr;
+    sa_build_rows_kernel<<<warp_blocks(((long long)b * s * k + rpw - 1) / rpw), kThreads, 0, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("sa_build_rows_kernel");
     return 0;
 }

@@ -101,7 +101,14 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         const int pj = pt & 7, pr = pt >> 3;  // piece column, row of every panel
         const uint32_t poff = pr * 128 + ((pj ^ (pr & 7)) << 4);
         const uint32_t stage0 = smem_u32(sStage);
-        const int D = w.nst - 1;
+        // panels that hold real columns; the padding panels of every stage are zeroed once, here, and never written again
+        const int npd_v = (p.n + 63) / 64, npx_v = (kw_here + 63) / 64;
+        for (int sl = 0; sl < w.nst; ++sl) {
+            unsigned char* st = sStage + sl * stage_bytes + poff;
+            for (int P = npd_v; P < w.npd; ++P) *reinterpret_cast<uint4*>(st + P * kPanel) = make_uint4(0u, 0u, 0u, 0u);
+            for (int P = npx_v; P < w.npx; ++P) *reinterpret_cast<uint4*>(st + (2 * w.npd + P) * kPanel) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        const int D = w.nst - 2;  // one stage of slack between publishing a stage and needing its slot back (see mlp_gemm_tc.cu)
         long long i_s = blockIdx.x, p_s = blockIdx.x;
         int i_slot = 0, p_slot = 0;
         uint32_t i_phase = 0;
@@ -113,13 +120,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                 const bool rok = row < p.rows;
                 const bf16* dzp = p.dz + row * p.dz_ld + pj * 8;
                 const act_t* yp = p.y + row * p.y_ld + pj * 8;
-                for (int P = 0; P < w.npd; ++P) {
+                for (int P = 0; P < npd_v; ++P) {
                     const bool ok = rok && P * 64 + pj * 8 < p.n;
                     cp_async16_s(st + P * kPanel, ok ? (const void*)(dzp + P * 64) : (const void*)p.dz, ok ? 16 : 0);
                     cp_async16_s(st + (w.npd + P) * kPanel, ok ? (const void*)(yp + P * 64) : (const void*)p.y, ok ? 16 : 0);
                 }
                 const act_t* xp = p.x + row * p.x_ld + k0 + pj * 8;
-                for (int P = 0; P < w.npx; ++P) {
+                for (int P = 0; P < npx_v; ++P) {
                     const bool ok = rok && P * 64 + pj * 8 < kw_here;
                     cp_async16_s(st + (2 * w.npd + P) * kPanel, ok ? (const void*)(xp + P * 64) : (const void*)p.x, ok ? 16 : 0);
                 }
@@ -129,18 +136,18 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
             cp_async_commit();
             if (c >= D) {
                 switch (D) {  // this thread's pieces of stage c - D have landed
+                    case 0: cp_wait<0>(); break;
                     case 1: cp_wait<1>(); break;
                     case 2: cp_wait<2>(); break;
                     case 3: cp_wait<3>(); break;
-                    case 4: cp_wait<4>(); break;
-                    default: cp_wait<5>(); break;
+                    default: cp_wait<4>(); break;
                 }
                 unsigned char* st = sStage + p_slot * stage_bytes + poff;
                 const bool rok = p_s * WR + pr < p.rows;
-                for (int P = 0; P < w.npd; ++P) {
+                for (int P = 0; P < npd_v; ++P) {
                     uint4* slot = reinterpret_cast<uint4*>(st + P * kPanel);
                     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (rok) {
+                    if (rok && P * 64 + pj * 8 < p.n) {
                         const uint4 qd = *slot;
                         const uint4 qy = *reinterpret_cast<const uint4*>(st + (w.npd + P) * kPanel);
                         const uint32_t* d = reinterpret_cast<const uint32_t*>(&qd);
@@ -160,10 +167,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                     }
                     *slot = v;
                 }
-                for (int P = 0; P < w.npx; ++P) {
+                for (int P = 0; P < npx_v; ++P) {
                     uint4* slot = reinterpret_cast<uint4*>(st + (2 * w.npd + P) * kPanel);
                     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (rok) {
+                    if (rok && P * 64 + pj * 8 < kw_here) {
                         const uint4 qx = *slot;
                         const uint32_t* x = reinterpret_cast<const uint32_t*>(&qx);
                         uint32_t* o = reinterpret_cast<uint32_t*>(&v);
@@ -187,7 +194,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                     }
                     *slot = v;
                 }
+#ifndef PN2_FENCE_CONSUMER
                 fence_proxy_async();
+#endif
                 mbar_arrive(&full[p_slot]);
                 p_s += gridDim.x;
                 if (++p_slot == w.nst) p_slot = 0;
@@ -201,6 +210,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         uint32_t phase = 0;
         for (long long c = 0; c < mine; ++c) {
             mbar_wait(&full[slot], phase);
+#ifdef PN2_FENCE_CONSUMER
+            fence_proxy_async();
+#endif
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t sa = smem_u32(sStage + slot * stage_bytes);
@@ -223,6 +235,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         // ================================ epilogue ================================
         mbar_wait(done, 0);
         tc_fence_after();
+        const bool vec4 = (p.dw_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;  // 16-byte aligned rows
         for (int m = 0; m < w.mt; ++m) {
             const int n = m * 128 + warp * 32 + lane;  // output channel of this thread (TMEM lane)
             for (int c16 = 0; c16 < kw_here; c16 += 16) {
@@ -231,10 +244,17 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                     tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + m * w.kw + c16, v);
                     if (n < p.n) {
                         float* dst = p.dw + (size_t)n * p.dw_ld + k0 + c16;
+                        if (vec4 && k0 + c16 + 16 <= p.k_true) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const float g = __uint_as_float(v[e]);
-                            if (k0 + c16 + e < p.k_true && g != 0.f) atomicAdd(dst + e, g);
+                            for (int e = 0; e < 16; e += 4)
+                                red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                                           __uint_as_float(v[e + 3]));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const float g = __uint_as_float(v[e]);
+                                if (k0 + c16 + e < p.k_true && g != 0.f) atomicAdd(dst + e, g);
+                            }
                         }
                     }
                 }
@@ -274,7 +294,7 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
     const size_t fixed = (size_t)(3 * w.npd * 64 + 2 * w.npx * 64) * 4 + 256 + 1024;
     int nst = (int)((kWSmem - fixed) / stage);
     if (nst > 6) nst = 6;
-    if (nst < 2) return fail_arg("pn2_mlp_gemm_wgrad", "stage does not fit shared memory");
+    if (nst < 3) return fail_arg("pn2_mlp_gemm_wgrad", "stage does not fit shared memory");
     w.nst = nst;
     const size_t smem = fixed + nst * stage;
     static bool configured = false;

@@ -61,6 +61,11 @@ __device__ __forceinline__ void cp_async16_s(uint32_t dst_smem_addr, const void*
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Vector reduction into global memory: one 16-byte red.global.add.v4.f32 (sm_90+) instead of four scalar atomics.
+__device__ __forceinline__ void red_add_v4(float* dst, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
     // bf16 -> fp32 is a 16-bit shift: low half = element 0, high half = element 1
     return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));

@@ -237,7 +237,7 @@ class PointNetSetAbstractionMsg_GivenCenterPoints(_MsgBase):
                 return_group_idx=False):
         xyz_t = new_xyz_t = None
         outs, idx_list = [], []
-        idx = None
+        idx = knn_all = None
         for i, radius in enumerate(self.radius_list):
             if pre_group_idx is not None:
                 idx = pre_group_idx[i]
@@ -245,7 +245,14 @@ class PointNetSetAbstractionMsg_GivenCenterPoints(_MsgBase):
                 if xyz_t is None:
                     xyz_t = xyz.transpose(1, 2).contiguous()
                     new_xyz_t = new_xyz.transpose(1, 2).contiguous()
-                idx = _neighbour_idx(self.knn, radius, self.nsample_list[i], xyz_t, new_xyz_t).long()
+                if self.knn:
+                    # the k nearest come back ascending with a stable tie rule (interpolate_gpu.cu:30-56), so the K
+                    # nearest are the first K columns of the max(K) nearest: one search serves every scale
+                    if knn_all is None:
+                        knn_all = _neighbour_idx(True, radius, max(self.nsample_list), xyz_t, new_xyz_t)
+                    idx = knn_all[..., :self.nsample_list[i]].long()
+                else:
+                    idx = _neighbour_idx(False, radius, self.nsample_list[i], xyz_t, new_xyz_t).long()
             idx_list.append(idx)
             outs.append(self._scale(i, xyz, points, new_xyz, idx.int(), new_points))
         out = torch.cat(outs, dim=1)

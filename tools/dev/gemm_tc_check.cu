@@ -223,6 +223,10 @@ static void time_dgrad(long long R, int NR, int KO, bool mask) {
 int main(int argc, char** argv) {
     const char* impl = getenv("PN2_GEMM_IMPL");
     printf("PN2_GEMM_IMPL=%s\n", impl ? impl : "(default tc)");
+    if (argc > 1 && !strcmp(argv[1], "prof2")) {  // the smallest wgrad (for ncu)
+        time_wgrad(262144, 64, 32, true);
+        return 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "prof")) {  // the two conv1 GEMMs only (for ncu)
         time_fwd(131072, 128, 384, true);
         time_dgrad(131072, 384, 128, true);
