@@ -593,6 +593,15 @@ __global__ void __launch_bounds__(256) center_kernel(long long rows, int kdim, i
     const int ns = rows < 16 ? (int)rows : 16;
     const long long step = rows / ns;
     const float inv = 1.f / (float)ns;
+    // this warp's weight row first: its loads do not depend on the sampled rows, so the two memory round trips of
+    // the kernel overlap (the kernel is pure latency: a few KB per CTA)
+    const int col = blockIdx.x * 8 + warp;
+    uint32_t wreg[16];  // kdim <= 1024: 2 x 16 values per lane
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int k = lane * 2 + i * 64;
+        wreg[i] = (col < n && k < kdim) ? __ldg(reinterpret_cast<const uint32_t*>(w + (size_t)col * kdim + k)) : 0u;
+    }
     for (int k = tid; k < kdim; k += 256) {
         float v[16];
 #pragma unroll
@@ -606,13 +615,16 @@ __global__ void __launch_bounds__(256) center_kernel(long long rows, int kdim, i
         sO[k] = in_offset ? in_offset[k] : 0.f;
     }
     __syncthreads();
-    const int col = blockIdx.x * 8 + warp;
     if (col >= n) return;
     float acc = 0.f, acc2 = 0.f;
-    for (int k = lane * 2; k < kdim; k += 64) {  // kdim is a multiple of 32: pairs never straddle the end
-        const float2 wv = h2_to_f2(*reinterpret_cast<const uint32_t*>(w + (size_t)col * kdim + k));
-        acc = fmaf(wv.x, sM[k], fmaf(wv.y, sM[k + 1], acc));
-        acc2 = fmaf(wv.x, sO[k], fmaf(wv.y, sO[k + 1], acc2));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int k = lane * 2 + i * 64;  // kdim is a multiple of 32: pairs never straddle the end
+        if (k < kdim) {
+            const float2 wv = h2_to_f2(wreg[i]);
+            acc = fmaf(wv.x, sM[k], fmaf(wv.y, sM[k + 1], acc));
+            acc2 = fmaf(wv.x, sO[k], fmaf(wv.y, sO[k + 1], acc2));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -663,24 +675,91 @@ __global__ void bn_eval_affine_kernel(int n, const float* __restrict__ gamma, co
     shift[c] = fmaf((bias ? bias[c] : 0.f) + (center ? center[c] : 0.f) - running_mean[c], sc, beta[c]);
 }
 
-__global__ void bn_bwd_coefs_kernel(int n, float inv_rows, const float* __restrict__ sums,
-                                    const float* __restrict__ gamma, const float* __restrict__ mean,
-                                    const float* __restrict__ rstd, float* cA, float* cB, float* cC, float* dgamma,
-                                    float* dbeta, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    const float s1 = sums[c], s2 = sums[n + c];
-    const float m1 = s1 * inv_rows, m2 = s2 * inv_rows;
-    const float gr = gamma[c] * rstd[c];
-    cA[c] = gr;
-    cB[c] = -gr * m2 * rstd[c];
-    cC[c] = gr * (m2 * rstd[c] * mean[c] - m1);
-    if (accumulate) {  // straight into the parameters' .grad (autograd's "+=" without an extra kernel)
-        dgamma[c] += s2;
-        dbeta[c] += s1;
-    } else {
-        dgamma[c] = s2;
-        dbeta[c] = s1;
+// BatchNorm-backward coefficients of a layer,  dY = cA*dZ + cB*Y + cC  per output channel, the parameter gradients
+// dgamma / dbeta, and (w != null) the layer's weights with the coefficients FOLDED IN for the input-gradient GEMM:
+//     dY * W  =  dZ * (cA o W)  +  Y * (cB o W)  +  cC * W
+// so that GEMM multiplies the stored dZ and Y rows as they are (no per-element transform of the big operands):
+//     wa[k][n] = bf16(S * cA[n] * w[n][k]),  wb[k][n] = fp16(S * cB[n] * w[n][k]),  negbias[k] = -sum_n cC[n] * w[n][k]
+// Y is stored fp16 and the tensor core multiplies like with like, so W_B is fp16 too; cB is gradient-sized (1e-8 is
+// ordinary), hence the power-of-two S = 2^(4 - ceil(log2 max|cB|)) that brings it into fp16's normal range; W_A carries
+// the same S so both products land in one accumulator.  wb_unscale = 1/S is applied by the GEMM's epilogue.
+// Block (bx, by) owns the 32 x 32 tile (input channels 32bx.., output channels 32by..) of the folded weights; blocks
+// with by == 0 also reduce the bias of their input channels; block (0,0) writes the coefficients and the parameter
+// gradients.  Every block recomputes the (cheap) coefficients of all n channels: S needs max|cB|.
+__global__ void __launch_bounds__(256) bn_bwd_coefs_kernel(int n, float inv_rows, const float* __restrict__ sums,
+                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, float* cA, float* cB, float* cC,
+                                                           float* dgamma, float* dbeta, int accumulate,
+                                                           const float* __restrict__ w, int k_true, int kp, bf16* wa,
+                                                           act_t* wb, float* negbias, float* wb_unscale) {
+    extern __shared__ float sco[];  // [3][n]
+    __shared__ float tile[32][33];
+    __shared__ float sbias[8][32];
+    __shared__ float smax[8];
+    const int tid = threadIdx.x;
+    const bool first = blockIdx.x == 0 && blockIdx.y == 0;
+    for (int c = tid; c < n; c += 256) {
+        const float s1 = sums[c], s2 = sums[n + c];
+        const float m1 = s1 * inv_rows, m2 = s2 * inv_rows;
+        const float gr = gamma[c] * rstd[c];
+        const float a_ = gr, b_ = -gr * m2 * rstd[c], c_ = gr * (m2 * rstd[c] * mean[c] - m1);
+        sco[c] = a_; sco[n + c] = b_; sco[2 * n + c] = c_;
+        if (first) {
+            cA[c] = a_; cB[c] = b_; cC[c] = c_;
+            if (accumulate) {  // straight into the parameters' .grad (autograd's "+=" without an extra kernel)
+                dgamma[c] += s2;
+                dbeta[c] += s1;
+            } else {
+                dgamma[c] = s2;
+                dbeta[c] = s1;
+            }
+        }
+    }
+    if (!w) return;
+    __syncthreads();
+    float mx = 0.f;  // every block derives the same scale from the same coefficients
+    for (int c = tid; c < n; c += 256) mx = fmaxf(mx, fabsf(sco[n + c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    if ((tid & 31) == 0) smax[tid >> 5] = mx;
+    __syncthreads();
+    mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, smax[i]);
+    int ex = 0;
+    if (mx > 0.f && mx < 3e38f) frexpf(mx, &ex);  // mx = f * 2^ex, f in [0.5, 1)
+    ex = max(-100, min(100, ex));
+    const float wscale = exp2f((float)(4 - ex)), unscale = exp2f((float)(ex - 4));
+    if (first && tid == 0) *wb_unscale = unscale;
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32, tx = tid & 31, ty = tid >> 5;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {  // read w[n0 + j][k0 + tx]: k contiguous
+        const int nn = n0 + j, kk = k0 + tx;
+        tile[j][tx] = (nn < n && kk < k_true) ? w[(size_t)nn * k_true + kk] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {  // write [k0 + j][n0 + tx]: n contiguous
+        const int kk = k0 + j, nn = n0 + tx;
+        if (kk < kp && nn < n) {
+            const float v = tile[tx][j];
+            wa[(size_t)kk * n + nn] = __float2bfloat16(sco[nn] * wscale * v);
+            wb[(size_t)kk * n + nn] = f_to_h(sco[n + nn] * wscale * v);
+        }
+    }
+    if (blockIdx.y == 0) {  // negbias[k] = -sum_n cC[n] * w[n][k] for this block's 32 input channels
+        const int kk = k0 + tx;
+        float bacc = 0.f;
+        if (kk < k_true) {
+#pragma unroll 4
+            for (int nn = ty; nn < n; nn += 8) bacc = fmaf(sco[2 * n + nn], __ldg(w + (size_t)nn * k_true + kk), bacc);
+        }
+        sbias[ty][tx] = bacc;
+        __syncthreads();
+        if (ty == 0 && kk < kp) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += sbias[i][tx];
+            negbias[kk] = -t;
+        }
     }
 }
 
@@ -733,21 +812,21 @@ extern "C" int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, 
 }
 
 extern "C" int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const void* dz, int dz_ld, const void* y,
-                                  int y_ld, const float* cA, const float* cB, const float* cC, const void* wt,
+                                  int y_ld, const void* wa, const void* wb, const float* negbias, const float* wb_unscale,
                                   const void* y_prev, int y_prev_ld, const float* prev_scale, const float* prev_shift,
                                   const float* prev_mean, const float* prev_rstd, void* dz_prev, int dz_prev_ld,
                                   float* sums_prev, pn2_stream_t stream) {
     if (int e = check_common("pn2_mlp_gemm_dgrad", rows, n_red, k_out)) return e;
     if (rows == 0) return 0;
-    if (!dz || !y || !cA || !cB || !cC || !wt || !dz_prev) return fail_arg("pn2_mlp_gemm_dgrad", "null pointer");
+    if (!dz || !y || !wa || !wb || !negbias || !wb_unscale || !dz_prev) return fail_arg("pn2_mlp_gemm_dgrad", "null pointer");
     if (dz_ld % 8 || y_ld % 8 || dz_prev_ld % 8 || dz_prev_ld < k_out)
         return fail_arg("pn2_mlp_gemm_dgrad", "bad leading dimension");
     GemmArgs a{};
     a.rows = rows; a.kdim = n_red; a.n = k_out;
     a.a0 = (const uint16_t*)dz; a.a0_ld = dz_ld;
     a.a1 = (const uint16_t*)y; a.a1_ld = y_ld;
-    a.c0 = cA; a.c1 = cB; a.c2 = cC;
-    a.b = (const uint16_t*)wt;
+    a.b = (const uint16_t*)wa; a.b1 = (const uint16_t*)wb; a.yscale = wb_unscale;
+    a.center = negbias;
     a.out = (uint16_t*)dz_prev; a.out_ld = dz_prev_ld;
     if (y_prev) {
         if (!prev_scale || !prev_shift || !prev_mean || !prev_rstd || !sums_prev || y_prev_ld % 8)
@@ -755,12 +834,10 @@ extern "C" int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const vo
         a.sums = sums_prev;
         a.yp = (const uint16_t*)y_prev; a.yp_ld = y_prev_ld;
         a.p_scale = prev_scale; a.p_shift = prev_shift; a.p_mean = prev_mean; a.p_rstd = prev_rstd;
-        if (gemm_use_tc()) return launch_gemm_tc(a, A_BNBWD, true, (cudaStream_t)stream);
-        return dispatch_bn<A_BNBWD, true>(a, (cudaStream_t)stream);
+        return launch_gemm_tc(a, A_BNBWD, true, (cudaStream_t)stream);
     }
     a.sums = nullptr;
-    if (gemm_use_tc()) return launch_gemm_tc(a, A_BNBWD, false, (cudaStream_t)stream);
-    return dispatch_bn<A_BNBWD, false>(a, (cudaStream_t)stream);
+    return launch_gemm_tc(a, A_BNBWD, false, (cudaStream_t)stream);
 }
 
 extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, const void* dz, int dz_ld,
@@ -793,7 +870,7 @@ extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, con
                   "wgrad: cudaFuncSetAttribute");
         configured = true;
     }
-    if (gemm_use_tc() && wgrad_tc_supported(a)) return launch_wgrad_tc(a, (cudaStream_t)stream);
+    if (wgrad_use_tc() && wgrad_tc_supported(a)) return launch_wgrad_tc(a, (cudaStream_t)stream);
     if (in_scale)
         wgrad_kernel<true><<<grid, kWgradThreads, kWgradSmem, (cudaStream_t)stream>>>(a);
     else
@@ -830,12 +907,17 @@ extern "C" int pn2_bn_eval_affine(int n, const float* gamma, const float* beta, 
 
 extern "C" int pn2_bn_bwd_coefs(int n, long long rows, const float* sums, const float* gamma, const float* mean,
                                 const float* rstd, float* cA, float* cB, float* cC, float* dgamma, float* dbeta,
-                                int accumulate, pn2_stream_t stream) {
+                                int accumulate, const float* w, int k_true, int kp, void* wa, void* wb, float* negbias,
+                                float* wb_unscale, pn2_stream_t stream) {
     if (n <= 0 || rows <= 0) return fail_arg("pn2_bn_bwd_coefs", "non-positive size");
     if (!sums || !gamma || !mean || !rstd || !cA || !cB || !cC || !dgamma || !dbeta)
         return fail_arg("pn2_bn_bwd_coefs", "null pointer");
-    bn_bwd_coefs_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, (float)(1.0 / (double)rows), sums, gamma,
-                                                                          mean, rstd, cA, cB, cC, dgamma, dbeta, accumulate);
+    if (n > 4096) return fail_arg("pn2_bn_bwd_coefs", "n > 4096");
+    if (w && (!wa || !wb || !negbias || !wb_unscale || k_true <= 0 || kp < k_true)) return fail_arg("pn2_bn_bwd_coefs", "bad folding arguments");
+    const dim3 blocks(w ? (kp + 31) / 32 : 1, w ? (n + 31) / 32 : 1);
+    bn_bwd_coefs_kernel<<<blocks, 256, 3 * n * sizeof(float), (cudaStream_t)stream>>>(
+        n, (float)(1.0 / (double)rows), sums, gamma, mean, rstd, cA, cB, cC, dgamma, dbeta, accumulate, w, k_true, kp, (bf16*)wa,
+        (act_t*)wb, negbias, wb_unscale);
     PN2_CHECK_LAUNCH("bn_bwd_coefs_kernel");
     return 0;
 }

@@ -14,7 +14,9 @@ struct GemmArgs {
     const uint16_t* a0; int a0_ld;   // forward: x (fp16);  BNBWD: dz (bf16)
     const uint16_t* a1; int a1_ld;   // BNBWD: y (fp16)
     const float *c0, *c1, *c2;
-    const uint16_t* b;               // forward: w (fp16);  BNBWD: wt (bf16)
+    const uint16_t* b;               // forward: w (fp16);  BNBWD: W_A = cA o W^T (bf16, [k_out][n_red])
+    const uint16_t* b1;              // BNBWD: W_B = yscale^-1 * cB o W^T (fp16, scaled into fp16 range by a power of two)
+    const float* yscale;             // BNBWD: device scalar, the factor that undoes W_B's scaling
     const float* center;  // [n] subtracted from the accumulators before 16-bit rounding (nullable)
     uint16_t* out; int out_ld;       // forward: y (fp16);  BNBWD: dz_prev (bf16)
     float* sums;
@@ -34,7 +36,11 @@ struct WgradArgs {
     float* dw; int dw_ld;
 };
 
-// tcgen05 weight-gradient kernel (mlp_wgrad_tc.cu); supported when the whole output-channel range fits TMEM (n <= 512)
+// tcgen05 weight-gradient kernel (mlp_wgrad_tc.cu); supported when the whole output-channel range fits TMEM (n <= 512).
+// Opt-in (env PN2_WGRAD_IMPL=tc): the row reduction makes both operands MN-major, and measured on B200 the tensor core
+// is fed MN-major 16-bit tiles at a fraction of the K-major rate (0.13-0.3 us per M=128,K=16 instruction), so the
+// warp-level kernel with ldmatrix.trans fragments (mlp_gemm.cu) is the faster one on this network's shapes.
+bool wgrad_use_tc();
 bool wgrad_tc_supported(const WgradArgs& a);
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream);
 

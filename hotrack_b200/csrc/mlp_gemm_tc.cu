@@ -61,11 +61,14 @@ template <int BN, int AMODE>
 struct TcCfg {
     static constexpr int kABytes = TM * 128;
     static constexpr int kNA = AMODE == A_BNBWD ? 2 : 1;
-    static constexpr int kStage = kABytes * kNA + BN * 128;
-    static constexpr int kEpiBN = BN < 128 ? BN : 128;         // columns per epilogue pass
+    static constexpr int kNB = kNA;                            // BNBWD: dZ x W_A and Y x W_B accumulate into one tile
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kStage = kABytes * kNA + kBBytes * kNB;
+    static constexpr int kEpiMax = AMODE == A_BNBWD ? 64 : 128;  // backward stages are twice as large: smaller staging tile
+    static constexpr int kEpiBN = BN < kEpiMax ? BN : kEpiMax;  // columns per epilogue pass
     static constexpr int kCLD = kEpiBN + 8;                    // 16-bit elements per sC row
     static constexpr int kSC = TM * kCLD * 2;
-    static constexpr int kNCoef = AMODE == A_PLAIN ? 0 : (AMODE == A_AFFINE ? 2 : 3);
+    static constexpr int kNCoef = AMODE == A_AFFINE ? 2 : 0;
     static constexpr int kFixed = kSC + kNCoef * kMaxK * 4 + 5 * BN * 4 + 256 + 1024;  // + barriers + alignment slack
     static constexpr int kNstRaw = (kSmemBudget - kFixed) / kStage;
     static constexpr int kNst = kNstRaw > 6 ? 6 : kNstRaw;
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     constexpr int RPP = kEpiThreads / CPR;  // rows per epilogue pass
     constexpr int WC = EBN / 2;           // columns of a pass-1 warp (two warps share a 32-lane quarter)
     constexpr int LDW = WC < 32 ? WC : 32;  // columns per tcgen05.ld
+    constexpr int ACC = BN;                 // TMEM columns per accumulator stage
     constexpr int PASSES = TM / RPP;
     constexpr bool FWD = AMODE != A_BNBWD;
     constexpr int NCOEF = Cfg::kNCoef;
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
         }
         mbar_fence_init();
     }
-    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two: BN in {32,64,128,256}
+    constexpr uint32_t kTmemCols = 2 * ACC < 32 ? 32 : 2 * ACC;  // power of two: BN in {32,64,128,256}
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(kTmemCols)
@@ -163,7 +167,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
         long long i_tile = blockIdx.x, p_tile = blockIdx.x;
         int i_kc = 0, i_slot = 0, p_kc = 0, p_slot = 0;
         uint32_t i_phase = 0;
-        for (long long c = 0; c < total + D; ++c) {
+        // Raw operands (forward layer 0, every backward GEMM): nothing happens between landing and multiplying, so the
+        // copies report their own completion to the stage barrier (cp.async.mbarrier.arrive.noinc) and the producers
+        // run ahead as far as there are free slots.  AFFINE: the thread comes back D chunks later to transform.
+        constexpr bool RAW = AMODE != A_AFFINE;
+        constexpr int LAG = RAW ? 0 : D;
+        for (long long c = 0; c < total + LAG; ++c) {
             if (c < total) {
                 mbar_wait(&empty[i_slot], i_phase ^ 1);  // the MMAs that read this slot NST chunks ago have completed
                 const uint32_t st = stage0 + i_slot * Cfg::kStage;
@@ -186,14 +195,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                 for (int i = 0; i < BN / 32; ++i) {
                     const bool ok = kok && 32 * i < n_left;
                     cp_async16_s(sb + poff + i * 4096, ok ? bp + (size_t)i * b_step : p.b, ok ? 16 : 0);
+                    if (AMODE == A_BNBWD)
+                        cp_async16_s(sb + Cfg::kBBytes + poff + i * 4096, ok ? p.b1 + (bp - p.b) + (size_t)i * b_step : p.b1,
+                                     ok ? 16 : 0);
                 }
+                if (RAW) cp_async_mbar_arrive_noinc(&full[i_slot]);
                 if (++i_kc == KT) { i_kc = 0; i_tile += gridDim.x; }
                 if (++i_slot == NST) { i_slot = 0; i_phase ^= 1; }
             }
+            if (RAW) continue;
             cp_async_commit();  // always: the group count stays in step with c
             if (c >= D) {
                 cp_wait<D>();   // this thread's pieces of chunk c - D have landed
-                if (AMODE != A_PLAIN) {
+                if (AMODE == A_AFFINE) {
                     unsigned char* st = sStage + p_slot * Cfg::kStage + poff;
                     const int cc = p_kc * TK + pj * 8;
                     const float4 ka0 = *reinterpret_cast<const float4*>(&sCoef[cc]);
@@ -202,45 +216,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                     const float4 kb1 = *reinterpret_cast<const float4*>(&sCoef[kpad + cc + 4]);
                     const float k0[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
                     const float k1[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
-                    float k2[8];
-                    if (AMODE == A_BNBWD) {
-                        const float4 kc0 = *reinterpret_cast<const float4*>(&sCoef[2 * kpad + cc]);
-                        const float4 kc1 = *reinterpret_cast<const float4*>(&sCoef[2 * kpad + cc + 4]);
-                        k2[0] = kc0.x; k2[1] = kc0.y; k2[2] = kc0.z; k2[3] = kc0.w;
-                        k2[4] = kc1.x; k2[5] = kc1.y; k2[6] = kc1.z; k2[7] = kc1.w;
-                    }
 #pragma unroll
                     for (int i = 0; i < TM / 32; ++i) {
-                        const uint32_t off = i * 4096;
-                        uint4* slot = reinterpret_cast<uint4*>(st + off);
+                        uint4* slot = reinterpret_cast<uint4*>(st + i * 4096);
                         const uint4 q0 = *slot;
                         const uint32_t* x0 = reinterpret_cast<const uint32_t*>(&q0);
                         uint4 v;
                         uint32_t* o = reinterpret_cast<uint32_t*>(&v);
-                        if (AMODE == A_AFFINE) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 a = h2_to_f2(x0[e]);
-                                o[e] = f2_to_h2(fmaxf(fmaf(a.x, k0[2 * e], k1[2 * e]), 0.f),
-                                                fmaxf(fmaf(a.y, k0[2 * e + 1], k1[2 * e + 1]), 0.f));
-                            }
-                        } else {
-                            const uint4 q1 = *reinterpret_cast<const uint4*>(st + Cfg::kABytes + off);
-                            const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&q1);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 a = bf2_to_f2(x0[e]);
-                                const float2 y = h2_to_f2(x1[e]);
-                                o[e] = f2_to_bf2(fmaf(k0[2 * e], a.x, fmaf(k1[2 * e], y.x, k2[2 * e])),
-                                                 fmaf(k0[2 * e + 1], a.y, fmaf(k1[2 * e + 1], y.y, k2[2 * e + 1])));
-                            }
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 a = h2_to_f2(x0[e]);
+                            o[e] = f2_to_h2(fmaxf(fmaf(a.x, k0[2 * e], k1[2 * e]), 0.f),
+                                            fmaxf(fmaf(a.y, k0[2 * e + 1], k1[2 * e + 1]), 0.f));
                         }
                         *slot = v;
                     }
                 }
-#ifndef PN2_FENCE_CONSUMER
                 fence_proxy_async();  // generic-proxy writes (cp.async + the in-place transform) -> visible to the tensor core
-#endif
                 mbar_arrive(&full[p_slot]);
                 if (++p_kc == KT) { p_kc = 0; p_tile += gridDim.x; }
                 if (++p_slot == NST) p_slot = 0;
@@ -249,9 +241,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
         (void)p_tile;
     } else if (warp == kMmaWarp) {
         // ================================ MMA issuer ================================
-        // instruction descriptor: D fp32 [4,6)=1, A/B format [7,10)/[10,13) (0 fp16, 1 bf16), both K-major, N>>3 [17,23), M>>4 [24,29)
-        constexpr uint32_t fmt = FWD ? 0u : 1u;
-        constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        // forward: fp16 x fp16.  backward: dZ (bf16) x W_A (bf16), then Y (fp16) x W_B (fp16) into the same fp32
+        // accumulator -- one instruction multiplies like with like (a mixed fp16 x bf16 tcgen05.mma is an illegal
+        // instruction), two instructions of different formats may share the accumulator.  Both weight sets carry the
+        // same power-of-two factor (W_B needs it to sit in fp16's range); the epilogue divides it out.
+        constexpr uint32_t idesc = FWD ? umma_idesc2(0u, 0u, false, false, TM, BN) : umma_idesc2(1u, 1u, false, false, TM, BN);
+        constexpr uint32_t idesc1 = umma_idesc2(0u, 0u, false, false, TM, BN);
         int slot = 0;
         uint32_t phase = 0, as = 0, aphase = 0;
         for (long long t = 0; t < my_tiles; ++t) {
@@ -259,17 +254,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
             tc_fence_after();
             for (int kc = 0; kc < KT; ++kc) {
                 mbar_wait(&full[slot], phase);
-#ifdef PN2_FENCE_CONSUMER
-                fence_proxy_async();
-#endif
+                if (AMODE != A_AFFINE) fence_proxy_async();  // raw stages: no writer-side fence (the copies arrive by themselves)
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(sStage + slot * Cfg::kStage);
                     const uint64_t adesc = umma_desc_k128(sa);
                     const uint64_t bdesc = umma_desc_k128(sa + Cfg::kABytes * Cfg::kNA);
                     const int ksteps = min(TK / 16, (p.kdim - kc * TK + 15) / 16);
-                    for (int k4 = 0; k4 < ksteps; ++k4)  // +32 bytes (>>4 = 2) along K inside the swizzle atom
-                        umma_f16(tmem_base + as * BN, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kc | k4) != 0);
+                    for (int k4 = 0; k4 < ksteps; ++k4) {  // +32 bytes (>>4 = 2) along K inside the swizzle atom
+                        umma_f16(tmem_base + as * ACC, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kc | k4) != 0);
+                        if (AMODE == A_BNBWD)
+                            umma_f16(tmem_base + as * ACC, umma_desc_k128(sa + Cfg::kABytes) + 2 * k4,
+                                     umma_desc_k128(sa + Cfg::kABytes * 2 + Cfg::kBBytes) + 2 * k4, idesc1, 1u);
+                    }
                     tc_commit(&empty[slot]);               // arrives when the MMAs above have finished reading the stage
                     if (kc == KT - 1) tc_commit(&tfull[as]);
                 }
@@ -282,6 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     } else {
         // ================================ epilogue ================================
         const int chunk = tid % CPR, r0 = tid / CPR;
+        const float yscale = AMODE == A_BNBWD ? __ldg(p.yscale) : 0.f;
         float s1[NH][8], s2[NH][8];
 #pragma unroll
         for (int h = 0; h < NH; ++h)
@@ -289,19 +287,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
             for (int e = 0; e < 8; ++e) s1[h][e] = s2[h][e] = 0.f;
         uint32_t as = 0, aphase = 0;
         long long tile = blockIdx.x;
+        // the previous layer's y pieces the MASK epilogue reads come from HBM: they are pulled into L2 one column pass
+        // ahead (no registers held), the loads proper are issued at the top of the pass that uses them
+        auto prefetch_yp = [&](long long tl, int hh) {
+            const int c0 = n0 + hh * EBN + chunk * 8;
+            if (c0 < p.n) {
+#pragma unroll
+                for (int ps = 0; ps < (MASK ? PASSES : 1); ++ps) {
+                    const long long grow = tl * TM + r0 + ps * RPP;
+                    if (grow < p.rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.yp + grow * p.yp_ld + c0));
+                }
+            }
+        };
         for (long long t = 0; t < my_tiles; ++t, tile += gridDim.x) {
+            if (MASK && t == 0) prefetch_yp(tile, 0);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
                 const int col0 = n0 + h * EBN + chunk * 8;  // first of this thread's 8 output columns (pass 2)
                 uint4 yq[MASK ? PASSES : 1];
-                if (MASK && col0 < p.n) {
+                if (MASK) {
+                    if (col0 < p.n) {
 #pragma unroll
-                    for (int ps = 0; ps < PASSES; ++ps) {
-                        const long long grow = tile * TM + r0 + ps * RPP;
-                        if (grow < p.rows) yq[ps] = __ldg(reinterpret_cast<const uint4*>(p.yp + grow * p.yp_ld + col0));
+                        for (int ps = 0; ps < PASSES; ++ps) {
+                            const long long grow = tile * TM + r0 + ps * RPP;
+                            if (grow < p.rows) yq[ps] = __ldg(reinterpret_cast<const uint4*>(p.yp + grow * p.yp_ld + col0));
+                        }
                     }
+                    if (h + 1 < NH) prefetch_yp(tile, h + 1);
+                    else if (t + 1 < my_tiles) prefetch_yp(tile + gridDim.x, 0);
                 }
                 // pass 1: TMEM -> registers -> 16-bit tile in shared memory (thread = row; warp = 32 rows x WC columns)
                 const int q4 = warp & 3, wc0 = (warp >> 2) * WC;
@@ -310,8 +325,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                     const int cb = wc0 + cw;  // first column (within this EBN-wide pass) of this load
                     if (n0 + h * EBN + cb < p.n) {  // warp-uniform
                         uint32_t v[32];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * BN + h * EBN + cb;
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * ACC + h * EBN + cb;
                         if (LDW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                        if (AMODE == A_BNBWD) {  // undo the common power-of-two factor of W_A / W_B
+#pragma unroll
+                            for (int e = 0; e < LDW; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * yscale);
+                        }
                         const int r = q4 * 32 + lane;
 #pragma unroll
                         for (int g8 = 0; g8 < LDW / 8; ++g8) {
@@ -337,12 +356,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                 epi_bar();
                 // pass 2: 16-byte pieces, coalesced stores, column sums in registers
                 if (col0 < p.n) {
-                    float ps_[8], ph_[8], pm_[8], pr_[8];
+                    float ps_[8], ph_[8];
                     if (MASK) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const int c = h * EBN + chunk * 8 + e;
-                            ps_[e] = sPrev[c]; ph_[e] = sPrev[BN + c]; pm_[e] = sPrev[2 * BN + c]; pr_[e] = sPrev[3 * BN + c];
+                            ps_[e] = sPrev[c]; ph_[e] = sPrev[BN + c];
                         }
                     }
 #pragma unroll
@@ -362,11 +381,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                                     const float a1 = fmaf(y.y, ps_[2 * e + 1], ph_[2 * e + 1]);
                                     d.x = a0 > 0.f ? d.x : 0.f;
                                     d.y = a1 > 0.f ? d.y : 0.f;
-                                    const float h0 = (y.x - pm_[2 * e]) * pr_[2 * e];
-                                    const float h1 = (y.y - pm_[2 * e + 1]) * pr_[2 * e + 1];
+                                    // sum d*xhat = rstd * (sum d*y - mean * sum d): the per-column constants wait for the end
                                     s1[h][2 * e] += d.x; s1[h][2 * e + 1] += d.y;
-                                    s2[h][2 * e] = fmaf(d.x, h0, s2[h][2 * e]);
-                                    s2[h][2 * e + 1] = fmaf(d.y, h1, s2[h][2 * e + 1]);
+                                    s2[h][2 * e] = fmaf(d.x, y.x, s2[h][2 * e]);
+                                    s2[h][2 * e + 1] = fmaf(d.y, y.y, s2[h][2 * e + 1]);
                                     vv[e] = f2_to_bf2(d.x, d.y);
                                 }
                             } else if (p.sums) {
@@ -416,6 +434,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                         float s = 0.f;
 #pragma unroll
                         for (int j = 0; j < kEpiWarps; ++j) s += red[(j * 2 + which) * EBN + c];
+                        if (MASK && which == 1) {  // (sum d*y - mean * sum d) * rstd
+                            float sd = 0.f;
+#pragma unroll
+                            for (int j = 0; j < kEpiWarps; ++j) sd += red[(j * 2 + 0) * EBN + c];
+                            s = (s - sPrev[2 * BN + h * EBN + c] * sd) * sPrev[3 * BN + h * EBN + c];
+                        }
                         atomicAdd(p.sums + (size_t)which * p.n + col, s);
                     }
                 }

@@ -8,6 +8,11 @@ namespace pn2 {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// the mbarrier receives one arrival (already counted in its expected count) when all cp.async issued so far by this
+// thread have completed; the thread itself does not wait
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -58,6 +63,12 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 // 1 bf16), A/B major ([15] / [16]: 0 K-major, 1 MN-major), N >> 3 in [17,23), M >> 4 in [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, bool a_mn_major, bool b_mn_major, int m, int n) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ... with separate A / B element formats (kind::f16 takes fp16 and bf16 operands in any combination)
+__host__ __device__ constexpr uint32_t umma_idesc2(uint32_t a_fmt, uint32_t b_fmt, bool a_mn_major, bool b_mn_major, int m, int n) {
+    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 

@@ -108,7 +108,7 @@ def rows_of(t):
 
 
 class _Layer:
-    __slots__ = ("w", "wt", "cin", "kp", "cout", "y", "scale", "shift", "mean", "rstd")
+    __slots__ = ("w", "cin", "kp", "cout", "y", "scale", "shift", "mean", "rstd")
 
 
 def _bn_momentum(bn):
@@ -202,8 +202,7 @@ class _MlpStack(Function):
             if L.cout % 32:
                 raise ValueError("fused engine needs layer widths that are multiples of 32 (got %d)" % L.cout)
             L.w = torch.empty(L.cout, kp, dtype=_F16, device=dev)
-            L.wt = torch.empty(kp, L.cout, dtype=_BF16, device=dev) if training else None
-            _lib.call("pn2_mlp_prep_weights", L.cout, L.cin, kp, w.data_ptr(), L.w.data_ptr(), _p(L.wt), st)
+            _lib.call("pn2_mlp_prep_weights", L.cout, L.cin, kp, w.data_ptr(), L.w.data_ptr(), 0, st)
             L.y = torch.empty(R, L.cout, dtype=_F16, device=dev)
             consts = torch.empty(6, L.cout, dtype=torch.float32, device=dev)
             L.scale, L.shift, L.mean, L.rstd, cen, cen_true = (consts[i] for i in range(6))
@@ -303,10 +302,20 @@ class _MlpStack(Function):
             direct = all(q.grad is not None and q.grad.is_contiguous() and q.grad.dtype == torch.float32
                          for q in (pw, pg, pbt))
             coefs = torch.empty(5, L.cout, dtype=torch.float32, device=dev)
+            # the input-gradient GEMM multiplies dz and y as stored: the BatchNorm-backward coefficients are folded into
+            # two copies of the weights (and a bias) by the same small kernel that derives them
+            want_dx = l > 0 or need_a or need_b
+            wa = wb = negbias = unscale = None
+            if want_dx:
+                wa = torch.empty(L.kp, L.cout, dtype=_BF16, device=dev)
+                wb = torch.empty(L.kp, L.cout, dtype=_F16, device=dev)
+                negbias = torch.empty(L.kp + 1, dtype=torch.float32, device=dev)
+                unscale = negbias[L.kp:]
             _lib.call("pn2_bn_bwd_coefs", L.cout, R, sums.data_ptr(), ctx.gammas[l].data_ptr(), L.mean.data_ptr(),
                       L.rstd.data_ptr(), coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(),
                       pg.grad.data_ptr() if direct else coefs[3].data_ptr(),
-                      pbt.grad.data_ptr() if direct else coefs[4].data_ptr(), 1 if direct else 0, st)
+                      pbt.grad.data_ptr() if direct else coefs[4].data_ptr(), 1 if direct else 0,
+                      pw.data_ptr() if want_dx else 0, L.cin, L.kp, _p(wa), _p(wb), _p(negbias), _p(unscale), st)
             if l > 0:
                 P = layers[l - 1]
                 x, x_ld, xs, xh = P.y, P.cout, P.scale, P.shift
@@ -329,7 +338,7 @@ class _MlpStack(Function):
                 sums_p = arena[a_off:a_off + 2 * P.cout]
                 a_off += 2 * P.cout
                 _lib.call("pn2_mlp_gemm_dgrad", R, L.cout, P.cout, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
-                          coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), L.wt.data_ptr(),
+                          wa.data_ptr(), wb.data_ptr(), negbias.data_ptr(), unscale.data_ptr(),
                           P.y.data_ptr(), P.cout, P.scale.data_ptr(), P.shift.data_ptr(), P.mean.data_ptr(),
                           P.rstd.data_ptr(), dzp.data_ptr(), P.cout, sums_p.data_ptr(), st)
                 dz, sums = dzp, sums_p
@@ -338,7 +347,7 @@ class _MlpStack(Function):
                 # still pre-BatchNorm: the producer's own backward applies its ReLU mask)
                 dx0 = torch.empty(R, L.kp, dtype=_BF16, device=dev)
                 _lib.call("pn2_mlp_gemm_dgrad", R, L.cout, L.kp, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
-                          coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), L.wt.data_ptr(), 0, 0, 0, 0, 0,
+                          wa.data_ptr(), wb.data_ptr(), negbias.data_ptr(), unscale.data_ptr(), 0, 0, 0, 0, 0,
                           0, dx0.data_ptr(), L.kp, 0, st)
         # weight grads come back in the conv weight's own shape
         da = db = None

@@ -87,16 +87,22 @@ int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* 
                  float* sums, pn2_stream_t stream);
 
 /* BatchNorm-backward per-channel coefficients: dY = cA*dz + cB*y + cC; dgamma = sums[c..2c), dbeta = sums[0..c)
- * (accumulate != 0: added to the existing contents -- the parameters' .grad buffers). */
+ * (accumulate != 0: added to the existing contents -- the parameters' .grad buffers).
+ * w != NULL (fp32 conv weight [n][k_true]): also the weights with the coefficients folded in, for pn2_mlp_gemm_dgrad:
+ * wa[kp][n] = bf16(S*cA[n]*w[n][k]), wb[kp][n] = fp16(S*cB[n]*w[n][k]) with S a power of two that brings cB into fp16 range
+ * (rows k >= k_true zero), negbias[kp] = -sum_n cC[n]*w[n][k], *wb_unscale = 1/S. */
 int pn2_bn_bwd_coefs(int n, long long rows, const float* sums, const float* gamma, const float* mean,
                      const float* rstd, float* cA, float* cB, float* cC, float* dgamma, float* dbeta, int accumulate,
+                     const float* w, int k_true, int kp, void* wa, void* wb, float* negbias, float* wb_unscale,
                      pn2_stream_t stream);
 
-/* dz_prev[rows][k_out] = dY[rows][n_red] * wt[k_out][n_red]^T with dY = cA*dz + cB*y + cC.  y_prev != NULL:
- * the result is masked by the previous layer's ReLU (y_prev*prev_scale+prev_shift > 0) and sums_prev receives
- * the two BatchNorm-backward sums of the previous layer.  y_prev == NULL: plain input gradient. */
+/* dz_prev[rows][k_out] = dY[rows][n_red] * W[n_red][k_out]  with dY = cA*dz + cB*y + cC, evaluated as
+ * *wb_unscale * (dz * wa^T + y * wb^T) - negbias  (wa, wb, negbias, wb_unscale from pn2_bn_bwd_coefs: the big operands
+ * are multiplied as stored, bf16 x bf16 and fp16 x fp16, into one fp32 TMEM accumulator).
+ * y_prev != NULL: the result is masked by the previous layer's ReLU (y_prev*prev_scale+prev_shift > 0) and sums_prev
+ * receives the two BatchNorm-backward sums of the previous layer.  y_prev == NULL: plain input gradient. */
 int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const void* dz, int dz_ld, const void* y, int y_ld,
-                       const float* cA, const float* cB, const float* cC, const void* wt, const void* y_prev,
+                       const void* wa, const void* wb, const float* negbias, const float* wb_unscale, const void* y_prev,
                        int y_prev_ld, const float* prev_scale, const float* prev_shift, const float* prev_mean,
                        const float* prev_rstd, void* dz_prev, int dz_prev_ld, float* sums_prev, pn2_stream_t stream);
 

@@ -77,33 +77,59 @@ def test_gemm_fwd_and_stats(lib, cuda, R, K, N, affine):
 
 @pytest.mark.parametrize("R,N,K,mask", [(1000, 64, 32, True), (3000, 128, 96, False), (513, 192, 128, True),
                                          (2048, 128, 416, False), (700, 32, 32, True)])
-def test_gemm_dgrad(lib, cuda, R, N, K, mask):
+def test_bn_bwd_coefs_and_gemm_dgrad(lib, cuda, R, N, K, mask):
+    """pn2_bn_bwd_coefs (coefficients, parameter gradients, coefficient-folded weights) + pn2_mlp_gemm_dgrad against
+    the plain fp32 statement  dz_prev = (cA*dz + cB*y + cC) @ W  of BatchNorm backward followed by the conv's
+    input gradient.  Gradient-sized numbers on purpose (1e-6): the folded weights must survive fp16."""
     g = torch.Generator(device="cpu").manual_seed(R + N)
-    dz = torch.randn(R, N, generator=g).to(cuda).to(BF)
+    gscale = 1e-6
+    dz = (torch.randn(R, N, generator=g) * gscale).to(cuda).to(BF)
     y = torch.randn(R, N, generator=g).to(cuda).to(HF)
-    cA, cB, cC = [(torch.randn(N, generator=g) * 0.5).to(cuda) for _ in range(3)]
-    wt = (torch.randn(K, N, generator=g) / N ** 0.5).to(cuda).to(BF)  # [k_out][n_red]
-    dY = (cA * dz.float() + cB * y.float() + cC).to(BF).float()
-    want = dY @ wt.float().t()
+    kt = K - 5 if K > 32 else K                                   # true input channels (< padded K)
+    w = (torch.randn(N, kt, generator=g) / N ** 0.5).to(cuda)     # conv weight [n][k_true]
+    gamma = (torch.rand(N, generator=g) + 0.5).to(cuda)
+    mean = y.float().mean(0)
+    var = y.float().var(0, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    xhat = (y.float() - mean) * rstd
+    sums = torch.stack([dz.float().sum(0), (dz.float() * xhat).sum(0)]).contiguous()
+    cA, cB, cC, dgam, dbet = [torch.full((N,), float("nan"), device=cuda) for _ in range(5)]
+    wa = torch.full((K, N), float("nan"), dtype=BF, device=cuda)
+    wb = torch.full((K, N), float("nan"), dtype=HF, device=cuda)
+    negbias = torch.full((K,), float("nan"), device=cuda)
+    unscale = torch.zeros(1, device=cuda)
+    lib.call("pn2_bn_bwd_coefs", N, R, sums.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), cA.data_ptr(),
+             cB.data_ptr(), cC.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), 0, w.data_ptr(), kt, K, wa.data_ptr(),
+             wb.data_ptr(), negbias.data_ptr(), unscale.data_ptr(), _st())
+    torch.testing.assert_close(dbet, sums[0])
+    torch.testing.assert_close(dgam, sums[1])
+    # BatchNorm backward in closed form: dY = gamma*rstd * (dz - mean(dz) - xhat * mean(dz*xhat))
+    dY = gamma * rstd * (dz.float() - sums[0] / R - xhat * (sums[1] / R))
+    torch.testing.assert_close(cA * dz.float() + cB * y.float() + cC, dY, rtol=1e-3, atol=1e-4 * gscale)
+    assert torch.isfinite(wa.float()).all() and torch.isfinite(wb.float()).all() and float(unscale) > 0
+    assert (wa[kt:].float() == 0).all() and (wb[kt:].float() == 0).all()
+    wpad = torch.zeros(N, K, device=cuda)
+    wpad[:, :kt] = w
+    want = dY @ wpad
     out = torch.full((R, K), float("nan"), dtype=BF, device=cuda)
     if mask:
         yp = torch.randn(R, K, generator=g).to(cuda).to(HF)
         ps, ph, pm, pr = [(torch.randn(K, generator=g) * 0.5 + (1 if i in (0, 3) else 0)).to(cuda) for i in range(4)]
-        sums = torch.zeros(2, K, device=cuda)
-        lib.call("pn2_mlp_gemm_dgrad", R, N, K, dz.data_ptr(), N, y.data_ptr(), N, cA.data_ptr(), cB.data_ptr(),
-                 cC.data_ptr(), wt.data_ptr(), yp.data_ptr(), K, ps.data_ptr(), ph.data_ptr(), pm.data_ptr(),
-                 pr.data_ptr(), out.data_ptr(), K, sums.data_ptr(), _st())
+        psums = torch.zeros(2, K, device=cuda)
+        lib.call("pn2_mlp_gemm_dgrad", R, N, K, dz.data_ptr(), N, y.data_ptr(), N, wa.data_ptr(), wb.data_ptr(),
+                 negbias.data_ptr(), unscale.data_ptr(), yp.data_ptr(), K, ps.data_ptr(), ph.data_ptr(), pm.data_ptr(),
+                 pr.data_ptr(), out.data_ptr(), K, psums.data_ptr(), _st())
         act = yp.float() * ps + ph > 0
-        want = torch.where(act, want.to(BF).float(), torch.zeros_like(want))
-        xhat = (yp.float() - pm) * pr
-        assert _rel(out, want) < 4e-3
+        want = torch.where(act, want, torch.zeros_like(want))
+        assert _rel(out, want) < 1.5e-2  # bf16 output of bf16/fp16-rounded folded weights
         o = out.float()
-        torch.testing.assert_close(sums[0], o.sum(0), rtol=2e-3, atol=2e-2 * R ** 0.5)
-        torch.testing.assert_close(sums[1], (o * xhat).sum(0), rtol=2e-3, atol=2e-2 * R ** 0.5)
+        xh_prev = (yp.float() - pm) * pr
+        torch.testing.assert_close(psums[0], o.sum(0), rtol=2e-3, atol=2e-2 * gscale * R ** 0.5)
+        torch.testing.assert_close(psums[1], (o * xh_prev).sum(0), rtol=2e-3, atol=2e-2 * gscale * R ** 0.5)
     else:
-        lib.call("pn2_mlp_gemm_dgrad", R, N, K, dz.data_ptr(), N, y.data_ptr(), N, cA.data_ptr(), cB.data_ptr(),
-                 cC.data_ptr(), wt.data_ptr(), 0, 0, 0, 0, 0, 0, out.data_ptr(), K, 0, _st())
-        assert _rel(out, want) < 4e-3
+        lib.call("pn2_mlp_gemm_dgrad", R, N, K, dz.data_ptr(), N, y.data_ptr(), N, wa.data_ptr(), wb.data_ptr(),
+                 negbias.data_ptr(), unscale.data_ptr(), 0, 0, 0, 0, 0, 0, out.data_ptr(), K, 0, _st())
+        assert _rel(out, want) < 1.5e-2
 
 
 @pytest.mark.parametrize("R,N,KP,KT,affine", [(1000, 32, 32, 3, False), (5000, 64, 96, 67, False), (999, 128, 128, 128, True),

@@ -67,8 +67,10 @@ def main():
         pm = [torch.randn(K, device=dev) * 0.3 + 1 for _ in range(4)]
         dzp = torch.empty(R, K, dtype=BF, device=dev)
         sums = torch.zeros(2, K, device=dev)
-        args = ("pn2_mlp_gemm_dgrad", R, N, K, dz.data_ptr(), N, y.data_ptr(), N, co[0].data_ptr(), co[1].data_ptr(),
-                co[2].data_ptr(), wt.data_ptr(), x.data_ptr(), K, pm[0].data_ptr(), pm[1].data_ptr(), pm[2].data_ptr(),
+        wb = wt.to(torch.float16)
+        unscale = torch.ones(1, device=dev)
+        args = ("pn2_mlp_gemm_dgrad", R, N, K, dz.data_ptr(), N, y.data_ptr(), N, wt.data_ptr(), wb.data_ptr(),
+                pm[0].data_ptr(), unscale.data_ptr(), x.data_ptr(), K, pm[0].data_ptr(), pm[1].data_ptr(), pm[2].data_ptr(),
                 pm[3].data_ptr(), dzp.data_ptr(), K, sums.data_ptr(), st())
         t = timeit(lambda: _lib.call(*args))
         nb = fused.alg_bytes("pn2_mlp_gemm_dgrad", args[1:])
