@@ -647,21 +647,8 @@ __global__ void bn_finalize_kernel(int n, float inv_rows, float unbias, const fl
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= n) return;
-    const float mean = sums[c] * inv_rows;
-    const float var = fmaxf(fmaf(-mean, mean, sums[n + c] * inv_rows), 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float sc = gamma[c] * rstd;
-    scale[c] = sc;
-    shift[c] = fmaf(-mean, sc, beta[c]);
-    mean_out[c] = mean;
-    rstd_out[c] = rstd;
-    if (running_mean) {
-        // the conv bias and the centring constant shift the batch mean BatchNorm sees; the GEMM omits
-        // both (BatchNorm cancels them exactly)
-        const float m = mean + (bias ? bias[c] : 0.f) + (center ? center[c] : 0.f);
-        running_mean[c] = fmaf(momentum, m - running_mean[c], running_mean[c]);
-        running_var[c] = fmaf(momentum, var * unbias - running_var[c], running_var[c]);
-    }
+    bn_finalize_channel(c, n, sums[c], sums[n + c], inv_rows, unbias, gamma, beta, bias, center, momentum, eps, running_mean,
+                        running_var, scale, shift, mean_out, rstd_out);
 }
 
 __global__ void bn_eval_affine_kernel(int n, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -773,10 +760,34 @@ __global__ void prep_weights_kernel(int n, int k_true, int kp, const float* __re
     if (wt) wt[(size_t)c * n + r] = __float2bfloat16(v);
 }
 
+// every layer's weights in one launch: blockIdx.y = layer, grid-stride over its [n][kp] elements
+struct PrepDesc {
+    const float* w;
+    act_t* wh;
+    int n, k_true, kp, pad;
+};
+__global__ void __launch_bounds__(256) prep_weights_multi_kernel(const PrepDesc* __restrict__ descs) {
+    const PrepDesc d = descs[blockIdx.y];
+    const int total = d.n * d.kp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / d.kp, c = i - r * d.kp;
+        d.wh[i] = f_to_h(c < d.k_true ? d.w[(size_t)r * d.k_true + c] : 0.f);
+    }
+}
+
 }  // namespace
 }  // namespace pn2
 
 using namespace pn2;
+
+extern "C" int pn2_mlp_prep_weights_multi(int n_layers, const void* descs, pn2_stream_t stream) {
+    if (n_layers < 0) return fail_arg("pn2_mlp_prep_weights_multi", "negative layer count");
+    if (n_layers == 0) return 0;
+    if (!descs) return fail_arg("pn2_mlp_prep_weights_multi", "null pointer");
+    prep_weights_multi_kernel<<<dim3(32, n_layers), 256, 0, (cudaStream_t)stream>>>((const PrepDesc*)descs);
+    PN2_CHECK_LAUNCH("prep_weights_multi_kernel");
+    return 0;
+}
 
 extern "C" int pn2_mlp_center(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
                               const float* in_shift, const void* w, const float* in_offset, float* center,
@@ -809,6 +820,34 @@ extern "C" int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, 
     if (gemm_use_tc()) return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
     if (in_scale) return dispatch_bn<A_AFFINE, false>(a, (cudaStream_t)stream);
     return dispatch_bn<A_PLAIN, false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int pn2_mlp_gemm_fwd_bn(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
+                                   const float* in_shift, const void* w, const float* center, void* y, int y_ld,
+                                   float* stats, unsigned int* counter, const float* gamma, const float* beta,
+                                   const float* conv_bias, const float* center_true, float momentum, float eps,
+                                   float* running_mean, float* running_var, long long* num_batches_tracked,
+                                   float* scale, float* shift, float* mean, float* rstd, pn2_stream_t stream) {
+    if (int e = check_common("pn2_mlp_gemm_fwd_bn", rows, kdim, n)) return e;
+    if (rows == 0) return fail_arg("pn2_mlp_gemm_fwd_bn", "BatchNorm statistics of zero rows");
+    if (!x || !w || !y || !stats || !counter || !gamma || !beta || !scale || !shift || !mean || !rstd)
+        return fail_arg("pn2_mlp_gemm_fwd_bn", "null pointer");
+    if (x_ld % 8 || y_ld % 8 || x_ld < kdim || y_ld < n) return fail_arg("pn2_mlp_gemm_fwd_bn", "bad leading dimension");
+    GemmArgs a{};
+    a.rows = rows; a.kdim = kdim; a.n = n;
+    a.a0 = (const uint16_t*)x; a.a0_ld = x_ld;
+    a.c0 = in_scale; a.c1 = in_shift;
+    a.b = (const uint16_t*)w;
+    a.center = center;
+    a.out = (uint16_t*)y; a.out_ld = y_ld;
+    a.sums = stats;
+    a.fin_counter = counter; a.fin_gamma = gamma; a.fin_beta = beta; a.fin_bias = conv_bias; a.fin_center = center_true;
+    a.fin_momentum = momentum; a.fin_eps = eps;
+    a.fin_unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
+    a.fin_inv_rows = (float)(1.0 / (double)rows);
+    a.fin_running_mean = running_mean; a.fin_running_var = running_var; a.fin_nbt = num_batches_tracked;
+    a.fin_scale = scale; a.fin_shift = shift; a.fin_mean = mean; a.fin_rstd = rstd;
+    return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
 }
 
 extern "C" int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const void* dz, int dz_ld, const void* y,

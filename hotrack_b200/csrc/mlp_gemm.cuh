@@ -23,7 +23,37 @@ struct GemmArgs {
     const uint16_t* yp; int yp_ld;   // MASK: previous layer's y (fp16)
     const float *p_scale, *p_shift, *p_mean, *p_rstd;
     int nst, bres;                   // set by the mma.sync launcher
+    // forward + training: BatchNorm finalisation by the last CTA to finish (fin_counter != null; zeroed by the caller)
+    unsigned int* fin_counter;
+    const float *fin_gamma, *fin_beta, *fin_bias, *fin_center;
+    float fin_momentum, fin_eps, fin_unbias, fin_inv_rows;
+    float *fin_running_mean, *fin_running_var;
+    long long* fin_nbt;
+    float *fin_scale, *fin_shift, *fin_mean, *fin_rstd;
 };
+
+// BatchNorm finalisation of one channel from the column sums (shared by bn_finalize_kernel and the GEMM tail)
+__device__ __forceinline__ void bn_finalize_channel(int c, int n, float s1, float s2, float inv_rows, float unbias,
+                                                    const float* gamma, const float* beta, const float* bias,
+                                                    const float* center, float momentum, float eps, float* running_mean,
+                                                    float* running_var, float* scale, float* shift, float* mean_out,
+                                                    float* rstd_out) {
+    const float mean = s1 * inv_rows;
+    const float var = fmaxf(fmaf(-mean, mean, s2 * inv_rows), 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = fmaf(-mean, sc, beta[c]);
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+    if (running_mean) {
+        // the conv bias and the centring constant shift the batch mean BatchNorm sees; the GEMM omits
+        // both (BatchNorm cancels them exactly)
+        const float m = mean + (bias ? bias[c] : 0.f) + (center ? center[c] : 0.f);
+        running_mean[c] = fmaf(momentum, m - running_mean[c], running_mean[c]);
+        running_var[c] = fmaf(momentum, var * unbias - running_var[c], running_var[c]);
+    }
+}
 
 struct WgradArgs {
     long long rows;

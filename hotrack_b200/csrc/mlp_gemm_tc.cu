@@ -445,6 +445,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                 }
                 epi_bar();
             }
+            if (FWD && p.fin_counter) {
+                // BatchNorm finalisation by the last CTA to get here: its predecessors' sums are complete (their
+                // atomics precede their counter increment) -- one launch less per layer
+                __shared__ int s_last;
+                __threadfence();
+                epi_bar();
+                if (tid == 0) s_last = atomicAdd(p.fin_counter, 1u) == gridDim.x * gridDim.y - 1;
+                epi_bar();
+                if (s_last) {
+                    __threadfence();
+                    if (tid == 0 && p.fin_nbt) *p.fin_nbt += 1;
+                    for (int c = tid; c < p.n; c += kEpiThreads)
+                        bn_finalize_channel(c, p.n, __ldcg(p.sums + c), __ldcg(p.sums + p.n + c), p.fin_inv_rows, p.fin_unbias,
+                                            p.fin_gamma, p.fin_beta, p.fin_bias, p.fin_center, p.fin_momentum, p.fin_eps,
+                                            p.fin_running_mean, p.fin_running_var, p.fin_scale, p.fin_shift, p.fin_mean,
+                                            p.fin_rstd);
+                }
+            }
         }
     }
 

@@ -58,6 +58,54 @@ def set_sparse_grad_sink(on):
     SPARSE_GRAD_SINK = bool(on)
 
 
+class WeightPlan:
+    """fp16 copies of the conv weights of a step, all converted by ONE launch at the top of the step.
+
+    The first step records which (weight, padded width) pairs the stacks ask for (and converts them one by one, as
+    the engine does without a plan); from then on ``prepare()`` converts all of them with a single
+    pn2_mlp_prep_weights_multi launch instead of one small launch in front of every GEMM.  ``finish()`` invalidates
+    the copies (the optimiser is about to change the weights).  Owned by TrainStep."""
+
+    def __init__(self):
+        self.entries = {}      # (data_ptr, kp) -> (weight view, fp16 buffer)
+        self.table = None      # device array of PrepDesc records, rebuilt when an entry is added
+        self.ready = False
+
+    def prepare(self):
+        self.ready = False
+        if not self.entries:
+            return
+        if self.table is None:
+            import struct
+            raw = b"".join(struct.pack("<QQiiii", w.data_ptr(), buf.data_ptr(), w.shape[0], w.shape[1], kp, 0)
+                           for (_, kp), (w, buf) in self.entries.items())
+            dev = next(iter(self.entries.values()))[0].device
+            self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        _lib.call("pn2_mlp_prep_weights_multi", len(self.entries), self.table.data_ptr(), _stream())
+        self.ready = True
+
+    def lookup(self, w, kp):
+        """fp16 [cout][kp] copy of ``w`` for this step (converted now if it was not planned)."""
+        key = (w.data_ptr(), kp)
+        e = self.entries.get(key)
+        if e is not None and self.ready:
+            return e[1]
+        buf = e[1] if e is not None else torch.empty(w.shape[0], kp, dtype=_F16, device=w.device)
+        _lib.call("pn2_mlp_prep_weights", w.shape[0], w.shape[1], kp, w.data_ptr(), buf.data_ptr(), 0, _stream())
+        if e is None:
+            # a detached alias: holding the autograd-tracked view would keep the parameter's grad accumulator of
+            # THAT step alive (with the stream it was created on), which a later CUDA-graph capture trips over
+            self.entries[key] = (w.detach(), buf)
+            self.table = None
+        return buf
+
+    def finish(self):
+        self.ready = False
+
+
+ACTIVE_PLAN = None  # set by TrainStep around its forward pass
+
+
 class _Sink:
     __slots__ = ("rows", "c", "buf")
 
@@ -192,7 +240,8 @@ class _MlpStack(Function):
                 in_off[start:start + r.c] = r.offset
         # one zero-filled arena for every accumulator of the forward pass (one memset per stack)
         widths = [params[4 * l].shape[0] for l in range(nl)]
-        arena = torch.zeros(2 * sum(widths) + widths[-1], dtype=torch.float32, device=dev)
+        arena = torch.zeros(2 * sum(widths) + widths[-1] + nl, dtype=torch.float32, device=dev)
+        counters = arena[2 * sum(widths) + widths[-1]:]  # one zeroed word per layer (GEMM tail: BatchNorm finalisation)
         a_off = 0
         for l in range(nl):
             w, bias, gamma, beta = params[4 * l: 4 * l + 4]
@@ -201,8 +250,11 @@ class _MlpStack(Function):
             L.cout, L.cin, L.kp = w.shape[0], w.shape[1], kp
             if L.cout % 32:
                 raise ValueError("fused engine needs layer widths that are multiples of 32 (got %d)" % L.cout)
-            L.w = torch.empty(L.cout, kp, dtype=_F16, device=dev)
-            _lib.call("pn2_mlp_prep_weights", L.cout, L.cin, kp, w.data_ptr(), L.w.data_ptr(), 0, st)
+            if ACTIVE_PLAN is not None and training:
+                L.w = ACTIVE_PLAN.lookup(w, kp)
+            else:
+                L.w = torch.empty(L.cout, kp, dtype=_F16, device=dev)
+                _lib.call("pn2_mlp_prep_weights", L.cout, L.cin, kp, w.data_ptr(), L.w.data_ptr(), 0, st)
             L.y = torch.empty(R, L.cout, dtype=_F16, device=dev)
             consts = torch.empty(6, L.cout, dtype=torch.float32, device=dev)
             L.scale, L.shift, L.mean, L.rstd, cen, cen_true = (consts[i] for i in range(6))
@@ -211,13 +263,13 @@ class _MlpStack(Function):
             if training:
                 stats = arena[a_off:a_off + 2 * L.cout]
                 a_off += 2 * L.cout
-                _lib.call("pn2_mlp_gemm_fwd", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
-                          cen.data_ptr(), L.y.data_ptr(), L.cout, stats.data_ptr(), st)
                 track = bn.track_running_stats and bn.running_mean is not None
-                _lib.call("pn2_bn_finalize", L.cout, R, stats.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
-                          _p(bias), cen_true.data_ptr(), _bn_momentum(bn), float(bn.eps), _p(bn.running_mean) if track else 0,
-                          _p(bn.running_var) if track else 0, _p(bn.num_batches_tracked) if track else 0,
-                          L.scale.data_ptr(), L.shift.data_ptr(), L.mean.data_ptr(), L.rstd.data_ptr(), st)
+                _lib.call("pn2_mlp_gemm_fwd_bn", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
+                          cen.data_ptr(), L.y.data_ptr(), L.cout, stats.data_ptr(), counters[l].data_ptr(),
+                          bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias), cen_true.data_ptr(), _bn_momentum(bn),
+                          float(bn.eps), _p(bn.running_mean) if track else 0, _p(bn.running_var) if track else 0,
+                          _p(bn.num_batches_tracked) if track else 0, L.scale.data_ptr(), L.shift.data_ptr(),
+                          L.mean.data_ptr(), L.rstd.data_ptr(), st)
             else:
                 _lib.call("pn2_bn_eval_affine", L.cout, bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias),
                           cen_true.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps),
@@ -233,7 +285,7 @@ class _MlpStack(Function):
         out = torch.empty(B, C, groups, dtype=torch.float32, device=dev)
         chan_sums = argmax = None
         if pool_k > 1:
-            chan_sums = arena[2 * sum(widths):]
+            chan_sums = arena[2 * sum(widths):2 * sum(widths) + widths[-1]]
             argmax = torch.empty(B, groups, C, dtype=torch.int32, device=dev) if training else None
         _lib.call("pn2_pool_fwd", B, groups, pool_k, C, last.y.data_ptr(), C, last.scale.data_ptr(),
                   last.shift.data_ptr(), out.data_ptr(), _p(chan_sums), _p(argmax), st)
@@ -457,7 +509,7 @@ def dense_stack(x, convs, bns, training):
 
 def alg_bytes(name, a):
     """Algorithmic bytes of one C-ABI call of the fused kernels (bench.py's roofline line)."""
-    if name == "pn2_mlp_gemm_fwd":
+    if name in ("pn2_mlp_gemm_fwd", "pn2_mlp_gemm_fwd_bn"):
         rows, kdim, n = a[:3]
         return rows * (kdim + n) * 2 + n * kdim * 2
     if name == "pn2_mlp_gemm_dgrad":

@@ -6,6 +6,8 @@ CUDA graph and replayed, which removes the per-launch host cost of the ~400 kern
 The reference's equivalent is Trainer.update (network/trainer.py:278-302): zero_grad, model forward,
 compute_loss, backward, optimizer.step, each a Python-dispatched op sequence.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -17,6 +19,9 @@ class TrainStep:
         self.model, self.loss_fn = model, loss_fn
         from . import fused
         fused.set_sparse_grad_sink(True)  # whole-step backward: gather gradients travel in row form
+        self._fused = fused
+        self.weights = fused.WeightPlan()
+        self.use_plan = os.environ.get("PN2_NO_WPLAN", "") == ""
         self.flat = FlatParams(model)
         self.flat.broadcast(0)
         self.opt = FlatAdam(self.flat, lr=lr, weight_decay=weight_decay)
@@ -28,7 +33,14 @@ class TrainStep:
 
     def _fwd_bwd(self, inputs):
         self.flat.zero_grad()
-        loss = self.loss_fn(self.model(*inputs))
+        if self.use_plan:
+            self.weights.prepare()  # fp16 weight copies of every layer, on a side stream, while the step starts
+            self._fused.ACTIVE_PLAN = self.weights
+        try:
+            loss = self.loss_fn(self.model(*inputs))
+        finally:
+            self._fused.ACTIVE_PLAN = None
+            self.weights.finish()
         loss.backward()
         return loss.detach()
 

@@ -86,6 +86,15 @@ int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* 
                  const float* shift, const float* mean, const float* rstd, const int* argmax, void* dz, int dz_ld,
                  float* sums, pn2_stream_t stream);
 
+/* pn2_mlp_gemm_fwd followed by pn2_bn_finalize in ONE launch: the last CTA to finish reads the complete column sums and
+ * writes scale / shift / mean / rstd and the running statistics.  counter: one zeroed unsigned int (consumed). */
+int pn2_mlp_gemm_fwd_bn(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
+                        const float* in_shift, const void* w, const float* center, void* y, int y_ld, float* stats,
+                        unsigned int* counter, const float* gamma, const float* beta, const float* conv_bias,
+                        const float* center_true, float momentum, float eps, float* running_mean, float* running_var,
+                        long long* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
+                        pn2_stream_t stream);
+
 /* BatchNorm-backward per-channel coefficients: dY = cA*dz + cB*y + cC; dgamma = sums[c..2c), dbeta = sums[0..c)
  * (accumulate != 0: added to the existing contents -- the parameters' .grad buffers).
  * w != NULL (fp32 conv weight [n][k_true]): also the weights with the coefficients folded in, for pn2_mlp_gemm_dgrad:
@@ -113,6 +122,10 @@ int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, const void* dz
 
 /* fp32 conv weight [n][k_true] -> bf16 [n][kp] (zero padded) and, if wt != NULL, its transpose [kp][n]. */
 int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_bf16, void* wt_bf16, pn2_stream_t stream);
+
+/* pn2_mlp_prep_weights (fp16 copy only) for n_layers layers in ONE launch.  descs: device array of n_layers records
+ * { const float* w; void* w_f16; int n; int k_true; int kp; int pad; } (32 bytes each). */
+int pn2_mlp_prep_weights_multi(int n_layers, const void* descs, pn2_stream_t stream);
 
 /* Gradient of sa_build_rows' output rows scattered to the feature tensors (fp32, zeroed by the caller, atomics):
  * dfeat_cm (B,feat_c,N) channel-major -- or, feat_rows_major != 0, rows [B*N][feat_c] (coalesced; the form
