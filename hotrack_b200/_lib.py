@@ -43,7 +43,7 @@ SIGNATURES = {
     "pn2_bn_finalize": [_i, _ll, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "pn2_bn_eval_affine": [_i, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p],
     "pn2_pool_fwd": [_i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p],
-    "pn2_pool_bwd": [_i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p],
+    "pn2_pool_bwd": [_i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p],
     "pn2_bn_bwd_coefs": [_i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p],
     "pn2_mlp_gemm_dgrad": [_ll, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p],
     "pn2_mlp_gemm_wgrad": [_ll, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p],

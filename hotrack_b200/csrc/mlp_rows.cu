@@ -216,6 +216,7 @@ struct PoolArgs {
     int* argmax;          // (B,S,C)
     const float* dout_cm; // backward (nullable when extra_rows carries the whole gradient)
     const float* extra_rows;  // backward, k == 1: additional output gradient in row form [B*S][C] (nullable)
+    const bf16* extra16; int extra16_ld;  // backward, k == 1: ... and one in bf16 rows (a dense consumer's dx; nullable)
     bf16* dz; int dz_ld;
     float* sums;          // [2][C]
 };
@@ -342,6 +343,115 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
     }
 }
 
+// ---- few groups (given-centre SA: 21 joints; group-all): one CTA per group at a time, the K rows of the group split
+// over the 8 warps, a lane owning 8 consecutive channels (16-byte row pieces), slabs of 256 channels.
+constexpr int kSlab = 256;
+
+__global__ void __launch_bounds__(kThreads) pool_fwd_grp_kernel(const PoolArgs a) {
+    __shared__ float sv[8][kSlab];
+    __shared__ int si[8][kSlab];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int groups = a.b * a.s;
+    for (int c0 = 0; c0 < a.c; c0 += kSlab) {
+        const int cw = min(kSlab, a.c - c0);        // channels of this slab (multiple of 8)
+        const int ch = c0 + lane * 8;
+        const bool on = lane * 8 < cw;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc[e] = on ? a.scale[ch + e] : 0.f; sh[e] = on ? a.shift[ch + e] : 0.f; }
+        float csum = 0.f;                           // thread tid <-> channel c0 + tid
+        for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+            float m[8];
+            int mi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { m[e] = -1.f; mi[e] = 0; }  // below every ReLU output: the first row always wins
+            if (on) {
+                const act_t* yr = a.y + ((size_t)g * a.k) * a.y_ld + ch;
+#pragma unroll 4
+                for (int kk = warp; kk < a.k; kk += 8) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(yr + (size_t)kk * a.y_ld));
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(&q);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = h2_to_f2(w[e]);
+                        const float r0 = fmaxf(fmaf(f.x, sc[2 * e], sh[2 * e]), 0.f);
+                        const float r1 = fmaxf(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]), 0.f);
+                        if (r0 > m[2 * e]) { m[2 * e] = r0; mi[2 * e] = kk; }
+                        if (r1 > m[2 * e + 1]) { m[2 * e + 1] = r1; mi[2 * e + 1] = kk; }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { sv[warp][lane * 8 + e] = m[e]; si[warp][lane * 8 + e] = mi[e]; }
+            }
+            __syncthreads();
+            if (tid < cw) {
+                float best = sv[0][tid];
+                int bi = si[0][tid];
+#pragma unroll
+                for (int w2 = 1; w2 < 8; ++w2) {  // first maximum in row order: larger value, or equal value and earlier row
+                    const float v = sv[w2][tid];
+                    const int i2 = si[w2][tid];
+                    if (v > best || (v == best && i2 < bi)) { best = v; bi = i2; }
+                }
+                const int b = g / a.s, s_ = g - b * a.s;
+                a.out_cm[((size_t)b * a.c + c0 + tid) * a.s + s_] = best;
+                if (a.argmax) a.argmax[(size_t)g * a.c + c0 + tid] = bi;
+                csum += best;
+            }
+            __syncthreads();
+        }
+        if (a.chan_sums && tid < cw && csum != 0.f) atomicAdd(a.chan_sums + c0 + tid, csum);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) pool_bwd_grp_kernel(const PoolArgs a) {
+    __shared__ float sg[kSlab];
+    __shared__ int si[kSlab];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int groups = a.b * a.s;
+    for (int c0 = 0; c0 < a.c; c0 += kSlab) {
+        const int cw = min(kSlab, a.c - c0);
+        const int c = c0 + tid;
+        const bool mine = tid < cw;
+        float sc = 0.f, sh = 0.f, mu = 0.f, rs = 0.f, p1 = 0.f, p2 = 0.f;
+        if (mine) { sc = a.scale[c]; sh = a.shift[c]; mu = a.mean[c]; rs = a.rstd[c]; }
+        for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+            if (mine) {  // the output gradient lands on the arg-max row, through the ReLU mask
+                const int b = g / a.s, s_ = g - b * a.s;
+                const int kk = a.argmax[(size_t)g * a.c + c];
+                const float yv = h_to_f(a.y[((size_t)g * a.k + kk) * a.y_ld + c]);
+                float d = a.dout_cm[((size_t)b * a.c + c) * a.s + s_];
+                d = fmaf(yv, sc, sh) > 0.f ? d : 0.f;
+                p1 += d;
+                p2 = fmaf(d, (yv - mu) * rs, p2);
+                sg[tid] = d;
+                si[tid] = kk;
+            }
+            __syncthreads();
+            if (lane * 8 < cw) {
+                float gv[8];
+                int gi[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { gv[e] = sg[lane * 8 + e]; gi[e] = si[lane * 8 + e]; }
+                bf16* dr = a.dz + ((size_t)g * a.k) * a.dz_ld + c0 + lane * 8;
+                for (int kk = warp; kk < a.k; kk += 8) {
+                    uint4 q;
+                    q.x = f2_to_bf2(gi[0] == kk ? gv[0] : 0.f, gi[1] == kk ? gv[1] : 0.f);
+                    q.y = f2_to_bf2(gi[2] == kk ? gv[2] : 0.f, gi[3] == kk ? gv[3] : 0.f);
+                    q.z = f2_to_bf2(gi[4] == kk ? gv[4] : 0.f, gi[5] == kk ? gv[5] : 0.f);
+                    q.w = f2_to_bf2(gi[6] == kk ? gv[6] : 0.f, gi[7] == kk ? gv[7] : 0.f);
+                    *reinterpret_cast<uint4*>(dr + (size_t)kk * a.dz_ld) = q;
+                }
+            }
+            __syncthreads();
+        }
+        if (mine) {
+            if (p1 != 0.f) atomicAdd(a.sums + c, p1);
+            if (p2 != 0.f) atomicAdd(a.sums + a.c + c, p2);
+        }
+    }
+}
+
 // ---- K == 1 (FP layers, head): BatchNorm+ReLU and rows -> channel-major transpose, wide accesses.
 // A CTA owns tiles of 32 consecutive rows x all C channels.  blockDim is a multiple of the C/8 16-byte
 // pieces of a row, so thread t always handles piece t % pieces (its 8 channels' constants and partial
@@ -422,6 +532,15 @@ __global__ void __launch_bounds__(kThreads) cm_to_rows_bwd_kernel(const PoolArgs
                     const float4 e1 = __ldg(reinterpret_cast<const float4*>(a.extra_rows + row * a.c + pc * 8 + 4));
                     ex[0] = e0.x; ex[1] = e0.y; ex[2] = e0.z; ex[3] = e0.w;
                     ex[4] = e1.x; ex[5] = e1.y; ex[6] = e1.z; ex[7] = e1.w;
+                }
+                if (a.extra16) {  // gradient a dense consumer (the next fused stack) left in bf16 row form
+                    const uint4 qe = __ldg(reinterpret_cast<const uint4*>(a.extra16 + row * a.extra16_ld + pc * 8));
+                    const uint32_t* ew = reinterpret_cast<const uint32_t*>(&qe);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = bf2_to_f2(ew[e]);
+                        ex[2 * e] += f.x; ex[2 * e + 1] += f.y;
+                    }
                 }
                 uint4 o;
                 uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
@@ -669,8 +788,8 @@ extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld,
         grid = dim3(s_tiles < 32 ? s_tiles : 32, b);
         rows_to_cm_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(a);
     } else if (k > 1 && s <= 64) {
-        pool_grid<8>(a, grid);
-        pool_fwd_kernel<8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        const int groups = b * s;
+        pool_fwd_grp_kernel<<<groups < 592 ? groups : 592, kThreads, 0, (cudaStream_t)stream>>>(a);
     } else {
         pool_grid<32>(a, grid);
         pool_fwd_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
@@ -679,19 +798,23 @@ extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld,
     return 0;
 }
 
-extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* extra_rows, const void* y,
-                            int y_ld, const float* scale, const float* shift, const float* mean, const float* rstd,
+extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* extra_rows,
+                            const void* extra_rows16, int extra16_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean, const float* rstd,
                             const int* argmax, void* dz, int dz_ld, float* sums, pn2_stream_t stream) {
     if (b < 0 || s <= 0 || k <= 0 || c <= 0 || c % 8) return fail_arg("pn2_pool_bwd", "bad size");
     if (b == 0) return 0;
     if (b > 65535) return fail_arg("pn2_pool_bwd", "b > 65535");
-    if ((!dout_cm && !extra_rows) || !y || !scale || !shift || !mean || !rstd || !dz || !sums)
+    if ((!dout_cm && !extra_rows && !extra_rows16) || !y || !scale || !shift || !mean || !rstd || !dz || !sums)
         return fail_arg("pn2_pool_bwd", "null pointer");
     if (k > 1 && !argmax) return fail_arg("pn2_pool_bwd", "argmax required when k > 1");
-    if (extra_rows && !(k == 1 && c <= 1024)) return fail_arg("pn2_pool_bwd", "extra_rows needs k == 1 and c <= 1024");
+    if ((extra_rows || extra_rows16) && !(k == 1 && c <= 1024))
+        return fail_arg("pn2_pool_bwd", "extra_rows needs k == 1 and c <= 1024");
+    if (extra_rows16 && (extra16_ld < c || extra16_ld % 8)) return fail_arg("pn2_pool_bwd", "bad extra16_ld");
+    if (k > 1 && !dout_cm) return fail_arg("pn2_pool_bwd", "dout_cm required when k > 1");
     PoolArgs a{};
     a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
     a.mean = mean; a.rstd = rstd; a.argmax = const_cast<int*>(argmax); a.dout_cm = dout_cm; a.extra_rows = extra_rows;
+    a.extra16 = (const bf16*)extra_rows16; a.extra16_ld = extra16_ld;
     a.dz = (bf16*)dz; a.dz_ld = dz_ld; a.sums = sums;
     dim3 grid;
     if (k == 1 && c <= 1024) {
@@ -710,8 +833,8 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
         grid = dim3(s_tiles < 32 ? s_tiles : 32, b);
         cm_to_rows_bwd_kernel<<<grid, threads, smem > red ? smem : red, (cudaStream_t)stream>>>(a);
     } else if (k > 1 && s <= 64) {
-        pool_grid<8>(a, grid);
-        pool_bwd_kernel<8><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        const int groups = b * s;
+        pool_bwd_grp_kernel<<<groups < 592 ? groups : 592, kThreads, 0, (cudaStream_t)stream>>>(a);
     } else {
         pool_grid<32>(a, grid);
         pool_bwd_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);

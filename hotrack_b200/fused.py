@@ -106,11 +106,18 @@ class WeightPlan:
 ACTIVE_PLAN = None  # set by TrainStep around its forward pass
 
 
+def _token(shape, dev):
+    """A gradient that occupies no memory (all strides 0, value 0): returned for an input whose real gradient went
+    through the producer's sink, so that autograd still schedules the producer's backward."""
+    return torch.zeros((), dtype=torch.float32, device=dev).expand(shape)
+
+
 class _Sink:
-    __slots__ = ("rows", "c", "buf")
+    __slots__ = ("rows", "c", "buf", "rows16")
 
     def __init__(self, rows, c):
         self.rows, self.c, self.buf = rows, c, None
+        self.rows16 = None  # (bf16 [rows][ld] tensor, ld): the input gradient of a dense consumer, left in row form
 
 
 class Rows:
@@ -300,7 +307,7 @@ class _MlpStack(Function):
             ctx.out_sink = _Sink(R, C) if (training and C <= 1024) else None
             _MlpStack.last_rows = Rows(last.y, C, C, last.scale, last.shift, sink=ctx.out_sink)
         # gather-type consumer of a producer that offers a sink: deliver the feature gradient in row form
-        ctx.feat_sink = ra.sink if (kind == "sa" and SPARSE_GRAD_SINK and training and ra is not None
+        ctx.feat_sink = ra.sink if (kind in ("sa", "dense") and SPARSE_GRAD_SINK and training and ra is not None
                                     and ra.sink is not None and a is not None and a.requires_grad) else None
 
         ctx.kind, ctx.meta, ctx.training = kind, meta, training
@@ -317,10 +324,13 @@ class _MlpStack(Function):
     def backward(ctx, dout):
         nl = len(ctx.layers)
         none_params = [None] * (4 * nl)
+        if dout is not None and dout.numel() > 1 and all(st_ == 0 for st_ in dout.stride()):
+            dout = None  # the zero-stride token of a consumer that delivered its gradient through the sink
         extra = ctx.out_sink.buf if ctx.out_sink is not None else None
+        extra16 = ctx.out_sink.rows16 if ctx.out_sink is not None else None
         if ctx.out_sink is not None:
-            ctx.out_sink.buf = None
-        if dout is None and extra is None:
+            ctx.out_sink.buf = ctx.out_sink.rows16 = None
+        if dout is None and extra is None and extra16 is None:
             return (None, None, None, None, None, None, None, *none_params)
         if not ctx.training:
             raise NotImplementedError("fused engine: backward through eval-mode BatchNorm is not implemented; "
@@ -338,7 +348,8 @@ class _MlpStack(Function):
         arena = torch.zeros(2 * sum(L.cout for L in layers), dtype=torch.float32, device=dev)
         a_off = 2 * C
         sums = arena[:a_off]
-        _lib.call("pn2_pool_bwd", B, groups, pool_k, C, _p(dout), _p(extra), last.y.data_ptr(), C, last.scale.data_ptr(),
+        _lib.call("pn2_pool_bwd", B, groups, pool_k, C, _p(dout), _p(extra), _p(extra16[0]) if extra16 else 0,
+                  extra16[1] if extra16 else 0, last.y.data_ptr(), C, last.scale.data_ptr(),
                   last.shift.data_ptr(), last.mean.data_ptr(), last.rstd.data_ptr(), _p(ctx.argmax), dz.data_ptr(), C,
                   sums.data_ptr(), st)
         need_a = ctx.needs_input_grad[5] and ctx.a_shape is not None
@@ -414,7 +425,8 @@ class _MlpStack(Function):
                 if sink is not None:
                     if sink.buf is None:
                         sink.buf = torch.zeros(sink.rows, sink.c, dtype=torch.float32, device=dev)
-                    dfeat, rows_major = sink.buf, 1  # da stays None: the producer's backward picks the buffer up
+                    dfeat, rows_major = sink.buf, 1  # the producer's backward picks the buffer up ...
+                    da = _token(ctx.a_shape, dev)      # ... and this memory-less zero makes autograd run it
                 elif need_a:
                     da = torch.zeros(ctx.a_shape, dtype=torch.float32, device=dev)
                     dfeat, rows_major = da, 0
@@ -435,6 +447,9 @@ class _MlpStack(Function):
                           _p(dcr), st)
                 if need_b:
                     db = dcr.view(B, S, c2).transpose(1, 2).contiguous()
+            elif ctx.feat_sink is not None and need_a:
+                ctx.feat_sink.rows16 = (dx0, dx0.shape[1])  # the producer's backward reads it as rows
+                da = _token(ctx.a_shape, dev)
             else:
                 Bc, Cc, Nc = ctx.a_shape
                 da = dx0.view(Bc, Nc, -1)[:, :, :Cc].transpose(1, 2).float().contiguous()

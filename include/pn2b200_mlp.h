@@ -81,7 +81,8 @@ int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld, const floa
  * sum(dz), sums[c..2c) += sum(dz * xhat)  (zeroed by the caller).  k == 1 only: extra_rows [B*S][c] fp32
  * (nullable) is a second output-gradient term in row form (what consumers that GATHER from this output
  * deliver, see pn2_sa_rows_bwd); dout_cm may then be NULL. */
-int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* extra_rows, const void* y, int y_ld,
+int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* extra_rows, const void* extra_rows16,
+                 int extra16_ld, const void* y, int y_ld,
                  const float* scale,
                  const float* shift, const float* mean, const float* rstd, const int* argmax, void* dz, int dz_ld,
                  float* sums, pn2_stream_t stream);

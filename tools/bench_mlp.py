@@ -103,7 +103,7 @@ def main():
         dout = torch.randn(B, C, S, device=dev)
         dz = torch.empty(R, C, dtype=BF, device=dev)
         sums = torch.zeros(2, C, device=dev)
-        args = ("pn2_pool_bwd", B, S, K, C, dout.data_ptr(), y.data_ptr(), C, c4[0].data_ptr(), c4[1].data_ptr(),
+        args = ("pn2_pool_bwd", B, S, K, C, dout.data_ptr(), 0, 0, 0, y.data_ptr(), C, c4[0].data_ptr(), c4[1].data_ptr(),
                 c4[2].data_ptr(), c4[3].data_ptr(), am.data_ptr() if K > 1 else 0, dz.data_ptr(), C, sums.data_ptr(), st())
         t = timeit(lambda: _lib.call(*args))
         nb = fused.alg_bytes("pn2_pool_bwd", args[1:])
