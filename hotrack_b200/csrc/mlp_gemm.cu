@@ -425,22 +425,25 @@ int check_common(const char* who, long long rows, int kdim, int n) {
 }
 
 // ------------------------------------------------------------------ wgrad -------------------
-constexpr int TN = 128, TK = 128, SLD = 128 + 8;
+constexpr int TN = 64, TK = 128;            // CTA tile: 64 output channels x 128 input channels
+constexpr int SLDN = TN + 8, SLD = TK + 8;   // shared-memory row strides (odd multiples of 16 bytes: conflict-free ldmatrix)
 
-// Stage = WBR rows x 128 columns of dz, y (-> dY in place over dz) and x (-> X' in place), brought in
-// by cp.async WST stages deep; one CTA per SM, >= 100 KB of loads in flight.
+// Stage = WBR rows of dz / y (64 columns; dz -> dY in place) and x (128 columns; -> X' in place), brought in by
+// cp.async WST stages deep.  8 warps and ~108 KB per CTA: TWO CTAs per SM, so one CTA's transform / barrier phase
+// overlaps the other's ldmatrix + mma phase (the kernel is latency-bound, not issue- or bandwidth-bound).
 constexpr int WBR = 64, WST = 3;
-constexpr int kWgradSmem = WST * 3 * WBR * SLD * 2 + 5 * 128 * 4;
+constexpr int kWgradStage = WBR * (2 * SLDN + SLD);  // 16-bit elements
+constexpr int kWgradSmem = WST * kWgradStage * 2 + 5 * 128 * 4;
 
-constexpr int kWgradThreads = 512;  // 16 warps: 4 (Cout) x 4 (Cin) warp tiles of 32 x 32
+constexpr int kWgradThreads = 256;  // 8 warps: 2 (Cout) x 4 (Cin) warp tiles of 32 x 32
 
 template <bool AFFINE>
-__global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const WgradArgs p) {
+__global__ void __launch_bounds__(kWgradThreads, 2) wgrad_kernel(const WgradArgs p) {
     constexpr int kThreads = kWgradThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint16_t* sD = reinterpret_cast<uint16_t*>(smem_raw);  // [WST][WBR][SLD] dz -> dY (bf16)
-    uint16_t* sY = sD + WST * WBR * SLD;                   // [WST][WBR][SLD] y (fp16)
-    uint16_t* sX = sY + WST * WBR * SLD;                   // [WST][WBR][SLD] x (fp16) -> X' (bf16)
+    uint16_t* sD = reinterpret_cast<uint16_t*>(smem_raw);  // [WST][WBR][SLDN] dz -> dY (bf16)
+    uint16_t* sY = sD + WST * WBR * SLDN;                  // [WST][WBR][SLDN] y (fp16)
+    uint16_t* sX = sY + WST * WBR * SLDN;                  // [WST][WBR][SLD]  x (fp16) -> X' (bf16)
     float* sCo = reinterpret_cast<float*>(sX + WST * WBR * SLD);  // [5][128]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const WgradArgs
         const int which = i >> 7, c = i & 127;
         float v = 0.f;
         if (which < 3) {
-            if (n0 + c < p.n) v = (which == 0 ? p.cA : (which == 1 ? p.cB : p.cC))[n0 + c];
+            if (c < TN && n0 + c < p.n) v = (which == 0 ? p.cA : (which == 1 ? p.cB : p.cC))[n0 + c];
         } else if (AFFINE) {
             if (k0 + c < p.kp) v = (which == 3 ? p.in_scale : p.in_shift)[k0 + c];
         }
@@ -459,8 +462,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const WgradArgs
 
     const long long chunks = (p.rows + WBR - 1) / WBR;
     const long long mine = blockIdx.z < chunks ? (chunks - blockIdx.z + gridDim.z - 1) / gridDim.z : 0;
-    const int p_row = tid >> 4, p_col = (tid & 15) * 8;  // 2 pieces per matrix per thread: rows p_row + 32*j
-    const bool ncol_ok = n0 + p_col < p.n, kcol_ok = k0 + p_col < p.kp;
+    const int d_row = tid >> 3, d_col = (tid & 7) * 8;    // dz / y: 2 pieces per thread, rows d_row + 32*j
+    const int x_row = tid >> 4, x_col = (tid & 15) * 8;   // x: 4 pieces per thread, rows x_row + 16*j
+    const bool ncol_ok = n0 + d_col < p.n, kcol_ok = k0 + x_col < p.kp;
 
     long long is_i = 0, is_ch = blockIdx.z;
     int is_st = 0;
@@ -470,14 +474,22 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const WgradArgs
             const int st = is_st;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int r = p_row + j * 32;
+                const int r = d_row + j * 32;
                 const long long row = ch * WBR + r;
                 const bool ok = row < p.rows;
                 const long long rr = ok ? row : 0;
-                const int off = (st * WBR + r) * SLD + p_col;
-                cp_async16(&sD[off], p.dz + rr * p.dz_ld + (ncol_ok ? n0 + p_col : 0), ok && ncol_ok ? 16 : 0);
-                cp_async16(&sY[off], p.y + rr * p.y_ld + (ncol_ok ? n0 + p_col : 0), ok && ncol_ok ? 16 : 0);
-                cp_async16(&sX[off], p.x + rr * p.x_ld + (kcol_ok ? k0 + p_col : 0), ok && kcol_ok ? 16 : 0);
+                const int off = (st * WBR + r) * SLDN + d_col;
+                cp_async16(&sD[off], p.dz + rr * p.dz_ld + (ncol_ok ? n0 + d_col : 0), ok && ncol_ok ? 16 : 0);
+                cp_async16(&sY[off], p.y + rr * p.y_ld + (ncol_ok ? n0 + d_col : 0), ok && ncol_ok ? 16 : 0);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = x_row + j * 16;
+                const long long row = ch * WBR + r;
+                const bool ok = row < p.rows;
+                const long long rr = ok ? row : 0;
+                cp_async16(&sX[(st * WBR + r) * SLD + x_col], p.x + rr * p.x_ld + (kcol_ok ? k0 + x_col : 0),
+                           ok && kcol_ok ? 16 : 0);
             }
             ++is_i;
             is_ch += gridDim.z;
@@ -488,26 +500,41 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const WgradArgs
     auto transform = [&](long long ch, int st) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int r = p_row + j * 32;
+            const int r = d_row + j * 32;
             const bool ok = ch * WBR + r < p.rows;
-            const int off = (st * WBR + r) * SLD + p_col;
-            uint4 vd = make_uint4(0u, 0u, 0u, 0u), vx = make_uint4(0u, 0u, 0u, 0u);
+            const int off = (st * WBR + r) * SLDN + d_col;
+            uint4 vd = make_uint4(0u, 0u, 0u, 0u);
             if (ok) {
                 const uint4 qd = *reinterpret_cast<const uint4*>(&sD[off]);
                 const uint4 qy = *reinterpret_cast<const uint4*>(&sY[off]);
-                const uint4 qx = *reinterpret_cast<const uint4*>(&sX[off]);
                 const uint32_t* a = reinterpret_cast<const uint32_t*>(&qd);
                 const uint32_t* b = reinterpret_cast<const uint32_t*>(&qy);
-                const uint32_t* x = reinterpret_cast<const uint32_t*>(&qx);
                 uint32_t* od = reinterpret_cast<uint32_t*>(&vd);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = d_col + 2 * e;
+                    const float2 d = bf2_to_f2(a[e]), y = h2_to_f2(b[e]);
+                    // columns beyond n have zero coefficients and zero-filled data: they stay 0
+                    od[e] = f2_to_bf2(fmaf(sCo[c], d.x, fmaf(sCo[128 + c], y.x, sCo[256 + c])),
+                                      fmaf(sCo[c + 1], d.y, fmaf(sCo[128 + c + 1], y.y, sCo[256 + c + 1])));
+                }
+            }
+            *reinterpret_cast<uint4*>(&sD[off]) = vd;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = x_row + j * 16;
+            const bool ok = ch * WBR + r < p.rows;
+            const int off = (st * WBR + r) * SLD + x_col;
+            uint4 vx = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) {
+                const uint4 qx = *reinterpret_cast<const uint4*>(&sX[off]);
+                const uint32_t* x = reinterpret_cast<const uint32_t*>(&qx);
                 uint32_t* ox = reinterpret_cast<uint32_t*>(&vx);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int c = p_col + 2 * e;
-                    const float2 d = bf2_to_f2(a[e]), y = h2_to_f2(b[e]), xv = h2_to_f2(x[e]);
-                    // columns beyond n / kp have zero coefficients and zero-filled data: they stay 0
-                    od[e] = f2_to_bf2(fmaf(sCo[c], d.x, fmaf(sCo[128 + c], y.x, sCo[256 + c])),
-                                      fmaf(sCo[c + 1], d.y, fmaf(sCo[128 + c + 1], y.y, sCo[256 + c + 1])));
+                    const int c = x_col + 2 * e;
+                    const float2 xv = h2_to_f2(x[e]);
                     if (AFFINE)
                         ox[e] = f2_to_bf2(fmaxf(fmaf(xv.x, sCo[384 + c], sCo[512 + c]), 0.f),
                                           fmaxf(fmaf(xv.y, sCo[384 + c + 1], sCo[512 + c + 1]), 0.f));
@@ -515,12 +542,11 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const WgradArgs
                         ox[e] = f2_to_bf2(xv.x, xv.y);  // the gradient GEMM runs in bf16
                 }
             }
-            *reinterpret_cast<uint4*>(&sD[off]) = vd;
             *reinterpret_cast<uint4*>(&sX[off]) = vx;
         }
     };
 
-    const int wn2 = warp >> 2, wk = warp & 3;  // 4 x 4 warps
+    const int wn2 = warp >> 2, wk = warp & 3;  // 2 x 4 warps
     const bool warp_on = (n0 + wn2 * 32 < p.n) && (k0 + wk * 32 < p.kp);
     float acc[2][4][4];
 #pragma unroll
@@ -545,7 +571,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) wgrad_kernel(const WgradArgs
                 uint32_t af[2][4], bfr[2][4];
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
-                    ldsm_x4_trans(af[mf], smem_u32(&sD[(st * WBR + rs + (mi >> 1) * 8 + l7) * SLD + wn2 * 32 + mf * 16 +
+                    ldsm_x4_trans(af[mf], smem_u32(&sD[(st * WBR + rs + (mi >> 1) * 8 + l7) * SLDN + wn2 * 32 + mf * 16 +
                                                        (mi & 1) * 8]));
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb)
@@ -897,7 +923,7 @@ extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, con
     a.dw = dw; a.dw_ld = dw_ld;
     const int gx = (n + TN - 1) / TN, gy = (kp + TK - 1) / TK;
     const long long chunks = (rows + WBR - 1) / WBR;
-    long long gz = 148 / (gx * gy);  // one CTA per SM (shared memory), all resident
+    long long gz = 296 / (gx * gy);  // two CTAs per SM (shared memory), all resident
     if (gz < 1) gz = 1;
     if (gz > chunks) gz = chunks;
     dim3 grid(gx, gy, (unsigned)gz);

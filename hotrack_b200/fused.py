@@ -425,8 +425,11 @@ class _MlpStack(Function):
                 if sink is not None:
                     if sink.buf is None:
                         sink.buf = torch.zeros(sink.rows, sink.c, dtype=torch.float32, device=dev)
-                    dfeat, rows_major = sink.buf, 1  # the producer's backward picks the buffer up ...
-                    da = _token(ctx.a_shape, dev)      # ... and this memory-less zero makes autograd run it
+                    # the producer's backward picks the buffer up; da stays None (a token here would be ADDED, by a
+                    # 201 MB elementwise kernel, to the dense gradient the backbone output also receives): a gather
+                    # consumer relies on the producer's output having one more, dense, consumer -- in HandTrackNet
+                    # the per-point heads / the loss -- for autograd to schedule the producer's backward
+                    dfeat, rows_major = sink.buf, 1
                 elif need_a:
                     da = torch.zeros(ctx.a_shape, dtype=torch.float32, device=dev)
                     dfeat, rows_major = da, 0
