@@ -462,6 +462,17 @@ def main():
                             "alg_bytes_per_launch": int(nb), "avg_launch_us": round(avg_ms * 1e3, 3), "peak_source": peak_src,
                             "share_of_our_kernels": round(t / ours_ms, 4),
                             "timing": "CUDA events around each launch, eager probe pass after the timed region"}
+        if best is not None:
+            # dram__bytes_read + write of the same kernel / shape from the committed ncu --set full capture
+            # (profiles/r01_traffic.json: "<entry point>:<size args>" -> bytes per launch), null when not captured
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+                key = "%s:%s" % (best["kernel"], ",".join(str(v) for v in best["shape"]))
+                if key in tr:
+                    best["traffic"] = tr[key]["dram_bytes"]
+                    best["traffic_source"] = tr[key].get("source")
+            except (OSError, ValueError):
+                pass
         line["roofline"] = best
         line["kernel_shares"] = shares[:12]
         if not ddp and not args.no_cpu_baseline and not args.profile_mode:  # rank 0 at N=1 only
