@@ -39,7 +39,7 @@ SIGNATURES = {
     "pn2_mlp_center": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p],
     "pn2_mlp_gemm_fwd": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p],
     "pn2_mlp_gemm_fwd_bn": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p,
-                            _p],
+                            _p, _p],
     "pn2_bn_finalize": [_i, _ll, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "pn2_bn_eval_affine": [_i, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p],
     "pn2_pool_fwd": [_i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p],

@@ -853,7 +853,8 @@ extern "C" int pn2_mlp_gemm_fwd_bn(long long rows, int kdim, int n, const void* 
                                    float* stats, unsigned int* counter, const float* gamma, const float* beta,
                                    const float* conv_bias, const float* center_true, float momentum, float eps,
                                    float* running_mean, float* running_var, long long* num_batches_tracked,
-                                   float* scale, float* shift, float* mean, float* rstd, pn2_stream_t stream) {
+                                   float* scale, float* shift, float* mean, float* rstd, float* next_center,
+                                   pn2_stream_t stream) {
     if (int e = check_common("pn2_mlp_gemm_fwd_bn", rows, kdim, n)) return e;
     if (rows == 0) return fail_arg("pn2_mlp_gemm_fwd_bn", "BatchNorm statistics of zero rows");
     if (!x || !w || !y || !stats || !counter || !gamma || !beta || !scale || !shift || !mean || !rstd)
@@ -873,6 +874,7 @@ extern "C" int pn2_mlp_gemm_fwd_bn(long long rows, int kdim, int n, const void* 
     a.fin_inv_rows = (float)(1.0 / (double)rows);
     a.fin_running_mean = running_mean; a.fin_running_var = running_var; a.fin_nbt = num_batches_tracked;
     a.fin_scale = scale; a.fin_shift = shift; a.fin_mean = mean; a.fin_rstd = rstd;
+    a.fin_next_center = next_center;
     return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
 }
 

@@ -30,6 +30,7 @@ struct GemmArgs {
     float *fin_running_mean, *fin_running_var;
     long long* fin_nbt;
     float *fin_scale, *fin_shift, *fin_mean, *fin_rstd;
+    float* fin_next_center;          // nullable: [n] <- batch mean of the un-centred output (next step's centre)
 };
 
 // BatchNorm finalisation of one channel from the column sums (shared by bn_finalize_kernel and the GEMM tail)

@@ -456,11 +456,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                 if (s_last) {
                     __threadfence();
                     if (tid == 0 && p.fin_nbt) *p.fin_nbt += 1;
-                    for (int c = tid; c < p.n; c += kEpiThreads)
-                        bn_finalize_channel(c, p.n, __ldcg(p.sums + c), __ldcg(p.sums + p.n + c), p.fin_inv_rows, p.fin_unbias,
+                    for (int c = tid; c < p.n; c += kEpiThreads) {
+                        const float s1c = __ldcg(p.sums + c);
+                        bn_finalize_channel(c, p.n, s1c, __ldcg(p.sums + p.n + c), p.fin_inv_rows, p.fin_unbias,
                                             p.fin_gamma, p.fin_beta, p.fin_bias, p.fin_center, p.fin_momentum, p.fin_eps,
                                             p.fin_running_mean, p.fin_running_var, p.fin_scale, p.fin_shift, p.fin_mean,
                                             p.fin_rstd);
+                        // next step's centring constant = this step's batch mean of the un-centred output (may alias
+                        // p.center / p.fin_center: every CTA cached the centre at start, this thread read its element above)
+                        if (p.fin_next_center) p.fin_next_center[c] = fmaf(s1c, p.fin_inv_rows, p.center ? p.center[c] : 0.f);
+                    }
                 }
             }
         }

@@ -106,10 +106,12 @@ class WeightPlan:
 ACTIVE_PLAN = None  # set by TrainStep around its forward pass
 
 
-def _token(shape, dev):
-    """A gradient that occupies no memory (all strides 0, value 0): returned for an input whose real gradient went
-    through the producer's sink, so that autograd still schedules the producer's backward."""
-    return torch.zeros((), dtype=torch.float32, device=dev).expand(shape)
+def reset_center_state(module):
+    """Forget the centring constants training left on the BatchNorm modules of ``module`` (``_pn2_center``): the next
+    training forward re-estimates them from 16 sampled rows, exactly as a first step does."""
+    for m in module.modules():
+        if hasattr(m, "_pn2_center"):
+            del m._pn2_center
 
 
 class _Sink:
@@ -265,8 +267,22 @@ class _MlpStack(Function):
             L.y = torch.empty(R, L.cout, dtype=_F16, device=dev)
             consts = torch.empty(6, L.cout, dtype=torch.float32, device=dev)
             L.scale, L.shift, L.mean, L.rstd, cen, cen_true = (consts[i] for i in range(6))
-            _lib.call("pn2_mlp_center", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
-                      _p(in_off) if l == 0 else 0, cen.data_ptr(), cen_true.data_ptr(), st)
+            # Centring constant.  Training keeps it as state on the BatchNorm module: the GEMM tail of step t leaves the
+            # batch mean of the un-centred output there, and step t+1 centres by it (BatchNorm is shift-invariant, any
+            # constant near the mean serves) -- the 16-row estimate (pn2_mlp_center) then only runs on the first step, in
+            # eval mode, and for layers whose input rows carry a per-channel offset (its W.offset term is needed too).
+            stateful = training and not (l == 0 and in_off is not None)
+            state = getattr(bn, "_pn2_center", None) if stateful else None
+            if state is not None and (state.device != dev or state.numel() != L.cout):
+                state = None
+            next_cen = None
+            if state is not None:
+                cen = cen_true = next_cen = state
+            else:
+                _lib.call("pn2_mlp_center", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
+                          _p(in_off) if l == 0 else 0, cen.data_ptr(), cen_true.data_ptr(), st)
+                if stateful:
+                    next_cen = bn._pn2_center = torch.empty(L.cout, dtype=torch.float32, device=dev)
             if training:
                 stats = arena[a_off:a_off + 2 * L.cout]
                 a_off += 2 * L.cout
@@ -276,7 +292,7 @@ class _MlpStack(Function):
                           bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias), cen_true.data_ptr(), _bn_momentum(bn),
                           float(bn.eps), _p(bn.running_mean) if track else 0, _p(bn.running_var) if track else 0,
                           _p(bn.num_batches_tracked) if track else 0, L.scale.data_ptr(), L.shift.data_ptr(),
-                          L.mean.data_ptr(), L.rstd.data_ptr(), st)
+                          L.mean.data_ptr(), L.rstd.data_ptr(), _p(next_cen), st)
             else:
                 _lib.call("pn2_bn_eval_affine", L.cout, bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias),
                           cen_true.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps),
@@ -324,8 +340,6 @@ class _MlpStack(Function):
     def backward(ctx, dout):
         nl = len(ctx.layers)
         none_params = [None] * (4 * nl)
-        if dout is not None and dout.numel() > 1 and all(st_ == 0 for st_ in dout.stride()):
-            dout = None  # the zero-stride token of a consumer that delivered its gradient through the sink
         extra = ctx.out_sink.buf if ctx.out_sink is not None else None
         extra16 = ctx.out_sink.rows16 if ctx.out_sink is not None else None
         if ctx.out_sink is not None:
@@ -425,11 +439,7 @@ class _MlpStack(Function):
                 if sink is not None:
                     if sink.buf is None:
                         sink.buf = torch.zeros(sink.rows, sink.c, dtype=torch.float32, device=dev)
-                    # the producer's backward picks the buffer up; da stays None (a token here would be ADDED, by a
-                    # 201 MB elementwise kernel, to the dense gradient the backbone output also receives): a gather
-                    # consumer relies on the producer's output having one more, dense, consumer -- in HandTrackNet
-                    # the per-point heads / the loss -- for autograd to schedule the producer's backward
-                    dfeat, rows_major = sink.buf, 1
+                    dfeat, rows_major = sink.buf, 1  # da stays None: the producer's backward picks the buffer up
                 elif need_a:
                     da = torch.zeros(ctx.a_shape, dtype=torch.float32, device=dev)
                     dfeat, rows_major = da, 0
@@ -451,8 +461,9 @@ class _MlpStack(Function):
                 if need_b:
                     db = dcr.view(B, S, c2).transpose(1, 2).contiguous()
             elif ctx.feat_sink is not None and need_a:
-                ctx.feat_sink.rows16 = (dx0, dx0.shape[1])  # the producer's backward reads it as rows
-                da = _token(ctx.a_shape, dev)
+                # the producer's backward reads it as rows; da stays None (autograd still runs the producer's node,
+                # with an undefined gradient: ctx.set_materialize_grads(False))
+                ctx.feat_sink.rows16 = (dx0, dx0.shape[1])
             else:
                 Bc, Cc, Nc = ctx.a_shape
                 da = dx0.view(Bc, Nc, -1)[:, :, :Cc].transpose(1, 2).float().contiguous()

@@ -88,13 +88,16 @@ int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* 
                  float* sums, pn2_stream_t stream);
 
 /* pn2_mlp_gemm_fwd followed by pn2_bn_finalize in ONE launch: the last CTA to finish reads the complete column sums and
- * writes scale / shift / mean / rstd and the running statistics.  counter: one zeroed unsigned int (consumed). */
+ * writes scale / shift / mean / rstd and the running statistics.  counter: one zeroed unsigned int (consumed).
+ * next_center (nullable, may alias center / center_true): [n] <- center + batch mean of y, i.e. the batch mean of the
+ * un-centred output -- the centring constant a training loop passes as `center` at the next step instead of calling
+ * pn2_mlp_center again. */
 int pn2_mlp_gemm_fwd_bn(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
                         const float* in_shift, const void* w, const float* center, void* y, int y_ld, float* stats,
                         unsigned int* counter, const float* gamma, const float* beta, const float* conv_bias,
                         const float* center_true, float momentum, float eps, float* running_mean, float* running_var,
                         long long* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
-                        pn2_stream_t stream);
+                        float* next_center, pn2_stream_t stream);
 
 /* BatchNorm-backward per-channel coefficients: dY = cA*dz + cB*y + cC; dgamma = sums[c..2c), dbeta = sums[0..c)
  * (accumulate != 0: added to the existing contents -- the parameters' .grad buffers).

@@ -343,6 +343,8 @@ def test_sparse_grad_sink_matches_dense_autograd_path(cuda):
             res = []
             for sink in (False, True):
                 fused.set_sparse_grad_sink(sink)
+                for m_ in (convs, bns, q):
+                    fused.reset_center_state(m_)  # same centring constants (the 16-row estimate) in both runs
                 for p_ in params:
                     p_.grad = None
                 x = x0.clone().requires_grad_(True)
