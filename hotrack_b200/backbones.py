@@ -96,6 +96,8 @@ class PointNet2Msg_fast(nn.Module):
         l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
         l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
         skip = torch.cat([l0_xyz, l0_points], dim=-2) if l0_points.shape[-2] else l0_xyz  # backbones.py:127-130
+        # FP1's output goes to the fused head and nowhere else: its fp32 (B,C,N) copy need not be written
+        self.fp1._rows_only = pu.get_engine() == "fused" and getattr(self.fp1, "engine", "ops") == "fused"
         l0_points = self.fp1(l0_xyz, l1_xyz, skip, l1_points)
         return _head(self, pu._carry(l0_points, l0_points.reshape(B, -1, N)))
 

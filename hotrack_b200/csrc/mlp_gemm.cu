@@ -711,6 +711,16 @@ __global__ void __launch_bounds__(256) bn_bwd_coefs_kernel(int n, float inv_rows
     __shared__ float smax[8];
     const int tid = threadIdx.x;
     const bool first = blockIdx.x == 0 && blockIdx.y == 0;
+    // this thread's four weights of the tile first: their loads do not depend on the coefficients (latency overlap)
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32, tx = tid & 31, ty = tid >> 5;  // 32 x 8
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (w) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {  // w[n0 + ty + 8 jj][k0 + tx]: k contiguous
+            const int nn = n0 + ty + 8 * jj, kk = k0 + tx;
+            if (nn < n && kk < k_true) wv[jj] = __ldg(w + (size_t)nn * k_true + kk);
+        }
+    }
     for (int c = tid; c < n; c += 256) {
         const float s1 = sums[c], s2 = sums[n + c];
         const float m1 = s1 * inv_rows, m2 = s2 * inv_rows;
@@ -744,11 +754,8 @@ __global__ void __launch_bounds__(256) bn_bwd_coefs_kernel(int n, float inv_rows
     ex = max(-100, min(100, ex));
     const float wscale = exp2f((float)(4 - ex)), unscale = exp2f((float)(ex - 4));
     if (first && tid == 0) *wb_unscale = unscale;
-    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32, tx = tid & 31, ty = tid >> 5;  // 32 x 8
-    for (int j = ty; j < 32; j += 8) {  // read w[n0 + j][k0 + tx]: k contiguous
-        const int nn = n0 + j, kk = k0 + tx;
-        tile[j][tx] = (nn < n && kk < k_true) ? w[(size_t)nn * k_true + kk] : 0.f;
-    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) tile[ty + 8 * jj][tx] = wv[jj];
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {  // write [k0 + j][n0 + tx]: n contiguous
         const int kk = k0 + j, nn = n0 + tx;

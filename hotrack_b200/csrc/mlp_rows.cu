@@ -99,6 +99,10 @@ __device__ __forceinline__ void row_vals8(const RowSrc& s, size_t row, int ch, f
 // feature segment are one 16-byte gather; pieces straddling a segment boundary (the 3 coordinates shift the centre
 // segment off the 8-channel grid) are assembled element by element.
 __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildArgs a) {
+    // centre features (given-centre SA with per-centre features, reference pointnet_utils.py:574-575) are the same for
+    // the K rows of a group: when the 8 rows of a CTA share their group the BatchNorm+ReLU'd centre row is staged ONCE,
+    // at its OUTPUT columns, and every row copies aligned 16-byte pieces of it
+    __shared__ __align__(16) act_t s_cen[1024 + 8];
     const int lane = threadIdx.x & 31;
     const int gpr = a.out_ld >> 3;
     const int rpw = gpr >= 32 ? 1 : 32 / gpr;
@@ -106,20 +110,31 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
     const long long wrow = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * rpw;
     const int sub = gpr >= 32 ? 0 : lane / gpr;
     const long long row = wrow + sub;
+    const int fc = a.feat.p ? a.feat.c : 0, cc = a.cen.p ? a.cen.c : 0;
+    const int f0 = a.xyz_first ? 3 : 0, x0 = a.xyz_first ? 0 : fc, c0 = fc + 3;
+    const bool staged = cc > 0 && rpw == 1 && (a.k & 7) == 0 && a.out_ld <= 1024;
+    if (staged) {
+        const long long grp = ((long long)blockIdx.x * (kThreads / 32)) / a.k;  // b * s + s_idx of all 8 rows
+        for (int col = (c0 & ~7) + threadIdx.x; col < a.out_ld; col += kThreads)
+            s_cen[col] = f_to_h((col >= c0 && col < c0 + cc) ? row_val(a.cen, (size_t)grp, col - c0) : 0.f);
+        __syncthreads();
+    }
     if (row >= total || sub >= rpw) return;
     const int kk = (int)(row % a.k);
     const long long bs = row / a.k;
     const int s = (int)(bs % a.s), b = (int)(bs / a.s);
     const int j = a.idx ? __ldg(a.idx + row) : kk;
     const size_t frow = (size_t)b * a.n + j, crow = (size_t)b * a.s + s;
-    const int fc = a.feat.p ? a.feat.c : 0, cc = a.cen.p ? a.cen.c : 0;
-    const int f0 = a.xyz_first ? 3 : 0, x0 = a.xyz_first ? 0 : fc, c0 = fc + 3;
     const bool fvec = fc > 0 && f0 == 0 && (fc & 7) == 0 && (a.feat.ld & 7) == 0;
     float rel[3] = {0.f, 0.f, 0.f};
     bool have_rel = false;
     act_t* o = a.out + (size_t)row * a.out_ld;
     for (int g = gpr >= 32 ? lane : lane - sub * gpr; g < gpr; g += 32) {
         const int col = g << 3;
+        if (staged && col >= c0 && col + 8 <= c0 + cc) {  // a piece of centre features only
+            *reinterpret_cast<uint4*>(o + col) = *reinterpret_cast<const uint4*>(&s_cen[col]);
+            continue;
+        }
         float v[8];
         if (fvec && col + 8 <= fc) {
             row_vals8(a.feat, frow, col, v);
@@ -138,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
                 float t = 0.f;
                 if (c >= f0 && c < f0 + fc) t = row_val(a.feat, frow, c - f0);
                 else if (c >= x0 && c < x0 + 3) t = rel[c - x0];
-                else if (c >= c0 && c < c0 + cc) t = row_val(a.cen, crow, c - c0);
+                else if (c >= c0 && c < c0 + cc) t = staged ? h_to_f(s_cen[c]) : row_val(a.cen, crow, c - c0);
                 v[e] = t;
             }
         }

@@ -106,6 +106,40 @@ class WeightPlan:
 ACTIVE_PLAN = None  # set by TrainStep around its forward pass
 
 
+class ZeroArena:
+    """One zero-filled fp32 buffer per step for the accumulators of every stack (BatchNorm statistics, channel sums,
+    BatchNorm-backward sums, last-CTA counters): ONE memset at the top of the step instead of two small ones per stack.
+    Bump allocation, nothing is returned; a stack that finds the arena absent or exhausted falls back to torch.zeros.
+    Owned by TrainStep (static addresses: CUDA-graph friendly)."""
+
+    def __init__(self, device, floats=1 << 18):
+        self.buf = torch.zeros(floats, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def begin(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, n):
+        n = (n + 3) // 4 * 4  # 16-byte granules
+        if self.off + n > self.buf.numel():
+            return None
+        t = self.buf[self.off:self.off + n]
+        self.off += n
+        return t
+
+
+ACTIVE_ARENA = None  # set by TrainStep for the whole step (forward and backward)
+
+
+def _zeros(n, dev):
+    if ACTIVE_ARENA is not None and ACTIVE_ARENA.buf.device == dev:
+        t = ACTIVE_ARENA.take(n)
+        if t is not None:
+            return t[:n]
+    return torch.zeros(n, dtype=torch.float32, device=dev)
+
+
 def reset_center_state(module):
     """Forget the centring constants training left on the BatchNorm modules of ``module`` (``_pn2_center``): the next
     training forward re-estimates them from 16 sampled rows, exactly as a first step does."""
@@ -205,7 +239,7 @@ class _MlpStack(Function):
                       _p(rb.y) if rb else 0, cc, rb.ld if rb else 0, _p(rb.scale) if rb else 0, _p(rb.shift) if rb else 0,
                       1 if xyz_first else 0, x0.data_ptr(), x0.shape[1], st)
         elif kind == "fp":
-            idx, dist2, N, S = meta
+            idx, dist2, N, S = meta[:4]
             B = b.shape[0]
             sc = ra.c if ra is not None else 0
             cin = sc + rb.c
@@ -249,7 +283,7 @@ class _MlpStack(Function):
                 in_off[start:start + r.c] = r.offset
         # one zero-filled arena for every accumulator of the forward pass (one memset per stack)
         widths = [params[4 * l].shape[0] for l in range(nl)]
-        arena = torch.zeros(2 * sum(widths) + widths[-1] + nl, dtype=torch.float32, device=dev)
+        arena = _zeros(2 * sum(widths) + widths[-1] + nl, dev)
         counters = arena[2 * sum(widths) + widths[-1]:]  # one zeroed word per layer (GEMM tail: BatchNorm finalisation)
         a_off = 0
         for l in range(nl):
@@ -306,12 +340,14 @@ class _MlpStack(Function):
         last = layers[-1]
         C = last.cout
         out = torch.empty(B, C, groups, dtype=torch.float32, device=dev)
+        rows_only = kind == "fp" and len(meta) > 4 and meta[4] and pool_k == 1
         chan_sums = argmax = None
         if pool_k > 1:
             chan_sums = arena[2 * sum(widths):2 * sum(widths) + widths[-1]]
             argmax = torch.empty(B, groups, C, dtype=torch.int32, device=dev) if training else None
-        _lib.call("pn2_pool_fwd", B, groups, pool_k, C, last.y.data_ptr(), C, last.scale.data_ptr(),
-                  last.shift.data_ptr(), out.data_ptr(), _p(chan_sums), _p(argmax), st)
+        if not rows_only:  # rows_only: the caller promises that only the attached row form is read (backbone FP1 -> head)
+            _lib.call("pn2_pool_fwd", B, groups, pool_k, C, last.y.data_ptr(), C, last.scale.data_ptr(),
+                      last.shift.data_ptr(), out.data_ptr(), _p(chan_sums), _p(argmax), st)
         if pool_k > 1:
             # pooled features go to the next fused consumer as bf16 rows centred on their channel mean
             inv = 1.0 / (B * groups)
@@ -359,7 +395,7 @@ class _MlpStack(Function):
         C = last.cout
         dz = torch.empty(R, C, dtype=_BF16, device=dev)
         # one zero-filled arena for the BatchNorm-backward sums of every layer
-        arena = torch.zeros(2 * sum(L.cout for L in layers), dtype=torch.float32, device=dev)
+        arena = _zeros(2 * sum(L.cout for L in layers), dev)
         a_off = 2 * C
         sums = arena[:a_off]
         _lib.call("pn2_pool_bwd", B, groups, pool_k, C, _p(dout), _p(extra), _p(extra16[0]) if extra16 else 0,
@@ -450,7 +486,7 @@ class _MlpStack(Function):
                 _lib.call("pn2_sa_rows_bwd", B, N, S, K, _p(idx), dx0.data_ptr(), dx0.shape[1], fc, _p(dfeat), rows_major,
                           cc, _p(db), 1 if xyz_first else 0, st)
             elif ctx.kind == "fp":
-                idx, dist2, N, S = ctx.meta
+                idx, dist2, N, S = ctx.meta[:4]
                 sc = ctx.a_shape[1] if ctx.a_shape is not None else 0
                 c2 = ctx.b_shape[1]
                 if need_a:
@@ -514,8 +550,10 @@ def sa_group_all(xyz, points, convs, bns, training):
     return _run("sa", meta, convs, bns, training, points, None)
 
 
-def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1):
-    """FP layer.  xyz1_t (B,N,3), xyz2_t (B,S,3), points1 (B*reps,D1,N)|None, points2 (B*reps,D2,S) -> (B*reps,Cout,N)."""
+def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1, rows_only=False):
+    """FP layer.  xyz1_t (B,N,3), xyz2_t (B,S,3), points1 (B*reps,D1,N)|None, points2 (B*reps,D2,S) -> (B*reps,Cout,N).
+    rows_only: the returned fp32 tensor is left UNINITIALISED (only its attached row form is valid) -- for a caller that
+    hands it straight to another fused stack (the backbone's FP1 -> conv1 head) and saves a 67 MB transpose."""
     _check_cuda(points2)
     B, N, _ = xyz1_t.shape
     S = xyz2_t.shape[1]
@@ -527,7 +565,7 @@ def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1):
         pc.three_nn_wrapper(B, N, S, u, k, dist2, idx)
         if reps > 1:
             dist2, idx = dist2.repeat_interleave(reps, dim=0), idx.repeat_interleave(reps, dim=0)
-    return _run("fp", (idx, dist2, N, S), convs, bns, training, points1, points2)
+    return _run("fp", (idx, dist2, N, S, bool(rows_only)), convs, bns, training, points1, points2)
 
 
 def dense_stack(x, convs, bns, training):

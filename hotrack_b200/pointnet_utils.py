@@ -322,7 +322,8 @@ class _FpBase(nn.Module, _EngineMixin):
         N, S = xyz1_t.shape[1], xyz2_t.shape[1]
         if self._fused():
             from . import fused
-            return fused.fp_layer(xyz1_t, xyz2_t, points1, points2, self.mlp_convs, self.mlp_bns, self.training, reps)
+            return fused.fp_layer(xyz1_t, xyz2_t, points1, points2, self.mlp_convs, self.mlp_bns, self.training, reps,
+                                  rows_only=getattr(self, "_rows_only", False))
         if S == 1:
             interpolated = points2.expand(-1, -1, N)
         else:

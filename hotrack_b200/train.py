@@ -22,6 +22,7 @@ class TrainStep:
         self._fused = fused
         self.weights = fused.WeightPlan()
         self.use_plan = os.environ.get("PN2_NO_WPLAN", "") == ""
+        self.arena = fused.ZeroArena(self.flat_device(model)) if self.use_plan else None
         self.flat = FlatParams(model)
         self.flat.broadcast(0)
         self.opt = FlatAdam(self.flat, lr=lr, weight_decay=weight_decay)
@@ -31,8 +32,21 @@ class TrainStep:
         self._loss = None
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
+    @staticmethod
+    def flat_device(model):
+        return next(model.parameters()).device
+
     def _fwd_bwd(self, inputs):
         self.flat.zero_grad()
+        if self.arena is not None:
+            self.arena.begin()
+            self._fused.ACTIVE_ARENA = self.arena
+        try:
+            return self._fwd_bwd_inner(inputs)
+        finally:
+            self._fused.ACTIVE_ARENA = None
+
+    def _fwd_bwd_inner(self, inputs):
         if self.use_plan:
             self.weights.prepare()  # fp16 weight copies of every layer, on a side stream, while the step starts
             self._fused.ACTIVE_PLAN = self.weights

@@ -16,8 +16,8 @@ ops) timeout 300 python tools/bench_ops.py > $out/bench_ops.log 2>&1; tail -3 $o
 latency) timeout 300 python tools/bench_latency.py > $out/latency.log 2>&1; tail -3 $out/latency.log;;
 gemm) export LD_LIBRARY_PATH=$PWD/hotrack_b200:$LD_LIBRARY_PATH; timeout 120 ./tools/dev/gemm_tc_check time > $out/gemm_check.log 2>&1; tail -3 $out/gemm_check.log;;
 full) timeout 600 ncu --set full --clock-control none \
-    -k regex:'gemm_tc_kernel|wgrad_kernel|cm_to_rows_bwd|sa_build_rows|sa_rows_bwd|bn_bwd_coefs|center_kernel|fps_regs|ball_query|knn_kernel|three_nn' \
-    --launch-skip ${FULL_SKIP:-540} --launch-count ${FULL_COUNT:-180} -o $out/full -f \
+    -k regex:"${FULL_REGEX:-gemm_tc_kernel|wgrad_kernel|cm_to_rows_bwd|rows_to_cm|fps_regs|ball_query|knn_kernel|three_nn}" \
+    --launch-skip ${FULL_SKIP:-270} --launch-count ${FULL_COUNT:-90} -o $out/full -f \
     python bench.py --steps 1 --warmup 3 --profile-mode --no-graph > $out/full_ncu.log 2>&1
   ncu -i $out/full.ncu-rep --page raw --csv > $out/full_raw.csv 2>/dev/null
   sz=$(stat -c %s $out/full.ncu-rep); if [ "$sz" -gt 30000000 ]; then rm -f $out/full.ncu-rep; echo "rep dropped ($sz bytes)"; fi;;
