@@ -28,6 +28,11 @@
 // W * mean of a few sampled input rows); BatchNorm is shift-invariant, so only the running mean and
 // the eval-mode shift need c added back (bn_finalize / bn_eval_affine).
 //
+// STATUS: the production forward / input-gradient GEMM is mlp_gemm_tc.cu (tcgen05).  gemm_rows_kernel below is kept as
+// the forward cross-check (PN2_GEMM_IMPL=mma; tools/dev/gemm_tc_check.cu, tests); its BNBWD mode is no longer
+// dispatched (the input gradient now takes coefficient-folded weights, see bn_bwd_coefs_kernel).  wgrad_kernel, the
+// per-layer constant kernels and every extern "C" entry point of include/pn2b200_mlp.h's GEMM section live here.
+//
 // Machine mapping: persistent CTAs (<= 2 per SM) walk 128-row tiles; A is register-prefetched one
 // chunk ahead (so the prologue runs once per element, not once per consuming warp), B (weights,
 // L2-resident) streams through cp.async; mma.sync.m16n8k16 bf16 with fp32 accumulation.  Every layer

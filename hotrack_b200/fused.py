@@ -591,7 +591,8 @@ def alg_bytes(name, a):
         return b * s * k * c * 2 + b * s * c * 4 + (b * s * c * 4 if k > 1 else 0)
     if name == "pn2_pool_bwd":
         b, s, k, c = a[:4]
-        return b * s * c * 4 + b * s * k * c * 2 + (b * s * c * (4 + 2) if k > 1 else b * s * c * 2)
+        extra = (b * s * c * 4 if a[5] else 0) + (b * s * c * 2 if a[6] else 0)  # row-form gradients of fused consumers
+        return (b * s * c * 4 if a[4] else 0) + extra + b * s * k * c * 2 + (b * s * c * (4 + 2) if k > 1 else b * s * c * 2)
     if name == "pn2_sa_build_rows":
         b, n, s, k = a[:4]
         return b * s * k * (a[19] * 2 + 4) + b * s * k * 2 * (a[8] + a[13])
