@@ -14,7 +14,10 @@ how the parity tests and bench.py's reference arm run the SAME path on the refer
 """
 import types
 
+import torch
 import torch.nn as nn
+
+_SIDE = {}  # device index -> side stream for the early neighbour search (kept off the module: modules get deep-copied)
 
 
 def _ours():
@@ -40,8 +43,20 @@ class HandTrackPointPath(nn.Module):
     def forward(self, xyz2, xyz1):
         """xyz2 (B,3,N) canonicalised hand cloud, xyz1 (B,3,21) canonicalised joints ->
         (src2 (B,384,N), f11 (B,384,21), f13 (B,384,21), group indices)."""
+        pre = None
+        if xyz2.is_cuda and hasattr(self.q1, "group_indices"):
+            # q1's neighbour search needs the coordinates only: it runs on a side stream while the backbone starts
+            # (farthest point sampling keeps 32 of the 148 SMs busy for ~100 us and nothing else can run beside it)
+            side = _SIDE.get(xyz2.device.index)
+            if side is None:
+                side = _SIDE[xyz2.device.index] = torch.cuda.Stream(device=xyz2.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                pre = self.q1.group_indices(xyz2, xyz1)
         src2 = self.bhand(xyz2)
-        f11, idx = self.q1(xyz2, src2, xyz1, None, return_group_idx=True)
+        if pre is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        f11, idx = self.q1(xyz2, src2, xyz1, None, pre_group_idx=pre, return_group_idx=True)
         f13 = self.q2(xyz2, src2, xyz1, f11, pre_group_idx=idx)
         return src2, f11, f13, idx
 

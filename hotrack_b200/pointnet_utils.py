@@ -233,26 +233,27 @@ class PointNetSetAbstractionMsg_GivenCenterPoints(_MsgBase):
         super().__init__()
         self._build(radius_list, nsample_list, in_channel, mlp_list, knn)
 
+    def group_indices(self, xyz, new_xyz):
+        """The per-scale group indices (int64 (B,S,K) each) ``forward`` would compute: they depend on the coordinates
+        only, so a caller may ask for them ahead of time (e.g. on a side stream, while the backbone runs) and pass
+        them back as ``pre_group_idx``."""
+        xyz_t = xyz.transpose(1, 2).contiguous()
+        new_xyz_t = new_xyz.transpose(1, 2).contiguous()
+        if self.knn:
+            # the k nearest come back ascending with a stable tie rule (interpolate_gpu.cu:30-56), so the K nearest
+            # are the first K columns of the max(K) nearest: one search serves every scale
+            knn_all = _neighbour_idx(True, self.radius_list[0], max(self.nsample_list), xyz_t, new_xyz_t)
+            return [knn_all[..., :k].long() for k in self.nsample_list]
+        return [_neighbour_idx(False, r, k, xyz_t, new_xyz_t).long() for r, k in zip(self.radius_list, self.nsample_list)]
+
     def forward(self, xyz, points, new_xyz, new_points, return_4nn=False, pre_group_idx=None,
                 return_group_idx=False):
-        xyz_t = new_xyz_t = None
         outs, idx_list = [], []
-        idx = knn_all = None
+        idx = None
+        if pre_group_idx is None:
+            pre_group_idx = self.group_indices(xyz, new_xyz)
         for i, radius in enumerate(self.radius_list):
-            if pre_group_idx is not None:
-                idx = pre_group_idx[i]
-            else:
-                if xyz_t is None:
-                    xyz_t = xyz.transpose(1, 2).contiguous()
-                    new_xyz_t = new_xyz.transpose(1, 2).contiguous()
-                if self.knn:
-                    # the k nearest come back ascending with a stable tie rule (interpolate_gpu.cu:30-56), so the K
-                    # nearest are the first K columns of the max(K) nearest: one search serves every scale
-                    if knn_all is None:
-                        knn_all = _neighbour_idx(True, radius, max(self.nsample_list), xyz_t, new_xyz_t)
-                    idx = knn_all[..., :self.nsample_list[i]].long()
-                else:
-                    idx = _neighbour_idx(False, radius, self.nsample_list[i], xyz_t, new_xyz_t).long()
+            idx = pre_group_idx[i]
             idx_list.append(idx)
             outs.append(self._scale(i, xyz, points, new_xyz, idx.int(), new_points))
         out = torch.cat(outs, dim=1)
