@@ -75,6 +75,96 @@ def test_gemm_fwd_and_stats(lib, cuda, R, K, N, affine):
     torch.testing.assert_close(stats[1], (yf * yf).sum(0), rtol=2e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("R,K,N", [(5000, 64, 128), (20000, 128, 384), (300, 32, 32)])
+def test_gemm_fwd_bn_tail_matches_separate_finalize(lib, cuda, R, K, N):
+    """pn2_mlp_gemm_fwd_bn (BatchNorm finalisation by the last CTA, next-step centre) against pn2_mlp_gemm_fwd followed
+    by pn2_bn_finalize, and the finalisation itself against nn.BatchNorm semantics."""
+    g = torch.Generator(device="cpu").manual_seed(R + K + N)
+    x = torch.randn(R, K, generator=g).to(cuda).to(HF)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda).to(HF)
+    cen = (torch.randn(N, generator=g) * 0.1).to(cuda)
+    gamma, beta, bias = [(torch.randn(N, generator=g) * 0.3 + (1 if i == 0 else 0)).to(cuda) for i in range(3)]
+    res = []
+    for fused_tail in (False, True):
+        y = torch.empty(R, N, dtype=HF, device=cuda)
+        stats = torch.zeros(2, N, device=cuda)
+        rm, rv = torch.zeros(N, device=cuda), torch.ones(N, device=cuda)
+        nbt = torch.zeros(1, dtype=torch.int64, device=cuda)
+        o = [torch.full((N,), float("nan"), device=cuda) for _ in range(4)]  # scale shift mean rstd
+        nxt = cen.clone()  # aliases the centre in production; here a copy so both runs start alike
+        if fused_tail:
+            counter = torch.zeros(1, dtype=torch.int32, device=cuda)
+            lib.call("pn2_mlp_gemm_fwd_bn", R, K, N, x.data_ptr(), K, 0, 0, w.data_ptr(), cen.data_ptr(), y.data_ptr(), N,
+                     stats.data_ptr(), counter.data_ptr(), gamma.data_ptr(), beta.data_ptr(), bias.data_ptr(),
+                     cen.data_ptr(), 0.1, 1e-5, rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(), o[0].data_ptr(),
+                     o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), nxt.data_ptr(), _st())
+        else:
+            lib.call("pn2_mlp_gemm_fwd", R, K, N, x.data_ptr(), K, 0, 0, w.data_ptr(), cen.data_ptr(), y.data_ptr(), N,
+                     stats.data_ptr(), _st())
+            lib.call("pn2_bn_finalize", N, R, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), bias.data_ptr(),
+                     cen.data_ptr(), 0.1, 1e-5, rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(), o[0].data_ptr(),
+                     o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), _st())
+        res.append((y, rm, rv, nbt, o, nxt))
+    (ya, rma, rva, nba, oa, _), (yb, rmb, rvb, nbb, ob, nxt) = res
+    assert torch.equal(ya, yb) and int(nba) == 1 and int(nbb) == 1
+    for a, b in zip(oa + [rma, rva], ob + [rmb, rvb]):
+        torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5)  # atomics order only
+    yf = yb.float()
+    mean, var = yf.mean(0), yf.var(0, unbiased=False)
+    torch.testing.assert_close(ob[2], mean, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(ob[0], gamma * (var + 1e-5).rsqrt(), rtol=2e-3, atol=1e-4)
+    torch.testing.assert_close(rmb, 0.1 * (mean + bias + cen), rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(nxt, cen + mean, rtol=1e-3, atol=1e-3)
+
+
+def test_prep_weights_multi_matches_single(lib, cuda):
+    import struct
+    g = torch.Generator(device="cpu").manual_seed(3)
+    shapes = [(32, 3, 32), (128, 131, 192), (384, 128, 128)]  # (cout, cin, kp)
+    ws = [torch.randn(n, k, generator=g).to(cuda) for n, k, _ in shapes]
+    single = [torch.empty(n, kp, dtype=HF, device=cuda) for n, _, kp in shapes]
+    multi = [torch.full((n, kp), float("nan"), dtype=HF, device=cuda) for n, _, kp in shapes]
+    for w_, o_, (n, k, kp) in zip(ws, single, shapes):
+        lib.call("pn2_mlp_prep_weights", n, k, kp, w_.data_ptr(), o_.data_ptr(), 0, _st())
+    raw = b"".join(struct.pack("<QQiiii", w_.data_ptr(), o_.data_ptr(), n, k, kp, 0) for w_, o_, (n, k, kp) in zip(ws, multi, shapes))
+    table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(cuda)
+    lib.call("pn2_mlp_prep_weights_multi", len(shapes), table.data_ptr(), _st())
+    for a, b in zip(single, multi):
+        assert torch.equal(a, b)
+
+
+def test_wgrad_tcgen05_opt_in_matches_fp32():
+    """The opt-in tcgen05 weight-gradient kernel (PN2_WGRAD_IMPL=tc is read once per process -> subprocess)."""
+    import os
+    import subprocess
+    import sys
+    code = """
+import torch
+from hotrack_b200 import _lib as lib
+dev = torch.device('cuda:0'); g = torch.Generator(device='cpu').manual_seed(0)
+st = torch.cuda.current_stream().cuda_stream
+for R, N, KP, KT, affine in [(3000, 384, 128, 128, True), (2000, 128, 416, 387, False), (1000, 32, 32, 3, False)]:
+    dz = torch.randn(R, N, generator=g).to(dev).bfloat16(); y = torch.randn(R, N, generator=g).to(dev).half()
+    cA, cB, cC = [(torch.randn(N, generator=g) * 0.5).to(dev) for _ in range(3)]
+    x = torch.randn(R, KP, generator=g).to(dev).half(); x[:, KT:] = 0
+    xin = x.float(); sc = sh = None
+    if affine:
+        sc = (torch.rand(KP, generator=g) + 0.5).to(dev); sh = (torch.randn(KP, generator=g) * 0.3).to(dev)
+        xin = torch.relu(xin * sc + sh)
+    want = ((cA * dz.float() + cB * y.float() + cC).t() @ xin)[:, :KT]
+    dw = torch.zeros(N, KT, device=dev)
+    lib.call('pn2_mlp_gemm_wgrad', R, N, KP, KT, dz.data_ptr(), N, y.data_ptr(), N, cA.data_ptr(), cB.data_ptr(), cC.data_ptr(),
+             x.data_ptr(), KP, 0 if sc is None else sc.data_ptr(), 0 if sh is None else sh.data_ptr(), dw.data_ptr(), KT, st)
+    rel = ((dw - want).norm() / want.norm()).item()
+    assert rel < 4e-3, (R, N, KP, rel)
+print('ok')
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PN2_WGRAD_IMPL="tc", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("R,N,K,mask", [(1000, 64, 32, True), (3000, 128, 96, False), (513, 192, 128, True),
                                          (2048, 128, 416, False), (700, 32, 32, True)])
 def test_bn_bwd_coefs_and_gemm_dgrad(lib, cuda, R, N, K, mask):
