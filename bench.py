@@ -349,9 +349,11 @@ def main():
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             if from_host:
-                x = xyz_h.to(dev, non_blocking=True)
-                k = kps_h.to(dev, non_blocking=True)
-                loss = step(x, k)
+                if args.impl == "ours" and train.use_graph:
+                    # H2D straight into the replayed graph's input buffers (TrainStep copies whatever it is given)
+                    loss = step(xyz_h, kps_h)
+                else:
+                    loss = step(xyz_h.to(dev, non_blocking=True), kps_h.to(dev, non_blocking=True))
                 loss_h.copy_(loss.reshape(1), non_blocking=True)
             else:
                 step(xyz_d, kps_d)

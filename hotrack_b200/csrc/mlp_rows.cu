@@ -479,14 +479,15 @@ constexpr int kRowTile = 32;
 __global__ void __launch_bounds__(kThreads) rows_to_cm_kernel(const PoolArgs a) {
     extern __shared__ __align__(16) float tile_dyn[];  // [32][C + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int b = blockIdx.y;
     const int pieces = a.c >> 3, ldt = a.c + 1;
     const int pc = tid % pieces, r0 = tid / pieces, rstep = blockDim.x / pieces;
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sc[e] = a.scale[pc * 8 + e]; sh[e] = a.shift[pc * 8 + e]; }
     const int s_tiles = (a.s + kRowTile - 1) / kRowTile;
-    for (int t = blockIdx.x; t < s_tiles; t += gridDim.x) {
+    // persistent CTAs over the B * s_tiles tiles (a grid of one CTA per tile slot would run 1.7 waves at B=32, N=4096)
+    for (int gt = blockIdx.x; gt < a.b * s_tiles; gt += gridDim.x) {
+        const int b = gt / s_tiles, t = gt - b * s_tiles;
         const int s0 = t * kRowTile;
         for (int r = r0; r < kRowTile; r += rstep) {
             if (s0 + r < a.s) {
@@ -508,10 +509,9 @@ __global__ void __launch_bounds__(kThreads) rows_to_cm_kernel(const PoolArgs a) 
     }
 }
 
-__global__ void __launch_bounds__(kThreads) cm_to_rows_bwd_kernel(const PoolArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) cm_to_rows_bwd_kernel(const PoolArgs a) {
     extern __shared__ __align__(16) float tile_dyn[];  // [32][C + 1] dout tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int b = blockIdx.y;
     const int pieces = a.c >> 3, ldt = a.c + 1;
     const int pc = tid % pieces, r0 = tid / pieces, rstep = blockDim.x / pieces;
     float sc[8], sh[8], mu[8], rs[8], p1[8], p2[8];
@@ -522,7 +522,8 @@ __global__ void __launch_bounds__(kThreads) cm_to_rows_bwd_kernel(const PoolArgs
         p1[e] = p2[e] = 0.f;
     }
     const int s_tiles = (a.s + kRowTile - 1) / kRowTile;
-    for (int t = blockIdx.x; t < s_tiles; t += gridDim.x) {
+    for (int gt = blockIdx.x; gt < a.b * s_tiles; gt += gridDim.x) {  // persistent CTAs over the B * s_tiles tiles
+        const int b = gt / s_tiles, t = gt - b * s_tiles;
         const int s0 = t * kRowTile;
         // channel-major side: 8 independent 128-byte runs in flight per warp (c is a multiple of 8)
         if (a.dout_cm) {
@@ -536,26 +537,42 @@ __global__ void __launch_bounds__(kThreads) cm_to_rows_bwd_kernel(const PoolArgs
             }
         }
         __syncthreads();
-        for (int r = r0; r < kRowTile; r += rstep) {
-            if (s0 + r < a.s) {
-                const size_t row = (size_t)b * a.s + s0 + r;
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.y + row * a.y_ld + pc * 8));
-                const uint32_t* v = reinterpret_cast<const uint32_t*>(&q);
-                float ex[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (a.extra_rows) {  // gradient contributions consumers delivered in row form (sparse gathers)
-                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(a.extra_rows + row * a.c + pc * 8));
-                    const float4 e1 = __ldg(reinterpret_cast<const float4*>(a.extra_rows + row * a.c + pc * 8 + 4));
-                    ex[0] = e0.x; ex[1] = e0.y; ex[2] = e0.z; ex[3] = e0.w;
-                    ex[4] = e1.x; ex[5] = e1.y; ex[6] = e1.z; ex[7] = e1.w;
-                }
-                if (a.extra16) {  // gradient a dense consumer (the next fused stack) left in bf16 row form
-                    const uint4 qe = __ldg(reinterpret_cast<const uint4*>(a.extra16 + row * a.extra16_ld + pc * 8));
-                    const uint32_t* ew = reinterpret_cast<const uint32_t*>(&qe);
+        // row side, four rows per thread at a time: every global load of the batch is issued before the first store (a
+        // store followed by the next row's loads would serialise one memory latency per row)
+        constexpr int RB = 4;
+        for (int rb = r0; rb < kRowTile; rb += RB * rstep) {
+            uint4 qy[RB], q16[RB];
+            float4 e0[RB], e1[RB];
+            bool ok[RB];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 f = bf2_to_f2(ew[e]);
-                        ex[2 * e] += f.x; ex[2 * e + 1] += f.y;
+            for (int u = 0; u < RB; ++u) {
+                const int r = rb + u * rstep;
+                ok[u] = r < kRowTile && s0 + r < a.s;
+                e0[u] = e1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                q16[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[u]) {
+                    const size_t row = (size_t)b * a.s + s0 + r;
+                    qy[u] = __ldg(reinterpret_cast<const uint4*>(a.y + row * a.y_ld + pc * 8));
+                    if (a.extra_rows) {  // gradient contributions consumers delivered in row form (sparse gathers)
+                        e0[u] = __ldg(reinterpret_cast<const float4*>(a.extra_rows + row * a.c + pc * 8));
+                        e1[u] = __ldg(reinterpret_cast<const float4*>(a.extra_rows + row * a.c + pc * 8 + 4));
                     }
+                    if (a.extra16)  // gradient a dense consumer (the next fused stack) left in bf16 row form
+                        q16[u] = __ldg(reinterpret_cast<const uint4*>(a.extra16 + row * a.extra16_ld + pc * 8));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                if (!ok[u]) continue;
+                const int r = rb + u * rstep;
+                const size_t row = (size_t)b * a.s + s0 + r;
+                const uint32_t* v = reinterpret_cast<const uint32_t*>(&qy[u]);
+                const uint32_t* ew = reinterpret_cast<const uint32_t*>(&q16[u]);
+                float ex[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = bf2_to_f2(ew[e]);
+                    ex[2 * e] += f.x; ex[2 * e + 1] += f.y;
                 }
                 uint4 o;
                 uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
@@ -713,6 +730,15 @@ __global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a
     }
 }
 
+// grid of the K == 1 transposing kernels: as many CTAs as fit the GPU at once (shared memory bound), tiles dealt round-robin
+unsigned k1_grid(long long tiles, size_t smem_bytes, int reg_cap) {
+    long long per_sm = (long long)(227 * 1024) / (long long)(smem_bytes + 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > reg_cap) per_sm = reg_cap;  // CTAs per SM the register file allows
+    const long long slots = 148 * per_sm;
+    return (unsigned)(tiles < slots ? tiles : slots);
+}
+
 RowSrc mk_src(const void* p, int c, int ld, const float* scale, const float* shift) {
     RowSrc s;
     s.p = (const act_t*)p; s.c = c; s.ld = ld; s.scale = scale; s.shift = shift;
@@ -800,7 +826,7 @@ extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld,
         }
         const int pieces = c / 8;
         const int threads = pieces >= kThreads ? pieces : (kThreads / pieces) * pieces;  // multiple of pieces
-        grid = dim3(s_tiles < 32 ? s_tiles : 32, b);
+        grid = dim3(k1_grid((long long)b * s_tiles, smem, 4));
         rows_to_cm_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(a);
     } else if (k > 1 && s <= 64) {
         const int groups = b * s;
@@ -845,7 +871,7 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
         const int pieces = c / 8;
         const int threads = pieces >= kThreads ? pieces : (kThreads / pieces) * pieces;
         const size_t red = (size_t)2 * threads * 8 * sizeof(float);  // the final [rstep][2][C] reduction reuses the tile
-        grid = dim3(s_tiles < 32 ? s_tiles : 32, b);
+        grid = dim3(k1_grid((long long)b * s_tiles, smem > red ? smem : red, 2));
         cm_to_rows_bwd_kernel<<<grid, threads, smem > red ? smem : red, (cudaStream_t)stream>>>(a);
     } else if (k > 1 && s <= 64) {
         const int groups = b * s;
