@@ -103,7 +103,7 @@ class PointNet2Msg_fast(nn.Module):
 
 
 def _head(self, feats):
-    """relu(bn1(conv1(x))) (backbones.py:69,131-132); fused engine: one bf16 tensor-core stack."""
+    """relu(bn1(conv1(x))) (backbones.py:69,131-132); fused engine: one 16-bit tensor-core stack."""
     if pu.get_engine() == "fused" and getattr(self.fp1, "engine", "ops") == "fused":
         from . import fused
         return fused.dense_stack(feats, [self.conv1], [self.bn1], self.training)

@@ -6,7 +6,7 @@ Host side of include/pn2b200_mlp.h.  One ``autograd.Function`` (``_MlpStack``) r
 stack and its backward; ``sa_scale`` / ``sa_group_all`` / ``fp_layer`` / ``dense_stack`` are the
 entry points ``pointnet_utils.py`` / ``backbones.py`` call when the engine is "fused".  They take
 and return the reference's tensor layouts (channel-major fp32), so the modules stay drop-in; the
-bf16 row form of every output is additionally attached to the returned tensor (``_pn2_rows``) and
+16-bit row form of every output is additionally attached to the returned tensor (``_pn2_rows``) and
 picked up by the next fused consumer, which then never touches the fp32 copy.
 
 What replaces what (reference network/models/pointnet_utils.py):
@@ -18,6 +18,13 @@ BatchNorm semantics are nn.BatchNorm's: batch statistics (biased variance) in tr
 running-statistics update (momentum, unbiased variance, num_batches_tracked), running statistics
 in eval.  Training-mode conv biases cancel in BatchNorm: they only enter the running mean, and
 their gradient is exactly zero.
+
+Kernels behind it: forward and input-gradient GEMMs on tcgen05 / TMEM (csrc/mlp_gemm_tc.cu; BatchNorm
+finalisation in the forward GEMM's tail, BatchNorm-backward coefficients folded into the weights for the backward one),
+weight gradient on warp-level mma.sync (csrc/mlp_gemm.cu), row builders / poolers / scatters in csrc/mlp_rows.cu.
+Step-level helpers owned by train.TrainStep: WeightPlan (one weight-conversion launch per step) and ZeroArena (one memset
+for every accumulator of the step).  Training leaves one piece of state outside state_dict: ``bn._pn2_center``, the
+centring constant of each fused BatchNorm (reset_center_state() forgets it).
 """
 import torch
 from torch.autograd import Function

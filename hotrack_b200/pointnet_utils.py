@@ -11,7 +11,7 @@ Two engines sit behind the same modules:
                  libpn2b200.so; the 1x1 convolutions and BatchNorm stay ``torch.nn`` fp32 exactly as in
                  the reference (pointnet_utils.py:399-403).  This is the fp32 parity configuration.
 * ``"fused"`` -- the whole grouped MLP (gather -> conv/BN/ReLU stack -> max-pool, and three-NN
-                 interpolate -> concat -> conv/BN/ReLU stack) runs in hand-written bf16 tensor-core
+                 interpolate -> concat -> conv/BN/ReLU stack) runs in hand-written 16-bit (fp16 forward / bf16 gradient) tensor-core
                  kernels (``hotrack_b200.fused``).  Indices are identical (they depend on coordinates
                  only); features agree to bf16 rounding.
 
