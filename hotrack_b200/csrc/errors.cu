@@ -24,6 +24,6 @@ int fail_arg(const char* where, const char* what) {
 }
 }  // namespace pn2
 
-extern "C" int pn2_version(void) { return 100; /* 0.1.0 */ }
+extern "C" int pn2_version(void) { return 200; /* 0.2.0: tcgen05 GEMMs; pn2_mlp_gemm_dgrad / pn2_bn_bwd_coefs / pn2_pool_bwd signatures changed */ }
 extern "C" long long pn2_launch_count(void) { return pn2::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* pn2_last_error(void) { return pn2::g_last_error; }
