@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 
 #include "pn2_common.cuh"
+#include "../../include/pn2b200_mlp.h"  // every extern "C" definition is checked against its declaration
 
 namespace pn2 {
 

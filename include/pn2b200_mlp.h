@@ -7,8 +7,9 @@
  * fused "engine" calls (hotrack_b200/fused.py); conventions as in pn2b200.h: raw device pointers, int
  * sizes, caller-owned buffers, asynchronous on `stream`, int status (0 = ok, see pn2_last_error()).
  *
- * ROW MATRICES: activations are bf16 matrices X[rows][ld], channels contiguous (ld % 8 == 0,
- * 16-byte aligned base), rows = B*S*K grouped neighbours or B*N points.  A "row source" is such a
+ * ROW MATRICES: activations are 16-bit matrices X[rows][ld] -- fp16 for every forward quantity (inputs, pre-BatchNorm
+ * layer outputs, weights), bf16 for gradients --, channels contiguous (ld % 8 == 0, 16-byte aligned base),
+ * rows = B*S*K grouped neighbours or B*N points.  A "row source" is such a
  * matrix plus optional per-channel fp32 scale/shift: when given, the consumer reads
  * relu(x*scale + shift) -- i.e. the producer's BatchNorm + ReLU, applied on the fly.
  */

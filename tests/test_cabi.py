@@ -40,6 +40,38 @@ def test_every_bound_signature_is_declared():
         assert name in d, "%s is bound in _lib.py but not declared in include/" % name
 
 
+def _prototypes():
+    """name -> list of C parameter types, parsed from the headers."""
+    protos = {}
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        for m in re.finditer(r"\bint\s+(pn2_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+            params = [q.strip() for q in m.group(2).replace("\n", " ").split(",")]
+            protos[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and pointer / scalar kind of every ctypes binding against the C prototype it calls: a drift here is
+    silent (ctypes passes whatever it is given) until a kernel reads a pointer where a size was meant."""
+    from hotrack_b200 import _lib
+
+    protos = _prototypes()
+    for name, argtypes in _lib.SIGNATURES.items():
+        params = protos[name]
+        assert len(params) == len(argtypes), "%s: header has %d parameters, _lib.py binds %d" % (name, len(params), len(argtypes))
+        for i, (c_decl, ct) in enumerate(zip(params, argtypes)):
+            is_ptr = "*" in c_decl or "pn2_stream_t" in c_decl
+            if ct is ctypes.c_void_p:
+                assert is_ptr, "%s arg %d: bound as pointer, declared '%s'" % (name, i, c_decl)
+            elif ct is ctypes.c_float:
+                assert re.match(r"(const\s+)?float\s+\w+$", c_decl), "%s arg %d: bound as float, declared '%s'" % (name, i, c_decl)
+            elif ct is ctypes.c_longlong:
+                assert re.match(r"(const\s+)?long long\s+\w+$", c_decl), "%s arg %d: bound as long long, declared '%s'" % (name, i, c_decl)
+            elif ct is ctypes.c_int:
+                assert re.match(r"(const\s+)?int\s+\w+$", c_decl), "%s arg %d: bound as int, declared '%s'" % (name, i, c_decl)
+
+
 def test_argument_errors_are_status_codes_not_exits():
     from hotrack_b200 import _lib
 
