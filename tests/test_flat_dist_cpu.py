@@ -81,3 +81,32 @@ def test_two_rank_gradient_allreduce_equals_full_batch():
     data = torch.arange(8 * 4, dtype=torch.float32).reshape(8, 4) / 10.0
     (m(data).square().sum() / 8).backward()
     torch.testing.assert_close(g0, flat.grad, rtol=1e-5, atol=1e-6)  # SUM of shard grads == full-batch grad
+
+
+def test_zero_arena_bump_allocation_and_fallback():
+    """fused.ZeroArena (TrainStep's one-memset-per-step accumulator buffer): slices are disjoint, 16-byte granular, zero
+    after begin(), and a stack that finds the arena exhausted falls back to a fresh allocation."""
+    import torch
+
+    from hotrack_b200 import fused
+
+    dev = torch.device("cpu")
+    arena = fused.ZeroArena(dev, floats=64)
+    arena.begin()
+    a, b = arena.take(5), arena.take(9)
+    assert a.numel() == 8 and b.numel() == 12  # rounded up to 4-float granules
+    a.fill_(1.0)
+    b.fill_(2.0)
+    assert a.data_ptr() + 8 * 4 == b.data_ptr() and float(arena.buf.sum()) == 8 + 24
+    assert arena.take(64) is None  # exhausted: callers fall back
+    arena.begin()
+    assert float(arena.buf.abs().sum()) == 0.0 and arena.off == 0
+    fused.ACTIVE_ARENA = arena
+    try:
+        z = fused._zeros(10, dev)
+        assert z.numel() == 10 and z.data_ptr() == arena.buf.data_ptr()
+        big = fused._zeros(1000, dev)  # does not fit -> ordinary zeros
+        assert big.numel() == 1000 and float(big.abs().sum()) == 0.0
+    finally:
+        fused.ACTIVE_ARENA = None
+    assert fused._zeros(3, dev).numel() == 3
