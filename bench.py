@@ -58,9 +58,12 @@ def parse():
 
 # ------------------------------------------------------------------ helpers -------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms.  Started BEFORE the warm-up steps: nvidia-smi's
+    own start-up (device enumeration, ~0.1-0.3 s) stalls the GPU it queries for milliseconds, and when it ran into the
+    timed region it showed up as a 1.5-2x slower end-to-end leg on some boxes.  Only the samples whose timestamp lies
+    inside the timed window are reported (all of them if the clock-skew-free match finds none)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -68,6 +71,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -77,10 +81,48 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def stop(self):
+    def window_begin(self):
+        self.t0 = time.time()
+
+    def window_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _ts(text):
+        import datetime
+        for fmt in ("%Y/%m/%d %H:%M:%S.%f", "%Y/%m/%d %H:%M:%S"):
+            try:
+                return datetime.datetime.strptime(text, fmt).timestamp()
+            except ValueError:
+                pass
+        return None
+
+    def parse(self, text):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
+        for line in text.splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 10:
+                continue
+            try:
+                rows.append((self._ts(c[0]), float(c[2]), float(c[3]),
+                             {nm for nm, v in zip(names, c[6:10]) if v.lower().startswith("active")}))
+            except ValueError:
+                continue
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None
+                  and self.t0 - 0.2 <= r[0] <= self.t1 + 0.2]
+        use = inside or rows
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if use:
+            sm = sorted(r[1] for r in use)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in use),
+                       reasons=sorted(set().union(*[r[3] for r in use])), samples=len(use),
+                       window="timed region" if inside else "whole run")
+        return out
+
+    def stop(self):
         if self.p is None:
-            return out
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         time.sleep(0.25)
         self.p.terminate()
         try:
@@ -89,25 +131,9 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [t.strip() for t in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+        text = self.f.read()
         os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
-        return out
+        return self.parse(text)
 
 
 def peaks():
@@ -367,15 +393,19 @@ def main():
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()  # before the warm-up: its start-up cost must not land in the timed region
     for _ in range(W):
         step(xyz_d, kps_d)
     barrier()
 
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.window_begin()
     ms_dev = timed(K, from_host=False)
     ms_e2e = ms_dev if args.profile_mode else timed(K, from_host=True)
+    if sampler:
+        sampler.window_end()
     clocks = sampler.stop() if sampler else None
 
     # Per-kernel device times of OUR kernels, CUDA events around every C-ABI call.  A replayed CUDA graph
