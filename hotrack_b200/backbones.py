@@ -84,6 +84,13 @@ class PointNet2Msg_fast(nn.Module):
         _build_encoder(self, cfg["pointnet"][net_type], PointNetSetAbstractionMsg_fast, PointNetSetAbstraction_fast)
         _build_decoder(self, cfg["pointnet"][net_type], PointNetFeaturePropagation_fast)
         self.device = cfg["device"]
+        # Fused engine: the encoder and FP3's first layer keep two-plane (hi + lo fp16) rows.  FP3 batch-normalises a
+        # global feature broadcast over the points of a cloud -- nearly the same vector for every cloud -- so every
+        # rounding made before that normalisation comes out ~40x larger at the end of the network (measured:
+        # tools/dev/emul_prec.py); everything behind it is well conditioned and stays fp16.
+        for m in (self.sa1, self.sa2, self.sa3):
+            m.precise_layers = 99
+        self.fp3.precise_layers = 1
 
     def forward(self, input):
         B, C, N = input.shape

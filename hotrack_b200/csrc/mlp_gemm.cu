@@ -789,12 +789,14 @@ __global__ void __launch_bounds__(256) bn_bwd_coefs_kernel(int n, float inv_rows
 }
 
 __global__ void prep_weights_kernel(int n, int k_true, int kp, const float* __restrict__ w, act_t* __restrict__ wh,
-                                    bf16* __restrict__ wt) {
+                                    bf16* __restrict__ wt, act_t* __restrict__ wl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * kp) return;
     const int r = i / kp, c = i - r * kp;
     const float v = c < k_true ? w[(size_t)r * k_true + c] : 0.f;
-    wh[i] = f_to_h(v);
+    const act_t h = f_to_h(v);
+    wh[i] = h;
+    if (wl) wl[i] = f_to_h(v - h_to_f(h));  // lo plane of the two-plane (hi + lo) form
     if (wt) wt[(size_t)c * n + r] = __float2bfloat16(v);
 }
 
@@ -802,14 +804,17 @@ __global__ void prep_weights_kernel(int n, int k_true, int kp, const float* __re
 struct PrepDesc {
     const float* w;
     act_t* wh;
-    int n, k_true, kp, pad;
+    int n, k_true, kp, two;  // two != 0: the lo plane follows the hi plane (wh + n * kp)
 };
 __global__ void __launch_bounds__(256) prep_weights_multi_kernel(const PrepDesc* __restrict__ descs) {
     const PrepDesc d = descs[blockIdx.y];
     const int total = d.n * d.kp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int r = i / d.kp, c = i - r * d.kp;
-        d.wh[i] = f_to_h(c < d.k_true ? d.w[(size_t)r * d.k_true + c] : 0.f);
+        const float v = c < d.k_true ? d.w[(size_t)r * d.k_true + c] : 0.f;
+        const act_t h = f_to_h(v);
+        d.wh[i] = h;
+        if (d.two) d.wh[total + i] = f_to_h(v - h_to_f(h));
     }
 }
 
@@ -840,45 +845,64 @@ extern "C" int pn2_mlp_center(long long rows, int kdim, int n, const void* x, in
     return 0;
 }
 
-extern "C" int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
-                                const float* in_shift, const void* w, const float* center, void* y, int y_ld,
-                                float* stats, pn2_stream_t stream) {
-    if (int e = check_common("pn2_mlp_gemm_fwd", rows, kdim, n)) return e;
+static int gemm_fwd_impl(const char* who, long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                         const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                         const float* center, void* y, void* y_lo, int y_ld, float* stats, pn2_stream_t stream) {
+    if (int e = check_common(who, rows, kdim, n)) return e;
     if (rows == 0) return 0;
-    if (!x || !w || !y) return fail_arg("pn2_mlp_gemm_fwd", "null pointer");
-    if (x_ld % 8 || y_ld % 8 || x_ld < kdim || y_ld < n) return fail_arg("pn2_mlp_gemm_fwd", "bad leading dimension");
+    if (!x || !w || !y) return fail_arg(who, "null pointer");
+    if (x_ld % 8 || y_ld % 8 || x_ld < kdim || y_ld < n) return fail_arg(who, "bad leading dimension");
+    if ((x_lo != nullptr) != (w_lo != nullptr) || (y_lo && !x_lo)) return fail_arg(who, "two-plane operands come as x_lo AND w_lo");
     GemmArgs a{};
     a.rows = rows; a.kdim = kdim; a.n = n;
     a.a0 = (const uint16_t*)x; a.a0_ld = x_ld;
+    a.a1 = (const uint16_t*)x_lo; a.a1_ld = x_ld;
     a.c0 = in_scale; a.c1 = in_shift;
-    a.b = (const uint16_t*)w;
+    a.b = (const uint16_t*)w; a.b1 = (const uint16_t*)w_lo;
     a.center = center;
-    a.out = (uint16_t*)y; a.out_ld = y_ld;
+    a.out = (uint16_t*)y; a.out_ld = y_ld; a.out_lo = (uint16_t*)y_lo;
     a.sums = stats;
-    if (gemm_use_tc()) return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
+    if (gemm_use_tc() || x_lo) return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
     if (in_scale) return dispatch_bn<A_AFFINE, false>(a, (cudaStream_t)stream);
     return dispatch_bn<A_PLAIN, false>(a, (cudaStream_t)stream);
 }
 
-extern "C" int pn2_mlp_gemm_fwd_bn(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
-                                   const float* in_shift, const void* w, const float* center, void* y, int y_ld,
-                                   float* stats, unsigned int* counter, const float* gamma, const float* beta,
-                                   const float* conv_bias, const float* center_true, float momentum, float eps,
-                                   float* running_mean, float* running_var, long long* num_batches_tracked,
-                                   float* scale, float* shift, float* mean, float* rstd, float* next_center,
+extern "C" int pn2_mlp_gemm_fwd(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
+                                const float* in_shift, const void* w, const float* center, void* y, int y_ld,
+                                float* stats, pn2_stream_t stream) {
+    return gemm_fwd_impl("pn2_mlp_gemm_fwd", rows, kdim, n, x, nullptr, x_ld, in_scale, in_shift, w, nullptr, center, y,
+                         nullptr, y_ld, stats, stream);
+}
+
+extern "C" int pn2_mlp_gemm_fwd_x2(long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                                   const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                                   const float* center, void* y, void* y_lo, int y_ld, float* stats,
                                    pn2_stream_t stream) {
-    if (int e = check_common("pn2_mlp_gemm_fwd_bn", rows, kdim, n)) return e;
-    if (rows == 0) return fail_arg("pn2_mlp_gemm_fwd_bn", "BatchNorm statistics of zero rows");
+    return gemm_fwd_impl("pn2_mlp_gemm_fwd_x2", rows, kdim, n, x, x_lo, x_ld, in_scale, in_shift, w, w_lo, center, y, y_lo,
+                         y_ld, stats, stream);
+}
+
+static int gemm_fwd_bn_impl(const char* who, long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                            const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                            const float* center, void* y, void* y_lo, int y_ld, float* stats, unsigned int* counter,
+                            const float* gamma, const float* beta, const float* conv_bias, const float* center_true,
+                            float momentum, float eps, float* running_mean, float* running_var,
+                            long long* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
+                            float* next_center, pn2_stream_t stream) {
+    if (int e = check_common(who, rows, kdim, n)) return e;
+    if (rows == 0) return fail_arg(who, "BatchNorm statistics of zero rows");
     if (!x || !w || !y || !stats || !counter || !gamma || !beta || !scale || !shift || !mean || !rstd)
-        return fail_arg("pn2_mlp_gemm_fwd_bn", "null pointer");
-    if (x_ld % 8 || y_ld % 8 || x_ld < kdim || y_ld < n) return fail_arg("pn2_mlp_gemm_fwd_bn", "bad leading dimension");
+        return fail_arg(who, "null pointer");
+    if (x_ld % 8 || y_ld % 8 || x_ld < kdim || y_ld < n) return fail_arg(who, "bad leading dimension");
+    if ((x_lo != nullptr) != (w_lo != nullptr) || (y_lo && !x_lo)) return fail_arg(who, "two-plane operands come as x_lo AND w_lo");
     GemmArgs a{};
     a.rows = rows; a.kdim = kdim; a.n = n;
     a.a0 = (const uint16_t*)x; a.a0_ld = x_ld;
+    a.a1 = (const uint16_t*)x_lo; a.a1_ld = x_ld;
     a.c0 = in_scale; a.c1 = in_shift;
-    a.b = (const uint16_t*)w;
+    a.b = (const uint16_t*)w; a.b1 = (const uint16_t*)w_lo;
     a.center = center;
-    a.out = (uint16_t*)y; a.out_ld = y_ld;
+    a.out = (uint16_t*)y; a.out_ld = y_ld; a.out_lo = (uint16_t*)y_lo;
     a.sums = stats;
     a.fin_counter = counter; a.fin_gamma = gamma; a.fin_beta = beta; a.fin_bias = conv_bias; a.fin_center = center_true;
     a.fin_momentum = momentum; a.fin_eps = eps;
@@ -888,6 +912,31 @@ extern "C" int pn2_mlp_gemm_fwd_bn(long long rows, int kdim, int n, const void* 
     a.fin_scale = scale; a.fin_shift = shift; a.fin_mean = mean; a.fin_rstd = rstd;
     a.fin_next_center = next_center;
     return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
+}
+
+extern "C" int pn2_mlp_gemm_fwd_bn(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
+                                   const float* in_shift, const void* w, const float* center, void* y, int y_ld,
+                                   float* stats, unsigned int* counter, const float* gamma, const float* beta,
+                                   const float* conv_bias, const float* center_true, float momentum, float eps,
+                                   float* running_mean, float* running_var, long long* num_batches_tracked,
+                                   float* scale, float* shift, float* mean, float* rstd, float* next_center,
+                                   pn2_stream_t stream) {
+    return gemm_fwd_bn_impl("pn2_mlp_gemm_fwd_bn", rows, kdim, n, x, nullptr, x_ld, in_scale, in_shift, w, nullptr, center, y,
+                            nullptr, y_ld, stats, counter, gamma, beta, conv_bias, center_true, momentum, eps, running_mean,
+                            running_var, num_batches_tracked, scale, shift, mean, rstd, next_center, stream);
+}
+
+extern "C" int pn2_mlp_gemm_fwd_bn_x2(long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                                      const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                                      const float* center, void* y, void* y_lo, int y_ld, float* stats,
+                                      unsigned int* counter, const float* gamma, const float* beta,
+                                      const float* conv_bias, const float* center_true, float momentum, float eps,
+                                      float* running_mean, float* running_var, long long* num_batches_tracked,
+                                      float* scale, float* shift, float* mean, float* rstd, float* next_center,
+                                      pn2_stream_t stream) {
+    return gemm_fwd_bn_impl("pn2_mlp_gemm_fwd_bn_x2", rows, kdim, n, x, x_lo, x_ld, in_scale, in_shift, w, w_lo, center, y,
+                            y_lo, y_ld, stats, counter, gamma, beta, conv_bias, center_true, momentum, eps, running_mean,
+                            running_var, num_batches_tracked, scale, shift, mean, rstd, next_center, stream);
 }
 
 extern "C" int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const void* dz, int dz_ld, const void* y,
@@ -1007,7 +1056,18 @@ extern "C" int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, v
     if (!w || !w_f16) return fail_arg("pn2_mlp_prep_weights", "null pointer");
     const int total = n * kp;
     prep_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, k_true, kp, w, (act_t*)w_f16,
-                                                                               (bf16*)wt_bf16);
+                                                                               (bf16*)wt_bf16, nullptr);
+    PN2_CHECK_LAUNCH("prep_weights_kernel");
+    return 0;
+}
+
+extern "C" int pn2_mlp_prep_weights_x2(int n, int k_true, int kp, const float* w, void* w_hi, void* w_lo,
+                                       pn2_stream_t stream) {
+    if (n <= 0 || k_true <= 0 || kp < k_true) return fail_arg("pn2_mlp_prep_weights_x2", "bad size");
+    if (!w || !w_hi || !w_lo) return fail_arg("pn2_mlp_prep_weights_x2", "null pointer");
+    const int total = n * kp;
+    prep_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, k_true, kp, w, (act_t*)w_hi, nullptr,
+                                                                               (act_t*)w_lo);
     PN2_CHECK_LAUNCH("prep_weights_kernel");
     return 0;
 }

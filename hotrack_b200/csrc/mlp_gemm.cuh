@@ -19,6 +19,7 @@ struct GemmArgs {
     const float* yscale;             // BNBWD: device scalar, the factor that undoes W_B's scaling
     const float* center;  // [n] subtracted from the accumulators before 16-bit rounding (nullable)
     uint16_t* out; int out_ld;       // forward: y (fp16);  BNBWD: dz_prev (bf16)
+    uint16_t* out_lo;                // forward, two-plane operands (a1 = x_lo, b1 = w_lo): y's lo plane, ld = out_ld (nullable)
     float* sums;
     const uint16_t* yp; int yp_ld;   // MASK: previous layer's y (fp16)
     const float *p_scale, *p_shift, *p_mean, *p_rstd;

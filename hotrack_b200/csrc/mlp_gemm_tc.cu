@@ -44,6 +44,7 @@ constexpr int kProdWarps = 8;    // warps 9..16
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kTcThreads = (kEpiWarps + 1 + kProdWarps) * 32;
 constexpr int kMaxK = 1024;
+constexpr int kMaxKSplit = 256;  // AFFINE + SPLIT: layers > 0 of the SA stacks (kdim <= 128 on this network)
 constexpr int kSmemBudget = 225 * 1024;
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -56,20 +57,28 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-// stage = [A0 16 KB][A1 16 KB, BNBWD only][B BN*128 B]
-template <int BN, int AMODE>
+// stage = [A0 16 KB][A1 16 KB, BNBWD / SPLIT only][B BN*128 B][B1, BNBWD / SPLIT only]
+//
+// SPLIT (forward only): every operand is a pair of fp16 planes (hi, lo) with value = hi + lo -- 22 significand bits --
+// and the product is evaluated as A_hi*B_hi + A_lo*B_hi + A_hi*B_lo into the one fp32 accumulator (the lo*lo term is
+// below fp32 resolution); the output is written as such a pair too.  Used for the stacks in front of the backbone's
+// ill-conditioned spot (FP3 normalises a broadcast global feature: every rounding before it is amplified ~40x by the
+// end of the network), where fp16's 11 bits are not enough for the 1e-2 parity bar.
+template <int BN, int AMODE, bool SPLIT = false>
 struct TcCfg {
     static constexpr int kABytes = TM * 128;
-    static constexpr int kNA = AMODE == A_BNBWD ? 2 : 1;
+    static constexpr bool kTwo = AMODE == A_BNBWD || SPLIT;
+    static constexpr int kNA = kTwo ? 2 : 1;
     static constexpr int kNB = kNA;                            // BNBWD: dZ x W_A and Y x W_B accumulate into one tile
     static constexpr int kBBytes = BN * 128;
     static constexpr int kStage = kABytes * kNA + kBBytes * kNB;
-    static constexpr int kEpiMax = AMODE == A_BNBWD ? 64 : 128;  // backward stages are twice as large: smaller staging tile
+    static constexpr int kEpiMax = SPLIT ? 32 : (AMODE == A_BNBWD ? 64 : 128);  // two-operand stages are twice as large: smaller staging tile
     static constexpr int kEpiBN = BN < kEpiMax ? BN : kEpiMax;  // columns per epilogue pass
     static constexpr int kCLD = kEpiBN + 8;                    // 16-bit elements per sC row
-    static constexpr int kSC = TM * kCLD * 2;
+    static constexpr int kSC = TM * kCLD * 2 * (SPLIT ? 2 : 1);  // SPLIT: hi tile + lo tile
     static constexpr int kNCoef = AMODE == A_AFFINE ? 2 : 0;
-    static constexpr int kFixed = kSC + kNCoef * kMaxK * 4 + 5 * BN * 4 + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int kCoefK = SPLIT ? kMaxKSplit : kMaxK;
+    static constexpr int kFixed = kSC + kNCoef * kCoefK * 4 + 5 * BN * 4 + 256 + 1024;  // + barriers + alignment slack
     static constexpr int kNstRaw = (kSmemBudget - kFixed) / kStage;
     static constexpr int kNst = kNstRaw > 6 ? 6 : kNstRaw;
     // chunks in flight per producer thread.  NST - 2, not NST - 1: refilling a slot waits for the MMAs of the chunk that
@@ -79,9 +88,11 @@ struct TcCfg {
     static_assert(kNst >= 3, "not enough shared memory for a three-stage ring");
 };
 
-template <int BN, int AMODE, bool MASK>
+template <int BN, int AMODE, bool MASK, bool SPLIT = false>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p) {
-    using Cfg = TcCfg<BN, AMODE>;
+    using Cfg = TcCfg<BN, AMODE, SPLIT>;
+    static_assert(!SPLIT || (AMODE != A_BNBWD && !MASK), "SPLIT is a forward mode");
+    constexpr bool TWO = Cfg::kTwo;
     constexpr int NST = Cfg::kNst, D = Cfg::kDist;
     constexpr int EBN = Cfg::kEpiBN, CLD = Cfg::kCLD, NH = BN / EBN;
     constexpr int CPR = EBN / 8;          // 16-byte pieces per sC row
@@ -181,12 +192,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                 const long long row0 = i_tile * TM + pr;
                 const int rows_left = (int)min((long long)TM, p.rows - i_tile * TM) - pr;  // rows pr + 32*i < rows_left are real
                 const uint16_t* a0p = p.a0 + row0 * p.a0_ld + kcol;
-                const uint16_t* a1p = AMODE == A_BNBWD ? p.a1 + row0 * p.a1_ld + kcol : nullptr;
+                const uint16_t* a1p = TWO ? p.a1 + row0 * p.a1_ld + kcol : nullptr;
 #pragma unroll
                 for (int i = 0; i < TM / 32; ++i) {
                     const bool ok = kok && 32 * i < rows_left;
                     cp_async16_s(st + poff + i * 4096, ok ? a0p + (size_t)i * a0_step : p.a0, ok ? 16 : 0);
-                    if (AMODE == A_BNBWD)
+                    if (TWO)
                         cp_async16_s(st + Cfg::kABytes + poff + i * 4096, ok ? a1p + (size_t)i * a1_step : p.a1, ok ? 16 : 0);
                 }
                 const uint32_t sb = st + Cfg::kABytes * Cfg::kNA;
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                 for (int i = 0; i < BN / 32; ++i) {
                     const bool ok = kok && 32 * i < n_left;
                     cp_async16_s(sb + poff + i * 4096, ok ? bp + (size_t)i * b_step : p.b, ok ? 16 : 0);
-                    if (AMODE == A_BNBWD)
+                    if (TWO)
                         cp_async16_s(sb + Cfg::kBBytes + poff + i * 4096, ok ? p.b1 + (bp - p.b) + (size_t)i * b_step : p.b1,
                                      ok ? 16 : 0);
                 }
@@ -223,6 +234,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                         const uint32_t* x0 = reinterpret_cast<const uint32_t*>(&q0);
                         uint4 v;
                         uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+                        if (SPLIT) {  // value = hi + lo; the activation is split again after BatchNorm + ReLU
+                            uint4* slot1 = reinterpret_cast<uint4*>(st + Cfg::kABytes + i * 4096);
+                            const uint4 q1 = *slot1;
+                            const uint32_t* x1 = reinterpret_cast<const uint32_t*>(&q1);
+                            uint4 vl;
+                            uint32_t* ol = reinterpret_cast<uint32_t*>(&vl);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 a = h2_to_f2(x0[e]), l = h2_to_f2(x1[e]);
+                                const float r0 = fmaxf(fmaf(a.x + l.x, k0[2 * e], k1[2 * e]), 0.f);
+                                const float r1 = fmaxf(fmaf(a.y + l.y, k0[2 * e + 1], k1[2 * e + 1]), 0.f);
+                                o[e] = f2_to_h2(r0, r1);
+                                const float2 back = h2_to_f2(o[e]);
+                                ol[e] = f2_to_h2(r0 - back.x, r1 - back.y);
+                            }
+                            *slot = v;
+                            *slot1 = vl;
+                            continue;
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float2 a = h2_to_f2(x0[e]);
@@ -266,6 +296,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                         if (AMODE == A_BNBWD)
                             umma_f16(tmem_base + as * ACC, umma_desc_k128(sa + Cfg::kABytes) + 2 * k4,
                                      umma_desc_k128(sa + Cfg::kABytes * 2 + Cfg::kBBytes) + 2 * k4, idesc1, 1u);
+                        if (SPLIT) {  // + A_lo x B_hi + A_hi x B_lo
+                            umma_f16(tmem_base + as * ACC, umma_desc_k128(sa + Cfg::kABytes) + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+                            umma_f16(tmem_base + as * ACC, adesc + 2 * k4,
+                                     umma_desc_k128(sa + Cfg::kABytes * 2 + Cfg::kBBytes) + 2 * k4, idesc, 1u);
+                        }
                     }
                     tc_commit(&empty[slot]);               // arrives when the MMAs above have finished reading the stage
                     if (kc == KT - 1) tc_commit(&tfull[as]);
@@ -346,6 +381,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                             q.w = FWD ? f2_to_h2(__uint_as_float(v[g8 * 8 + 6]) - ce1.z, __uint_as_float(v[g8 * 8 + 7]) - ce1.w)
                                       : f2_to_bf2(__uint_as_float(v[g8 * 8 + 6]) - ce1.z, __uint_as_float(v[g8 * 8 + 7]) - ce1.w);
                             *reinterpret_cast<uint4*>(&sC[r * CLD + cb + g8 * 8]) = q;
+                            if (SPLIT) {  // lo plane: what the fp16 rounding of the hi plane left over
+                                const float ce[8] = {ce0.x, ce0.y, ce0.z, ce0.w, ce1.x, ce1.y, ce1.z, ce1.w};
+                                const uint32_t* qh = reinterpret_cast<const uint32_t*>(&q);
+                                uint4 ql;
+                                uint32_t* qlw = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 back = h2_to_f2(qh[e]);
+                                    qlw[e] = f2_to_h2(__uint_as_float(v[g8 * 8 + 2 * e]) - ce[2 * e] - back.x,
+                                                      __uint_as_float(v[g8 * 8 + 2 * e + 1]) - ce[2 * e + 1] - back.y);
+                                }
+                                *reinterpret_cast<uint4*>(&sC[TM * CLD + r * CLD + cb + g8 * 8]) = ql;
+                            }
                         }
                     }
                 }
@@ -387,6 +435,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                                     s2[h][2 * e + 1] = fmaf(d.y, y.y, s2[h][2 * e + 1]);
                                     vv[e] = f2_to_bf2(d.x, d.y);
                                 }
+                            } else if (SPLIT) {
+                                const uint4 vl = *reinterpret_cast<const uint4*>(&sC[TM * CLD + r * CLD + chunk * 8]);
+                                const uint32_t* vlw = reinterpret_cast<const uint32_t*>(&vl);
+                                if (p.sums) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        float2 d = h2_to_f2(vv[e]);
+                                        const float2 l = h2_to_f2(vlw[e]);
+                                        d.x += l.x; d.y += l.y;
+                                        s1[h][2 * e] += d.x; s1[h][2 * e + 1] += d.y;
+                                        s2[h][2 * e] = fmaf(d.x, d.x, s2[h][2 * e]);
+                                        s2[h][2 * e + 1] = fmaf(d.y, d.y, s2[h][2 * e + 1]);
+                                    }
+                                }
+                                if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + grow * p.out_ld + col0) = vl;
                             } else if (p.sums) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
@@ -480,14 +543,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     }
 }
 
-template <int BN, int AMODE, bool MASK>
+template <int BN, int AMODE, bool MASK, bool SPLIT = false>
 int launch_tc(const GemmArgs& a, cudaStream_t stream) {
-    using Cfg = TcCfg<BN, AMODE>;
+    using Cfg = TcCfg<BN, AMODE, SPLIT>;
     const int kpad = (a.kdim + TK - 1) / TK * TK;
     const size_t smem = (size_t)Cfg::kNst * Cfg::kStage + Cfg::kSC + (size_t)Cfg::kNCoef * kpad * 4 + 5 * BN * 4 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        PN2_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PN2_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, MASK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemBudget),
                   "gemm_tc: cudaFuncSetAttribute");
         configured = true;
@@ -503,7 +566,7 @@ int launch_tc(const GemmArgs& a, cudaStream_t stream) {
     long long gx = sms / ny;  // persistent: one CTA per SM (shared memory, TMEM), tiles dealt round-robin
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
-    gemm_tc_kernel<BN, AMODE, MASK><<<dim3((unsigned)gx, ny), kTcThreads, smem, stream>>>(a);
+    gemm_tc_kernel<BN, AMODE, MASK, SPLIT><<<dim3((unsigned)gx, ny), kTcThreads, smem, stream>>>(a);
     PN2_CHECK_LAUNCH("gemm_tc_kernel");
     return 0;
 }
@@ -531,6 +594,16 @@ int dispatch_tc(const GemmArgs& a, cudaStream_t stream) {
     }
 }
 
+// SPLIT: column tiles of at most 128 (the two-plane stage of a 256-wide tile would leave no room for a 3-stage ring)
+template <int AMODE>
+int dispatch_tc_split(const GemmArgs& a, cudaStream_t stream) {
+    switch (pick_bn(a.n, false)) {
+        case 128: return launch_tc<128, AMODE, false, true>(a, stream);
+        case 64: return launch_tc<64, AMODE, false, true>(a, stream);
+        default: return launch_tc<32, AMODE, false, true>(a, stream);
+    }
+}
+
 }  // namespace
 
 bool gemm_use_tc() {
@@ -544,6 +617,11 @@ bool gemm_use_tc() {
 
 int launch_gemm_tc(const GemmArgs& a, int amode, bool mask, cudaStream_t stream) {
     if (a.kdim > kMaxK) return fail_arg("pn2_mlp_gemm", "reduction dimension > 1024");
+    if (a.a1 && amode != A_BNBWD) {  // two-plane (hi + lo) forward operands
+        if (!a.b1) return fail_arg("pn2_mlp_gemm", "two-plane input rows need two-plane weights");
+        if (amode == A_AFFINE && a.kdim > kMaxKSplit) return fail_arg("pn2_mlp_gemm", "two-plane BatchNorm'd input: reduction dimension > 256");
+        return amode == A_AFFINE ? dispatch_tc_split<A_AFFINE>(a, stream) : dispatch_tc_split<A_PLAIN>(a, stream);
+    }
     if (amode == A_PLAIN) return dispatch_tc<A_PLAIN, false>(a, stream);
     if (amode == A_AFFINE) return dispatch_tc<A_AFFINE, false>(a, stream);
     if (mask) return dispatch_tc<A_BNBWD, true>(a, stream);

@@ -34,7 +34,7 @@ constexpr int kThreads = 256;
 // ------------------------------------------------------------------ to_rows -----------------
 __global__ void __launch_bounds__(256) to_rows_kernel(int c, int n, int ld, const float* __restrict__ src,
                                                        const float* __restrict__ sub_sums, float sub_scale,
-                                                       act_t* __restrict__ dst) {
+                                                       act_t* __restrict__ dst, act_t* __restrict__ dst_lo) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -48,18 +48,25 @@ __global__ void __launch_bounds__(256) to_rows_kernel(int c, int n, int ld, cons
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int nn = n0 + j, cc = c0 + tx;
-        if (nn < n && cc < ld) dst[((size_t)b * n + nn) * ld + cc] = f_to_h(tile[tx][j]);
+        if (nn < n && cc < ld) {
+            const float v = tile[tx][j];
+            const act_t h = f_to_h(v);
+            dst[((size_t)b * n + nn) * ld + cc] = h;
+            if (dst_lo) dst_lo[((size_t)b * n + nn) * ld + cc] = f_to_h(v - h_to_f(h));  // two-plane rows: value = hi + lo
+        }
     }
 }
 
 // ------------------------------------------------------------------ sa_build_rows -----------
 struct RowSrc {  // fp16 rows with an optional per-channel affine + ReLU ("still pre-BatchNorm")
     const act_t* p;
+    const act_t* lo;  // nullable: second plane of two-plane rows (value = p + lo), same leading dimension
     int c, ld;
     const float *scale, *shift;
 };
 __device__ __forceinline__ float row_val(const RowSrc& s, size_t row, int ch) {
     float v = h_to_f(s.p[row * s.ld + ch]);
+    if (s.lo) v += h_to_f(s.lo[row * s.ld + ch]);
     if (s.scale) v = fmaxf(fmaf(v, __ldg(s.scale + ch), __ldg(s.shift + ch)), 0.f);
     return v;
 }
@@ -71,6 +78,7 @@ struct SaBuildArgs {
     RowSrc feat, cen;
     int xyz_first;
     act_t* out;
+    act_t* out_lo;  // nullable: lo plane of the output rows
     int out_ld;
 };
 
@@ -83,6 +91,15 @@ __device__ __forceinline__ void row_vals8(const RowSrc& s, size_t row, int ch, f
     for (int e = 0; e < 4; ++e) {
         const float2 f = h2_to_f2(w[e]);
         v[2 * e] = f.x; v[2 * e + 1] = f.y;
+    }
+    if (s.lo) {
+        const uint4 ql = __ldg(reinterpret_cast<const uint4*>(s.lo + row * s.ld + ch));
+        const uint32_t* wl = reinterpret_cast<const uint32_t*>(&ql);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = h2_to_f2(wl[e]);
+            v[2 * e] += f.x; v[2 * e + 1] += f.y;
+        }
     }
     if (s.scale) {
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(s.scale + ch)), s1 = __ldg(reinterpret_cast<const float4*>(s.scale + ch + 4));
@@ -103,6 +120,7 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
     // the K rows of a group: when the 8 rows of a CTA share their group the BatchNorm+ReLU'd centre row is staged ONCE,
     // at its OUTPUT columns, and every row copies aligned 16-byte pieces of it
     __shared__ __align__(16) act_t s_cen[1024 + 8];
+    __shared__ __align__(16) act_t s_cen_lo[1024 + 8];
     const int lane = threadIdx.x & 31;
     const int gpr = a.out_ld >> 3;
     const int rpw = gpr >= 32 ? 1 : 32 / gpr;
@@ -115,8 +133,12 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
     const bool staged = cc > 0 && rpw == 1 && (a.k & 7) == 0 && a.out_ld <= 1024;
     if (staged) {
         const long long grp = ((long long)blockIdx.x * (kThreads / 32)) / a.k;  // b * s + s_idx of all 8 rows
-        for (int col = (c0 & ~7) + threadIdx.x; col < a.out_ld; col += kThreads)
-            s_cen[col] = f_to_h((col >= c0 && col < c0 + cc) ? row_val(a.cen, (size_t)grp, col - c0) : 0.f);
+        for (int col = (c0 & ~7) + threadIdx.x; col < a.out_ld; col += kThreads) {
+            const float v = (col >= c0 && col < c0 + cc) ? row_val(a.cen, (size_t)grp, col - c0) : 0.f;
+            const act_t h = f_to_h(v);
+            s_cen[col] = h;
+            s_cen_lo[col] = f_to_h(v - h_to_f(h));
+        }
         __syncthreads();
     }
     if (row >= total || sub >= rpw) return;
@@ -129,10 +151,12 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
     float rel[3] = {0.f, 0.f, 0.f};
     bool have_rel = false;
     act_t* o = a.out + (size_t)row * a.out_ld;
+    act_t* ol = a.out_lo ? a.out_lo + (size_t)row * a.out_ld : nullptr;
     for (int g = gpr >= 32 ? lane : lane - sub * gpr; g < gpr; g += 32) {
         const int col = g << 3;
         if (staged && col >= c0 && col + 8 <= c0 + cc) {  // a piece of centre features only
             *reinterpret_cast<uint4*>(o + col) = *reinterpret_cast<const uint4*>(&s_cen[col]);
+            if (ol) *reinterpret_cast<uint4*>(ol + col) = *reinterpret_cast<const uint4*>(&s_cen_lo[col]);
             continue;
         }
         float v[8];
@@ -153,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
                 float t = 0.f;
                 if (c >= f0 && c < f0 + fc) t = row_val(a.feat, frow, c - f0);
                 else if (c >= x0 && c < x0 + 3) t = rel[c - x0];
-                else if (c >= c0 && c < c0 + cc) t = staged ? h_to_f(s_cen[c]) : row_val(a.cen, crow, c - c0);
+                else if (c >= c0 && c < c0 + cc) t = staged ? h_to_f(s_cen[c]) + h_to_f(s_cen_lo[c]) : row_val(a.cen, crow, c - c0);
                 v[e] = t;
             }
         }
@@ -165,6 +189,16 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
             qq[e] = f2_to_h2(lo, hi);
         }
         *reinterpret_cast<uint4*>(o + col) = q;
+        if (ol) {
+            uint4 ql;
+            uint32_t* qlw = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 back = h2_to_f2(qq[e]);
+                qlw[e] = f2_to_h2(v[2 * e] - back.x, v[2 * e + 1] - back.y);
+            }
+            *reinterpret_cast<uint4*>(ol + col) = ql;
+        }
     }
 }
 
@@ -175,6 +209,7 @@ struct FpBuildArgs {
     const int* idx;       // (B,N,3)
     const float* dist2;   // (B,N,3) squared distances from three_nn
     act_t* out;
+    act_t* out_lo;        // nullable: lo plane of the output rows
     int out_ld;
 };
 // weights of reference pointnet_utils.py:446-449: w_j = (1/(sqrt(d2_j)+1e-8)) / sum_j(...), in fp32
@@ -217,7 +252,9 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
                 v = row_val(a.coarse, (size_t)b, ch);
             }
         }
-        o[col] = f_to_h(v);
+        const act_t h = f_to_h(v);
+        o[col] = h;
+        if (a.out_lo) a.out_lo[(size_t)row * a.out_ld + col] = f_to_h(v - h_to_f(h));
     }
 }
 
@@ -225,6 +262,7 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
 struct PoolArgs {
     int b, s, k, c;
     const act_t* y; int y_ld;
+    const act_t* y_lo;    // forward, nullable: lo plane of two-plane rows (value = y + y_lo)
     const float *scale, *shift, *mean, *rstd;
     float* out_cm;        // (B,C,S)
     float* chan_sums;     // [C] += sum over (b,s) of the output (nullable)
@@ -260,9 +298,14 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
             int i0 = 0, i1 = 0;
             if (ok && s < a.s) {
                 const act_t* yr = a.y + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch;
+                const act_t* yl = a.y_lo ? a.y_lo + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch : nullptr;
 #pragma unroll 4
                 for (int kk = 0; kk < a.k; ++kk) {
-                    const float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
+                    float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
+                    if (yl) {
+                        const float2 l = h2_to_f2(*reinterpret_cast<const uint32_t*>(yl + (size_t)kk * a.y_ld));
+                        v.x += l.x; v.y += l.y;
+                    }
                     const float r0 = fmaxf(fmaf(v.x, sc0, sh0), 0.f), r1 = fmaxf(fmaf(v.y, sc1, sh1), 0.f);
                     if (r0 > m0) { m0 = r0; i0 = kk; }
                     if (r1 > m1) { m1 = r1; i1 = kk; }
@@ -382,13 +425,19 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_grp_kernel(const PoolArgs a
             for (int e = 0; e < 8; ++e) { m[e] = -1.f; mi[e] = 0; }  // below every ReLU output: the first row always wins
             if (on) {
                 const act_t* yr = a.y + ((size_t)g * a.k) * a.y_ld + ch;
+                const act_t* yl = a.y_lo ? a.y_lo + ((size_t)g * a.k) * a.y_ld + ch : nullptr;
 #pragma unroll 4
                 for (int kk = warp; kk < a.k; kk += 8) {
                     const uint4 q = __ldg(reinterpret_cast<const uint4*>(yr + (size_t)kk * a.y_ld));
+                    uint4 ql = make_uint4(0u, 0u, 0u, 0u);  // fp16 zeros
+                    if (yl) ql = __ldg(reinterpret_cast<const uint4*>(yl + (size_t)kk * a.y_ld));
                     const uint32_t* w = reinterpret_cast<const uint32_t*>(&q);
+                    const uint32_t* wl = reinterpret_cast<const uint32_t*>(&ql);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float2 f = h2_to_f2(w[e]);
+                        float2 f = h2_to_f2(w[e]);
+                        const float2 fl = h2_to_f2(wl[e]);
+                        f.x += fl.x; f.y += fl.y;
                         const float r0 = fmaxf(fmaf(f.x, sc[2 * e], sh[2 * e]), 0.f);
                         const float r1 = fmaxf(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]), 0.f);
                         if (r0 > m[2 * e]) { m[2 * e] = r0; mi[2 * e] = kk; }
@@ -492,10 +541,15 @@ __global__ void __launch_bounds__(kThreads) rows_to_cm_kernel(const PoolArgs a) 
         for (int r = r0; r < kRowTile; r += rstep) {
             if (s0 + r < a.s) {
                 const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.y + ((size_t)b * a.s + s0 + r) * a.y_ld + pc * 8));
+                uint4 ql = make_uint4(0u, 0u, 0u, 0u);
+                if (a.y_lo) ql = __ldg(reinterpret_cast<const uint4*>(a.y_lo + ((size_t)b * a.s + s0 + r) * a.y_ld + pc * 8));
                 const uint32_t* v = reinterpret_cast<const uint32_t*>(&q);
+                const uint32_t* vl = reinterpret_cast<const uint32_t*>(&ql);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float2 f = h2_to_f2(v[e]);
+                    float2 f = h2_to_f2(v[e]);
+                    const float2 fl = h2_to_f2(vl[e]);
+                    f.x += fl.x; f.y += fl.y;
                     tile_dyn[r * ldt + (2 * e) * pieces + pc] = fmaxf(fmaf(f.x, sc[2 * e], sh[2 * e]), 0.f);
                     tile_dyn[r * ldt + (2 * e + 1) * pieces + pc] = fmaxf(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]), 0.f);
                 }
@@ -739,9 +793,9 @@ unsigned k1_grid(long long tiles, size_t smem_bytes, int reg_cap) {
     return (unsigned)(tiles < slots ? tiles : slots);
 }
 
-RowSrc mk_src(const void* p, int c, int ld, const float* scale, const float* shift) {
+RowSrc mk_src(const void* p, const void* lo, int c, int ld, const float* scale, const float* shift) {
     RowSrc s;
-    s.p = (const act_t*)p; s.c = c; s.ld = ld; s.scale = scale; s.shift = shift;
+    s.p = (const act_t*)p; s.lo = (const act_t*)lo; s.c = c; s.ld = ld; s.scale = scale; s.shift = shift;
     return s;
 }
 unsigned warp_blocks(long long rows) { return (unsigned)((rows + (kThreads / 32) - 1) / (kThreads / 32)); }
@@ -751,16 +805,21 @@ unsigned warp_blocks(long long rows) { return (unsigned)((rows + (kThreads / 32)
 
 using namespace pn2;
 
-extern "C" int pn2_to_rows(int b, int c, int n, const float* src, const float* sub_sums, float sub_scale, void* dst,
-                           int ld, pn2_stream_t stream) {
+extern "C" int pn2_to_rows_x2(int b, int c, int n, const float* src, const float* sub_sums, float sub_scale, void* dst,
+                              void* dst_lo, int ld, pn2_stream_t stream) {
     if (b < 0 || c < 0 || n < 0 || ld < c) return fail_arg("pn2_to_rows", "bad size");
     if (b == 0 || n == 0 || ld == 0) return 0;
     if (!src || !dst) return fail_arg("pn2_to_rows", "null pointer");
     if (b > 65535) return fail_arg("pn2_to_rows", "b > 65535");
     dim3 grid((n + 31) / 32, (ld + 31) / 32, b);
-    to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, ld, src, sub_sums, sub_scale, (act_t*)dst);
+    to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, ld, src, sub_sums, sub_scale, (act_t*)dst, (act_t*)dst_lo);
     PN2_CHECK_LAUNCH("to_rows_kernel");
     return 0;
+}
+
+extern "C" int pn2_to_rows(int b, int c, int n, const float* src, const float* sub_sums, float sub_scale, void* dst,
+                           int ld, pn2_stream_t stream) {
+    return pn2_to_rows_x2(b, c, n, src, sub_sums, sub_scale, dst, nullptr, ld, stream);
 }
 
 extern "C" int pn2_sa_build_rows(int b, int n, int s, int k, const float* xyz, const float* new_xyz, const int* idx,
@@ -768,6 +827,16 @@ extern "C" int pn2_sa_build_rows(int b, int n, int s, int k, const float* xyz, c
                                  const float* feat_shift, const void* cen, int cen_c, int cen_ld,
                                  const float* cen_scale, const float* cen_shift, int xyz_first, void* out, int out_ld,
                                  pn2_stream_t stream) {
+    return pn2_sa_build_rows_x2(b, n, s, k, xyz, new_xyz, idx, feat, nullptr, feat_c, feat_ld, feat_scale, feat_shift, cen,
+                                nullptr, cen_c, cen_ld, cen_scale, cen_shift, xyz_first, out, nullptr, out_ld, stream);
+}
+
+extern "C" int pn2_sa_build_rows_x2(int b, int n, int s, int k, const float* xyz, const float* new_xyz, const int* idx,
+                                    const void* feat, const void* feat_lo, int feat_c, int feat_ld,
+                                    const float* feat_scale, const float* feat_shift, const void* cen,
+                                    const void* cen_lo, int cen_c, int cen_ld, const float* cen_scale,
+                                    const float* cen_shift, int xyz_first, void* out, void* out_lo, int out_ld,
+                                    pn2_stream_t stream) {
     if (b < 0 || n <= 0 || s <= 0 || k <= 0) return fail_arg("pn2_sa_build_rows", "bad size");
     if (b == 0) return 0;
     if (!xyz || !out) return fail_arg("pn2_sa_build_rows", "null pointer");
@@ -777,9 +846,9 @@ extern "C" int pn2_sa_build_rows(int b, int n, int s, int k, const float* xyz, c
     if (!idx && k != n) return fail_arg("pn2_sa_build_rows", "identity grouping needs k == n");
     SaBuildArgs a;
     a.b = b; a.n = n; a.s = s; a.k = k; a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx;
-    a.feat = mk_src(feat, feat_c, feat_ld, feat_scale, feat_shift);
-    a.cen = mk_src(cen, cen_c, cen_ld, cen_scale, cen_shift);
-    a.xyz_first = xyz_first; a.out = (act_t*)out; a.out_ld = out_ld;
+    a.feat = mk_src(feat, feat_lo, feat_c, feat_ld, feat_scale, feat_shift);
+    a.cen = mk_src(cen, cen_lo, cen_c, cen_ld, cen_scale, cen_shift);
+    a.xyz_first = xyz_first; a.out = (act_t*)out; a.out_lo = (act_t*)out_lo; a.out_ld = out_ld;
     const int gpr = out_ld >> 3, rpw = gpr >= 32 ? 1 : 32 / gpr;
     sa_build_rows_kernel<<<warp_blocks(((long long)b * s * k + rpw - 1) / rpw), kThreads, 0, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("sa_build_rows_kernel");
@@ -790,15 +859,24 @@ extern "C" int pn2_fp_build_rows(int b, int n, int s, const void* skip, int skip
                                  const float* skip_scale, const float* skip_shift, const void* coarse, int coarse_c,
                                  int coarse_ld, const float* coarse_scale, const float* coarse_shift, const int* idx,
                                  const float* dist2, void* out, int out_ld, pn2_stream_t stream) {
+    return pn2_fp_build_rows_x2(b, n, s, skip, nullptr, skip_c, skip_ld, skip_scale, skip_shift, coarse, nullptr, coarse_c,
+                                coarse_ld, coarse_scale, coarse_shift, idx, dist2, out, nullptr, out_ld, stream);
+}
+
+extern "C" int pn2_fp_build_rows_x2(int b, int n, int s, const void* skip, const void* skip_lo, int skip_c, int skip_ld,
+                                    const float* skip_scale, const float* skip_shift, const void* coarse,
+                                    const void* coarse_lo, int coarse_c, int coarse_ld, const float* coarse_scale,
+                                    const float* coarse_shift, const int* idx, const float* dist2, void* out,
+                                    void* out_lo, int out_ld, pn2_stream_t stream) {
     if (b < 0 || n <= 0 || s <= 0) return fail_arg("pn2_fp_build_rows", "bad size");
     if (b == 0) return 0;
     if (!coarse || !out || (s > 1 && (!idx || !dist2))) return fail_arg("pn2_fp_build_rows", "null pointer");
     if (out_ld < (skip ? skip_c : 0) + coarse_c || out_ld % 8) return fail_arg("pn2_fp_build_rows", "bad out_ld");
     FpBuildArgs a;
     a.b = b; a.n = n; a.s = s;
-    a.skip = mk_src(skip, skip_c, skip_ld, skip_scale, skip_shift);
-    a.coarse = mk_src(coarse, coarse_c, coarse_ld, coarse_scale, coarse_shift);
-    a.idx = idx; a.dist2 = dist2; a.out = (act_t*)out; a.out_ld = out_ld;
+    a.skip = mk_src(skip, skip_lo, skip_c, skip_ld, skip_scale, skip_shift);
+    a.coarse = mk_src(coarse, coarse_lo, coarse_c, coarse_ld, coarse_scale, coarse_shift);
+    a.idx = idx; a.dist2 = dist2; a.out = (act_t*)out; a.out_lo = (act_t*)out_lo; a.out_ld = out_ld;
     fp_build_rows_kernel<<<warp_blocks((long long)b * n), kThreads, 0, (cudaStream_t)stream>>>(a);
     PN2_CHECK_LAUNCH("fp_build_rows_kernel");
     return 0;
@@ -806,12 +884,18 @@ extern "C" int pn2_fp_build_rows(int b, int n, int s, const void* skip, int skip
 
 extern "C" int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld, const float* scale,
                             const float* shift, float* out_cm, float* chan_sums, int* argmax, pn2_stream_t stream) {
+    return pn2_pool_fwd_x2(b, s, k, c, y, nullptr, y_ld, scale, shift, out_cm, chan_sums, argmax, stream);
+}
+
+extern "C" int pn2_pool_fwd_x2(int b, int s, int k, int c, const void* y, const void* y_lo, int y_ld, const float* scale,
+                               const float* shift, float* out_cm, float* chan_sums, int* argmax, pn2_stream_t stream) {
     if (b < 0 || s <= 0 || k <= 0 || c <= 0 || c % 8) return fail_arg("pn2_pool_fwd", "bad size");
     if (b == 0) return 0;
     if (b > 65535) return fail_arg("pn2_pool_fwd", "b > 65535");
     if (!y || !scale || !shift || !out_cm) return fail_arg("pn2_pool_fwd", "null pointer");
     PoolArgs a{};
-    a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
+    a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_lo = (const act_t*)y_lo; a.y_ld = y_ld;
+    a.scale = scale; a.shift = shift;
     a.out_cm = out_cm; a.chan_sums = chan_sums; a.argmax = argmax;
     dim3 grid;
     if (k == 1 && !chan_sums && c <= 1024) {

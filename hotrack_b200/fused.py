@@ -74,7 +74,7 @@ class WeightPlan:
     the copies (the optimiser is about to change the weights).  Owned by TrainStep."""
 
     def __init__(self):
-        self.entries = {}      # (data_ptr, kp) -> (weight view, fp16 buffer)
+        self.entries = {}      # (data_ptr, kp, two) -> (weight view, fp16 buffer [1 or 2 planes][cout][kp])
         self.table = None      # device array of PrepDesc records, rebuilt when an entry is added
         self.ready = False
 
@@ -84,21 +84,22 @@ class WeightPlan:
             return
         if self.table is None:
             import struct
-            raw = b"".join(struct.pack("<QQiiii", w.data_ptr(), buf.data_ptr(), w.shape[0], w.shape[1], kp, 0)
-                           for (_, kp), (w, buf) in self.entries.items())
+            raw = b"".join(struct.pack("<QQiiii", w.data_ptr(), buf.data_ptr(), w.shape[0], w.shape[1], kp, 1 if two else 0)
+                           for (_, kp, two), (w, buf) in self.entries.items())
             dev = next(iter(self.entries.values()))[0].device
             self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         _lib.call("pn2_mlp_prep_weights_multi", len(self.entries), self.table.data_ptr(), _stream())
         self.ready = True
 
-    def lookup(self, w, kp):
-        """fp16 [cout][kp] copy of ``w`` for this step (converted now if it was not planned)."""
-        key = (w.data_ptr(), kp)
+    def lookup(self, w, kp, two=False):
+        """fp16 [planes][cout][kp] copy of ``w`` for this step (converted now if it was not planned); planes = 2
+        (hi, lo) when ``two``."""
+        key = (w.data_ptr(), kp, bool(two))
         e = self.entries.get(key)
         if e is not None and self.ready:
             return e[1]
-        buf = e[1] if e is not None else torch.empty(w.shape[0], kp, dtype=_F16, device=w.device)
-        _lib.call("pn2_mlp_prep_weights", w.shape[0], w.shape[1], kp, w.data_ptr(), buf.data_ptr(), 0, _stream())
+        buf = e[1] if e is not None else _prep_weight(w, kp, two, convert=False)
+        _prep_weight(w, kp, two, buf=buf)
         if e is None:
             # a detached alias: holding the autograd-tracked view would keep the parameter's grad accumulator of
             # THAT step alive (with the stream it was created on), which a later CUDA-graph capture trips over
@@ -110,7 +111,32 @@ class WeightPlan:
         self.ready = False
 
 
+def _prep_weight(w, kp, two, buf=None, convert=True):
+    if buf is None:
+        buf = torch.empty(2 if two else 1, w.shape[0], kp, dtype=_F16, device=w.device)
+    if convert:
+        if two:
+            _lib.call("pn2_mlp_prep_weights_x2", w.shape[0], w.shape[1], kp, w.data_ptr(), buf[0].data_ptr(),
+                      buf[1].data_ptr(), _stream())
+        else:
+            _lib.call("pn2_mlp_prep_weights", w.shape[0], w.shape[1], kp, w.data_ptr(), buf.data_ptr(), 0, _stream())
+    return buf
+
+
 ACTIVE_PLAN = None  # set by TrainStep around its forward pass
+
+# Two-plane ("x2") forward precision.  A stack run with precise=L keeps its first L layers' operands and outputs as
+# (hi, lo) fp16 pairs (include/pn2b200_mlp.h).  backbones.PointNet2Msg_fast asks for it on SA1-SA3 and FP3's first
+# layer: measured on BASELINE config 3 (tools/dev/emul_prec.py), plain fp16 rows in SA1 ALONE put 7 % on the last
+# module's output (FP3 normalises a broadcast global feature, x40 amplification by the end of the network), with those
+# stacks two-plane the whole path is within 4e-3 of strict fp32.  PRECISE_ENABLED = False ignores the requests (all
+# fp16, the round-1 engine) for A/B measurements.
+PRECISE_ENABLED = True
+
+
+def set_precise(on):
+    global PRECISE_ENABLED
+    PRECISE_ENABLED = bool(on)
 
 
 class ZeroArena:
@@ -167,9 +193,10 @@ class Rows:
     """fp16 row matrix [rows][ld] with c valid channels; scale/shift (fp32, length >= c) mean the
     consumer must read relu(y*scale + shift) -- the producer's BatchNorm+ReLU applied on the fly."""
 
-    __slots__ = ("y", "c", "ld", "scale", "shift", "offset", "sink", "numel", "version")
+    __slots__ = ("y", "lo", "c", "ld", "scale", "shift", "offset", "sink", "numel", "version")
 
-    def __init__(self, y, c, ld, scale=None, shift=None, offset=None, sink=None):
+    def __init__(self, y, c, ld, scale=None, shift=None, offset=None, sink=None, lo=None):
+        self.lo = lo  # second fp16 plane of two-plane rows (value = y + lo), same shape; None for plain rows
         # offset (fp32 [c]): the rows are stored CENTRED, true value = y + offset (pooled features)
         self.y, self.c, self.ld, self.scale, self.shift, self.offset = y, c, ld, scale, shift, offset
         self.sink = sink  # _Sink of the producing K=1 stack (row-form gradient hand-over), or None
@@ -190,8 +217,8 @@ def carry_rows(src, dst):
     return dst
 
 
-def rows_of(t):
-    """Row source of a (B,C,N) fp32 tensor: the attached one if still valid, else a conversion."""
+def rows_of(t, two=False):
+    """Row source of a (B,C,N) fp32 tensor: the attached one if still valid, else a conversion (two-plane if asked)."""
     r = getattr(t, "_pn2_rows", None)
     if r is not None and r.numel == t.numel() and r.version == t._version:
         return r
@@ -200,13 +227,13 @@ def rows_of(t):
     if t.dtype != torch.float32:
         raise TypeError("fused engine expects fp32 feature tensors")
     ld = (C + 7) // 8 * 8
-    y = torch.empty(B * N, ld, dtype=_F16, device=t.device)
-    _lib.call("pn2_to_rows", B, C, N, t.data_ptr(), 0, 0.0, y.data_ptr(), ld, _stream())
-    return Rows(y, C, ld)
+    y = torch.empty(2 if two else 1, B * N, ld, dtype=_F16, device=t.device)
+    _lib.call("pn2_to_rows_x2", B, C, N, t.data_ptr(), 0, 0.0, y[0].data_ptr(), y[1].data_ptr() if two else 0, ld, _stream())
+    return Rows(y[0], C, ld, lo=y[1] if two else None)
 
 
 class _Layer:
-    __slots__ = ("w", "cin", "kp", "cout", "y", "scale", "shift", "mean", "rstd")
+    __slots__ = ("w", "cin", "kp", "cout", "y", "scale", "shift", "mean", "rstd")  # w, y: hi planes (what backward reads)
 
 
 def _bn_momentum(bn):
@@ -221,12 +248,14 @@ class _MlpStack(Function):
        kind 'dense' : a = x (B,C,N)                                                  -> (B,Cout,N)"""
 
     @staticmethod
-    def forward(ctx, kind, meta, bns, pobjs, training, a, b, *params):
+    def forward(ctx, kind, meta, bns, pobjs, training, precise, a, b, *params):
         dev = params[0].device
         st = _stream()
         nl = len(params) // 4
-        ra = rows_of(a) if a is not None else None
-        rb = rows_of(b) if b is not None else None
+        precise = min(int(precise), nl) if PRECISE_ENABLED else 0  # leading layers with two-plane operands
+        two0 = precise > 0
+        ra = rows_of(a, two0) if a is not None else None
+        rb = rows_of(b, two0) if b is not None else None
 
         # ---- layer-0 input rows
         if kind == "sa":
@@ -240,37 +269,45 @@ class _MlpStack(Function):
             cc = rb.c if rb is not None else 0
             cin = fc + 3 + cc
             R, groups, pool_k = B * S * K, S, K
-            x0 = torch.empty(R, _padk(cin), dtype=_F16, device=dev)
-            _lib.call("pn2_sa_build_rows", B, N, S, K, xyz.data_ptr(), _p(new_xyz), _p(idx),
-                      _p(ra.y) if ra else 0, fc, ra.ld if ra else 0, _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0,
-                      _p(rb.y) if rb else 0, cc, rb.ld if rb else 0, _p(rb.scale) if rb else 0, _p(rb.shift) if rb else 0,
-                      1 if xyz_first else 0, x0.data_ptr(), x0.shape[1], st)
+            x0p = torch.empty(2 if two0 else 1, R, _padk(cin), dtype=_F16, device=dev)
+            x0, x0_lo = x0p[0], (x0p[1] if two0 else None)
+            _lib.call("pn2_sa_build_rows_x2", B, N, S, K, xyz.data_ptr(), _p(new_xyz), _p(idx),
+                      _p(ra.y) if ra else 0, _p(ra.lo) if ra else 0, fc, ra.ld if ra else 0, _p(ra.scale) if ra else 0,
+                      _p(ra.shift) if ra else 0,
+                      _p(rb.y) if rb else 0, _p(rb.lo) if rb else 0, cc, rb.ld if rb else 0, _p(rb.scale) if rb else 0,
+                      _p(rb.shift) if rb else 0,
+                      1 if xyz_first else 0, x0.data_ptr(), _p(x0_lo), x0.shape[1], st)
         elif kind == "fp":
             idx, dist2, N, S = meta[:4]
             B = b.shape[0]
             sc = ra.c if ra is not None else 0
             cin = sc + rb.c
             R, groups, pool_k = B * N, N, 1
-            x0 = torch.empty(R, _padk(cin), dtype=_F16, device=dev)
-            _lib.call("pn2_fp_build_rows", B, N, S, _p(ra.y) if ra else 0, sc, ra.ld if ra else 0,
-                      _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0, rb.y.data_ptr(), rb.c, rb.ld, _p(rb.scale),
-                      _p(rb.shift), _p(idx), _p(dist2), x0.data_ptr(), x0.shape[1], st)
+            x0p = torch.empty(2 if two0 else 1, R, _padk(cin), dtype=_F16, device=dev)
+            x0, x0_lo = x0p[0], (x0p[1] if two0 else None)
+            _lib.call("pn2_fp_build_rows_x2", B, N, S, _p(ra.y) if ra else 0, _p(ra.lo) if ra else 0, sc, ra.ld if ra else 0,
+                      _p(ra.scale) if ra else 0, _p(ra.shift) if ra else 0, rb.y.data_ptr(), _p(rb.lo), rb.c, rb.ld,
+                      _p(rb.scale), _p(rb.shift), _p(idx), _p(dist2), x0.data_ptr(), _p(x0_lo), x0.shape[1], st)
         else:
             B, cin, N = a.shape
             R, groups, pool_k = B * N, N, 1
-            x0 = None  # the dense stack reads its input rows in place
+            x0 = x0_lo = None  # the dense stack reads its input rows in place
 
         # ---- L x (GEMM + batch statistics)
         layers = []
         if x0 is not None:
-            x, x_ld, xs, xh, kp = x0, x0.shape[1], None, None, x0.shape[1]
+            x, x_lo, x_ld, xs, xh, kp = x0, x0_lo, x0.shape[1], None, None, x0.shape[1]
         else:
             if ra.ld == _padk(ra.c):
-                x, x_ld, xs, xh, kp = ra.y, ra.ld, ra.scale, ra.shift, ra.ld
+                x, x_lo, x_ld, xs, xh, kp = ra.y, ra.lo, ra.ld, ra.scale, ra.shift, ra.ld
             else:  # re-pad the row form to the GEMM's chunk granularity
                 kp = _padk(ra.c)
                 x = torch.zeros(R, kp, dtype=_F16, device=dev)
                 x[:, :ra.c] = ra.y[:, :ra.c]
+                x_lo = None
+                if ra.lo is not None:
+                    x_lo = torch.zeros(R, kp, dtype=_F16, device=dev)
+                    x_lo[:, :ra.c] = ra.lo[:, :ra.c]
                 x_ld, xs, xh = kp, ra.scale, ra.shift
             if xs is not None and xs.numel() < kp:
                 xs = torch.cat([xs, xs.new_zeros(kp - xs.numel())])
@@ -300,12 +337,14 @@ class _MlpStack(Function):
             L.cout, L.cin, L.kp = w.shape[0], w.shape[1], kp
             if L.cout % 32:
                 raise ValueError("fused engine needs layer widths that are multiples of 32 (got %d)" % L.cout)
-            if ACTIVE_PLAN is not None and training:
-                L.w = ACTIVE_PLAN.lookup(w, kp)
-            else:
-                L.w = torch.empty(L.cout, kp, dtype=_F16, device=dev)
-                _lib.call("pn2_mlp_prep_weights", L.cout, L.cin, kp, w.data_ptr(), L.w.data_ptr(), 0, st)
-            L.y = torch.empty(R, L.cout, dtype=_F16, device=dev)
+            # two-plane layer: BatchNorm'd two-plane inputs are limited to 256 columns by the kernel (wider: fp16 planes)
+            two = l < precise and not (xs is not None and kp > 256)
+            if two and x_lo is None:  # a one-plane producer in front of a two-plane layer
+                x_lo = torch.zeros_like(x)
+            wbuf = ACTIVE_PLAN.lookup(w, kp, two) if (ACTIVE_PLAN is not None and training) else _prep_weight(w, kp, two)
+            L.w, w_lo = wbuf[0], (wbuf[1] if two else None)
+            yp = torch.empty(2 if two else 1, R, L.cout, dtype=_F16, device=dev)
+            L.y, y_lo = yp[0], (yp[1] if two else None)
             consts = torch.empty(6, L.cout, dtype=torch.float32, device=dev)
             L.scale, L.shift, L.mean, L.rstd, cen, cen_true = (consts[i] for i in range(6))
             # Centring constant.  Training keeps it as state on the BatchNorm module: the GEMM tail of step t leaves the
@@ -328,8 +367,9 @@ class _MlpStack(Function):
                 stats = arena[a_off:a_off + 2 * L.cout]
                 a_off += 2 * L.cout
                 track = bn.track_running_stats and bn.running_mean is not None
-                _lib.call("pn2_mlp_gemm_fwd_bn", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
-                          cen.data_ptr(), L.y.data_ptr(), L.cout, stats.data_ptr(), counters[l].data_ptr(),
+                _lib.call("pn2_mlp_gemm_fwd_bn_x2", R, kp, L.cout, x.data_ptr(), _p(x_lo) if two else 0, x_ld, _p(xs), _p(xh),
+                          L.w.data_ptr(), _p(w_lo), cen.data_ptr(), L.y.data_ptr(), _p(y_lo), L.cout, stats.data_ptr(),
+                          counters[l].data_ptr(),
                           bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias), cen_true.data_ptr(), _bn_momentum(bn),
                           float(bn.eps), _p(bn.running_mean) if track else 0, _p(bn.running_var) if track else 0,
                           _p(bn.num_batches_tracked) if track else 0, L.scale.data_ptr(), L.shift.data_ptr(),
@@ -338,10 +378,10 @@ class _MlpStack(Function):
                 _lib.call("pn2_bn_eval_affine", L.cout, bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias),
                           cen_true.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps),
                           L.scale.data_ptr(), L.shift.data_ptr(), st)
-                _lib.call("pn2_mlp_gemm_fwd", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
-                          cen.data_ptr(), L.y.data_ptr(), L.cout, 0, st)
+                _lib.call("pn2_mlp_gemm_fwd_x2", R, kp, L.cout, x.data_ptr(), _p(x_lo) if two else 0, x_ld, _p(xs), _p(xh),
+                          L.w.data_ptr(), _p(w_lo), cen.data_ptr(), L.y.data_ptr(), _p(y_lo), L.cout, 0, st)
             layers.append(L)
-            x, x_ld, xs, xh, kp = L.y, L.cout, L.scale, L.shift, L.cout
+            x, x_lo, x_ld, xs, xh, kp = L.y, y_lo, L.cout, L.scale, L.shift, L.cout
 
         # ---- BN + ReLU (+ max over the group) -> module output
         last = layers[-1]
@@ -353,21 +393,24 @@ class _MlpStack(Function):
             chan_sums = arena[2 * sum(widths):2 * sum(widths) + widths[-1]]
             argmax = torch.empty(B, groups, C, dtype=torch.int32, device=dev) if training else None
         if not rows_only:  # rows_only: the caller promises that only the attached row form is read (backbone FP1 -> head)
-            _lib.call("pn2_pool_fwd", B, groups, pool_k, C, last.y.data_ptr(), C, last.scale.data_ptr(),
+            _lib.call("pn2_pool_fwd_x2", B, groups, pool_k, C, last.y.data_ptr(), _p(x_lo), C, last.scale.data_ptr(),
                       last.shift.data_ptr(), out.data_ptr(), _p(chan_sums), _p(argmax), st)
         if pool_k > 1:
             # pooled features go to the next fused consumer as bf16 rows centred on their channel mean
             inv = 1.0 / (B * groups)
-            out_rows = torch.empty(B * groups, C, dtype=_F16, device=dev)
-            _lib.call("pn2_to_rows", B, C, groups, out.data_ptr(), chan_sums.data_ptr(), inv, out_rows.data_ptr(), C, st)
-            _MlpStack.last_rows = Rows(out_rows, C, C, offset=chan_sums * inv)
+            two_out = x_lo is not None  # the last layer was two-plane: so are the pooled rows
+            out_rows = torch.empty(2 if two_out else 1, B * groups, C, dtype=_F16, device=dev)
+            _lib.call("pn2_to_rows_x2", B, C, groups, out.data_ptr(), chan_sums.data_ptr(), inv, out_rows[0].data_ptr(),
+                      out_rows[1].data_ptr() if two_out else 0, C, st)
+            _MlpStack.last_rows = Rows(out_rows[0], C, C, offset=chan_sums * inv, lo=out_rows[1] if two_out else None)
             ctx.out_sink = None
         else:
             ctx.out_sink = _Sink(R, C) if (training and C <= 1024) else None
-            _MlpStack.last_rows = Rows(last.y, C, C, last.scale, last.shift, sink=ctx.out_sink)
+            _MlpStack.last_rows = Rows(last.y, C, C, last.scale, last.shift, sink=ctx.out_sink, lo=x_lo)
         # gather-type consumer of a producer that offers a sink: deliver the feature gradient in row form
         ctx.feat_sink = ra.sink if (kind in ("sa", "dense") and SPARSE_GRAD_SINK and training and ra is not None
                                     and ra.sink is not None and a is not None and a.requires_grad) else None
+        del x_lo, x0_lo  # lo planes are forward-only: backward reads the hi planes
 
         ctx.kind, ctx.meta, ctx.training = kind, meta, training
         ctx.dims = (B, groups, pool_k, R, cin)
@@ -388,7 +431,7 @@ class _MlpStack(Function):
         if ctx.out_sink is not None:
             ctx.out_sink.buf = ctx.out_sink.rows16 = None
         if dout is None and extra is None and extra16 is None:
-            return (None, None, None, None, None, None, None, *none_params)
+            return (None, None, None, None, None, None, None, None, *none_params)
         if not ctx.training:
             raise NotImplementedError("fused engine: backward through eval-mode BatchNorm is not implemented; "
                                       "use engine 'ops' for that")
@@ -409,8 +452,8 @@ class _MlpStack(Function):
                   extra16[1] if extra16 else 0, last.y.data_ptr(), C, last.scale.data_ptr(),
                   last.shift.data_ptr(), last.mean.data_ptr(), last.rstd.data_ptr(), _p(ctx.argmax), dz.data_ptr(), C,
                   sums.data_ptr(), st)
-        need_a = ctx.needs_input_grad[5] and ctx.a_shape is not None
-        need_b = ctx.needs_input_grad[6] and ctx.b_shape is not None
+        need_a = ctx.needs_input_grad[6] and ctx.a_shape is not None
+        need_b = ctx.needs_input_grad[7] and ctx.b_shape is not None
         grads = [None] * (4 * nl)
         dx0 = None
         for l in range(nl - 1, -1, -1):
@@ -510,7 +553,7 @@ class _MlpStack(Function):
             else:
                 Bc, Cc, Nc = ctx.a_shape
                 da = dx0.view(Bc, Nc, -1)[:, :, :Cc].transpose(1, 2).float().contiguous()
-        return (None, None, None, None, None, da, db, *grads)
+        return (None, None, None, None, None, None, da, db, *grads)
 
 
 def _params(convs, bns):
@@ -527,12 +570,12 @@ def _check_cuda(t):
         raise ValueError("hotrack_b200 has no CPU path")
 
 
-def _run(kind, meta, convs, bns, training, a, b):
+def _run(kind, meta, convs, bns, training, a, b, precise=0):
     ps = _params(convs, bns)
     views = []
     for i, p in enumerate(ps):
         views.append(p.view(p.shape[0], -1) if i % 4 == 0 else p)  # conv weight (Cout,Cin,1[,1]) -> (Cout,Cin)
-    out = _MlpStack.apply(kind, meta, list(bns), ps, bool(training), a, b, *views)
+    out = _MlpStack.apply(kind, meta, list(bns), ps, bool(training), int(precise), a, b, *views)
     rows, _MlpStack.last_rows = _MlpStack.last_rows, None  # set by forward (single-threaded hand-over)
     return attach_rows(out, rows) if rows is not None else out
 
@@ -540,24 +583,24 @@ def _run(kind, meta, convs, bns, training, a, b):
 _MlpStack.last_rows = None
 
 
-def sa_scale(xyz, points, new_xyz, idx, centre_feat, convs, bns, training):
+def sa_scale(xyz, points, new_xyz, idx, centre_feat, convs, bns, training, precise=0):
     """One SA scale.  xyz (B,3,N), points (B,D,N)|None, new_xyz (B,3,S), idx (B,S,K) int32,
     centre_feat (B,E,S)|None -> (B,Cout,S)."""
     _check_cuda(xyz)
     if points is not None and points.shape[1] == 0:
         points = None
     meta = (xyz.contiguous().float(), new_xyz.contiguous().float(), idx.contiguous().int(), False)
-    return _run("sa", meta, convs, bns, training, points, centre_feat)
+    return _run("sa", meta, convs, bns, training, points, centre_feat, precise)
 
 
-def sa_group_all(xyz, points, convs, bns, training):
+def sa_group_all(xyz, points, convs, bns, training, precise=0):
     """Group-all SA.  xyz (B,3,N), points (B,D,N)|None -> (B,Cout,1); channel order [xyz, points]."""
     _check_cuda(xyz)
     meta = (xyz.contiguous().float(), None, None, True)
-    return _run("sa", meta, convs, bns, training, points, None)
+    return _run("sa", meta, convs, bns, training, points, None, precise)
 
 
-def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1, rows_only=False):
+def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1, rows_only=False, precise=0):
     """FP layer.  xyz1_t (B,N,3), xyz2_t (B,S,3), points1 (B*reps,D1,N)|None, points2 (B*reps,D2,S) -> (B*reps,Cout,N).
     rows_only: the returned fp32 tensor is left UNINITIALISED (only its attached row form is valid) -- for a caller that
     hands it straight to another fused stack (the backbone's FP1 -> conv1 head) and saves a 67 MB transpose."""
@@ -572,13 +615,13 @@ def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1, row
         pc.three_nn_wrapper(B, N, S, u, k, dist2, idx)
         if reps > 1:
             dist2, idx = dist2.repeat_interleave(reps, dim=0), idx.repeat_interleave(reps, dim=0)
-    return _run("fp", (idx, dist2, N, S, bool(rows_only)), convs, bns, training, points1, points2)
+    return _run("fp", (idx, dist2, N, S, bool(rows_only)), convs, bns, training, points1, points2, precise)
 
 
-def dense_stack(x, convs, bns, training):
+def dense_stack(x, convs, bns, training, precise=0):
     """relu(bn(conv1x1(x))) stack on (B,C,N) -> (B,Cout,N)."""
     _check_cuda(x)
-    return _run("dense", None, convs, bns, training, x, None)
+    return _run("dense", None, convs, bns, training, x, None, precise)
 
 
 def alg_bytes(name, a):

@@ -165,7 +165,7 @@ class _MsgBase(nn.Module, _EngineMixin):
         if self._fused():
             from . import fused
             return fused.sa_scale(xyz, points, new_xyz, idx, centre_feat, self.conv_blocks[i], self.bn_blocks[i],
-                                  self.training)
+                                  self.training, precise=getattr(self, "precise_layers", 0))
         grouped = futils.grouping_operation(xyz.contiguous(), idx) - new_xyz.unsqueeze(-1)
         if points is not None:
             grouped = torch.cat([futils.grouping_operation(points.contiguous(), idx), grouped], dim=1)
@@ -278,7 +278,8 @@ class _GroupAllBase(nn.Module, _EngineMixin):
         assert self.group_all, "Not Implemented"  # as the reference (pointnet_utils.py:502)
         if self._fused():
             from . import fused
-            return fused.sa_group_all(xyz, points, self.mlp_convs, self.mlp_bns, self.training)
+            return fused.sa_group_all(xyz, points, self.mlp_convs, self.mlp_bns, self.training,
+                                      precise=getattr(self, "precise_layers", 0))
         x = xyz if points is None else torch.cat([xyz, points], dim=1)
         return _run_stack(x.unsqueeze(-1), self.mlp_convs, self.mlp_bns).max(dim=2)[0]
 
@@ -324,7 +325,8 @@ class _FpBase(nn.Module, _EngineMixin):
         if self._fused():
             from . import fused
             return fused.fp_layer(xyz1_t, xyz2_t, points1, points2, self.mlp_convs, self.mlp_bns, self.training, reps,
-                                  rows_only=getattr(self, "_rows_only", False))
+                                  rows_only=getattr(self, "_rows_only", False),
+                                  precise=getattr(self, "precise_layers", 0))
         if S == 1:
             interpolated = points2.expand(-1, -1, N)
         else:

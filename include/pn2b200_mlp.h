@@ -129,7 +129,7 @@ int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, const void* dz
 int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_bf16, void* wt_bf16, pn2_stream_t stream);
 
 /* pn2_mlp_prep_weights (fp16 copy only) for n_layers layers in ONE launch.  descs: device array of n_layers records
- * { const float* w; void* w_f16; int n; int k_true; int kp; int pad; } (32 bytes each). */
+ * { const float* w; void* w_f16; int n; int k_true; int kp; int two; } (32 bytes each). */
 int pn2_mlp_prep_weights_multi(int n_layers, const void* descs, pn2_stream_t stream);
 
 /* Gradient of sa_build_rows' output rows scattered to the feature tensors (fp32, zeroed by the caller, atomics):
@@ -143,6 +143,43 @@ int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const void* dx, 
  * rows, zeroed by the caller, atomics; either may be NULL. */
 int pn2_fp_rows_bwd(int b, int n, int s, const int* idx, const float* dist2, const void* dx, int dx_ld, int skip_c,
                     float* dskip_cm, int coarse_c, float* dcoarse_rows, pn2_stream_t stream);
+
+/* ---- TWO-PLANE ("x2") forward rows -------------------------------------------------------------------------------
+ * A row matrix may come as a PAIR of fp16 planes (hi, lo) of the same shape and leading dimension with
+ * value = hi + lo (22 significand bits; lo = fp16(v - fp16(v))).  The forward GEMM then evaluates
+ * x_hi*w_hi + x_lo*w_hi + x_hi*w_lo into its fp32 accumulator and writes y as such a pair.  The engine uses this
+ * for the stacks in front of the backbone's ill-conditioned spot (SA1-SA3 and FP3's first layer: every rounding there
+ * is amplified ~40x by the end of the network), where 11-bit fp16 rows miss the 1e-2 parity bar; the backward
+ * kernels read the hi planes only.  Each _x2 entry point is its one-plane namesake with nullable lo pointers added
+ * (all lo pointers NULL = identical behaviour). */
+int pn2_to_rows_x2(int b, int c, int n, const float* src, const float* sub_sums, float sub_scale, void* dst, void* dst_lo,
+                   int ld, pn2_stream_t stream);
+int pn2_sa_build_rows_x2(int b, int n, int s, int k, const float* xyz, const float* new_xyz, const int* idx,
+                         const void* feat, const void* feat_lo, int feat_c, int feat_ld, const float* feat_scale,
+                         const float* feat_shift, const void* cen, const void* cen_lo, int cen_c, int cen_ld,
+                         const float* cen_scale, const float* cen_shift, int xyz_first, void* out, void* out_lo,
+                         int out_ld, pn2_stream_t stream);
+int pn2_fp_build_rows_x2(int b, int n, int s, const void* skip, const void* skip_lo, int skip_c, int skip_ld,
+                         const float* skip_scale, const float* skip_shift, const void* coarse, const void* coarse_lo,
+                         int coarse_c, int coarse_ld, const float* coarse_scale, const float* coarse_shift,
+                         const int* idx, const float* dist2, void* out, void* out_lo, int out_ld, pn2_stream_t stream);
+/* x_lo and w_lo come together (both or neither); y_lo nullable (the last layer of a stack whose consumer is the
+ * pooling kernel still wants it: the max is taken over hi + lo).  in_scale != NULL with two planes: kdim <= 256. */
+int pn2_mlp_gemm_fwd_x2(long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                        const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                        const float* center, void* y, void* y_lo, int y_ld, float* stats, pn2_stream_t stream);
+int pn2_mlp_gemm_fwd_bn_x2(long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                           const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                           const float* center, void* y, void* y_lo, int y_ld, float* stats, unsigned int* counter,
+                           const float* gamma, const float* beta, const float* conv_bias, const float* center_true,
+                           float momentum, float eps, float* running_mean, float* running_var,
+                           long long* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
+                           float* next_center, pn2_stream_t stream);
+int pn2_pool_fwd_x2(int b, int s, int k, int c, const void* y, const void* y_lo, int y_ld, const float* scale,
+                    const float* shift, float* out_cm, float* chan_sums, int* argmax, pn2_stream_t stream);
+/* fp32 conv weight [n][k_true] -> fp16 planes w_hi, w_lo [n][kp] (zero padded).  pn2_mlp_prep_weights_multi: a
+ * record whose last int ("two") is non-zero writes the lo plane right behind the hi plane (w_f16 + n*kp). */
+int pn2_mlp_prep_weights_x2(int n, int k_true, int kp, const float* w, void* w_hi, void* w_lo, pn2_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,103 @@ def test_gemm_fwd_and_stats(lib, cuda, R, K, N, affine):
     torch.testing.assert_close(stats[1], (yf * yf).sum(0), rtol=2e-3, atol=1e-2)
 
 
+def _split(t):
+    """fp32 -> (hi, lo) fp16 planes with t ~= hi + lo (the two-plane row form of include/pn2b200_mlp.h)."""
+    hi = t.to(HF)
+    return hi, (t - hi.float()).to(HF)
+
+
+@pytest.mark.parametrize("R,K,N,affine", [(1000, 32, 32, False), (4096, 128, 64, True), (777, 64, 128, True),
+                                           (5000, 640, 256, False), (129, 128, 512, True), (40000, 32, 64, True),
+                                           (4096, 192, 128, False)])
+def test_gemm_fwd_two_plane(lib, cuda, R, K, N, affine):
+    """pn2_mlp_gemm_fwd_x2: operands and output as (hi, lo) fp16 pairs -> fp32-class accuracy (vs an fp64 product)."""
+    g = torch.Generator(device="cpu").manual_seed(R + K + N)
+    x32 = torch.randn(R, K, generator=g).to(cuda)
+    w32 = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    xh, xl = _split(x32)
+    wh, wl = _split(w32)
+    xv = xh.double() + xl.double()
+    wv = wh.double() + wl.double()
+    sc = sh = None
+    if affine:
+        sc = (torch.rand(K, generator=g) + 0.5).to(cuda)
+        sh = (torch.randn(K, generator=g) * 0.3).to(cuda)
+        xv = torch.relu(torch.addcmul(sh, xv.float(), sc)).double()  # fp32 fma, as the kernel
+    cen = (torch.randn(N, generator=g) * 0.2).to(cuda)
+    want = xv @ wv.t() - cen.double()
+    yh = torch.full((R, N), float("nan"), dtype=HF, device=cuda)
+    yl = torch.full((R, N), float("nan"), dtype=HF, device=cuda)
+    stats = torch.zeros(2, N, device=cuda)
+    lib.call("pn2_mlp_gemm_fwd_x2", R, K, N, xh.data_ptr(), xl.data_ptr(), K, 0 if sc is None else sc.data_ptr(),
+             0 if sh is None else sh.data_ptr(), wh.data_ptr(), wl.data_ptr(), cen.data_ptr(), yh.data_ptr(),
+             yl.data_ptr(), N, stats.data_ptr(), _st())
+    got = yh.double() + yl.double()
+    assert torch.isfinite(got).all()
+    assert torch.equal(yh, (got.float()).to(HF)) or _rel(yh, got) < 6e-4  # hi plane = the fp16 rounding of the value
+    err = ((got - want).norm() / want.norm()).item()
+    assert err < 3e-6, err   # one-plane fp16 operands give ~4e-4 here
+    torch.testing.assert_close(stats[0].double(), got.sum(0), rtol=1e-3, atol=2e-2 * R ** 0.5)
+    torch.testing.assert_close(stats[1].double(), (got * got).sum(0), rtol=1e-3, atol=1e-2)
+    # lo pointers NULL: the one-plane kernel, bit for bit
+    y1 = torch.empty(R, N, dtype=HF, device=cuda)
+    y2 = torch.empty(R, N, dtype=HF, device=cuda)
+    for name, extra, out in (("pn2_mlp_gemm_fwd", None, y1), ("pn2_mlp_gemm_fwd_x2", 0, y2)):
+        st2 = torch.zeros(2, N, device=cuda)
+        if extra is None:
+            lib.call(name, R, K, N, xh.data_ptr(), K, 0 if sc is None else sc.data_ptr(), 0 if sh is None else sh.data_ptr(),
+                     wh.data_ptr(), cen.data_ptr(), out.data_ptr(), N, st2.data_ptr(), _st())
+        else:
+            lib.call(name, R, K, N, xh.data_ptr(), 0, K, 0 if sc is None else sc.data_ptr(), 0 if sh is None else sh.data_ptr(),
+                     wh.data_ptr(), 0, cen.data_ptr(), out.data_ptr(), 0, N, st2.data_ptr(), _st())
+    assert torch.equal(y1, y2)
+
+
+def test_two_plane_row_kernels(lib, cuda):
+    """to_rows / sa_build_rows / fp_build_rows / pool_fwd / prep_weights in two-plane form: hi + lo reproduces the fp32
+    value to ~2^-21, and the hi plane equals the one-plane output."""
+    g = torch.Generator(device="cpu").manual_seed(11)
+    B, C, N, S, K = 3, 24, 200, 16, 8
+    feat = torch.randn(B, C, N, generator=g).to(cuda) * 3
+    hi = torch.empty(B * N, C, dtype=HF, device=cuda); lo = torch.empty_like(hi); one = torch.empty_like(hi)
+    lib.call("pn2_to_rows_x2", B, C, N, feat.data_ptr(), 0, 0.0, hi.data_ptr(), lo.data_ptr(), C, _st())
+    lib.call("pn2_to_rows", B, C, N, feat.data_ptr(), 0, 0.0, one.data_ptr(), C, _st())
+    want = feat.transpose(1, 2).reshape(B * N, C)
+    assert torch.equal(hi, one)
+    assert _rel(hi.float() + lo.float(), want) < 2e-6 and _rel(hi, want) > 1e-5
+    # grouped rows: [feat | xyz - centre | pad]
+    xyz = torch.rand(B, 3, N, generator=g).to(cuda)
+    new_xyz = xyz[:, :, :S].contiguous()
+    idx = torch.randint(0, N, (B, S, K), generator=g, dtype=torch.int32).to(cuda)
+    ld = 32
+    oh = torch.empty(B * S * K, ld, dtype=HF, device=cuda); ol = torch.empty_like(oh)
+    lib.call("pn2_sa_build_rows_x2", B, N, S, K, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), hi.data_ptr(),
+             lo.data_ptr(), C, C, 0, 0, 0, 0, 0, 0, 0, 0, 0, oh.data_ptr(), ol.data_ptr(), ld, _st())
+    bi = torch.arange(B, device=cuda).view(B, 1, 1).expand(B, S, K)
+    gf = feat.transpose(1, 2)[bi, idx.long()]                                   # (B,S,K,C)
+    gx = xyz.transpose(1, 2)[bi, idx.long()] - new_xyz.transpose(1, 2).unsqueeze(2)
+    want = torch.cat([gf, gx], -1).reshape(B * S * K, C + 3)
+    got = (oh.float() + ol.float())[:, :C + 3]
+    assert _rel(got, want) < 2e-6
+    assert (oh[:, C + 3:] == 0).all() and (ol[:, C + 3:] == 0).all()
+    # pooling over two-plane rows
+    y32 = torch.randn(B * S * K, 16, generator=g).to(cuda)
+    yh, yl = _split(y32)
+    sc = (torch.rand(16, generator=g) + 0.5).to(cuda); sh = (torch.randn(16, generator=g) * 0.1).to(cuda)
+    out = torch.empty(B, 16, S, device=cuda)
+    am = torch.empty(B, S, 16, dtype=torch.int32, device=cuda)
+    cs = torch.zeros(16, device=cuda)
+    lib.call("pn2_pool_fwd_x2", B, S, K, 16, yh.data_ptr(), yl.data_ptr(), 16, sc.data_ptr(), sh.data_ptr(), out.data_ptr(),
+             cs.data_ptr(), am.data_ptr(), _st())
+    v = torch.relu(torch.addcmul(sh, yh.float() + yl.float(), sc)).view(B, S, K, 16)
+    torch.testing.assert_close(out, v.max(2)[0].permute(0, 2, 1), rtol=1e-6, atol=1e-6)
+    # weights
+    w = torch.randn(40, 19, generator=g).to(cuda)
+    wh = torch.empty(40, 32, dtype=HF, device=cuda); wl = torch.empty_like(wh)
+    lib.call("pn2_mlp_prep_weights_x2", 40, 19, 32, w.data_ptr(), wh.data_ptr(), wl.data_ptr(), _st())
+    assert _rel((wh.float() + wl.float())[:, :19], w) < 2e-6 and (wh[:, 19:] == 0).all() and (wl[:, 19:] == 0).all()
+
+
 @pytest.mark.parametrize("R,K,N", [(5000, 64, 128), (20000, 128, 384), (300, 32, 32)])
 def test_gemm_fwd_bn_tail_matches_separate_finalize(lib, cuda, R, K, N):
     """pn2_mlp_gemm_fwd_bn (BatchNorm finalisation by the last CTA, next-step centre) against pn2_mlp_gemm_fwd followed
