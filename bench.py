@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "ops", "fused"])
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "off", "all"],
+                    help="fused engine: which stacks keep two-plane (hi+lo fp16) forward rows (hotrack_b200.fused.set_precise)")
     ap.add_argument("--batch", type=int, default=32, help="clouds per GPU")
     ap.add_argument("--points", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -317,6 +319,9 @@ def main():
         except ImportError:
             engine = "ops"
 
+    if args.impl == "ours" and engine == "fused":
+        from hotrack_b200 import fused
+        fused.set_precise(args.precision)
     model = build_model(args.impl, engine, dev)
     if args.impl == "ours":
         from hotrack_b200 import _lib

@@ -242,9 +242,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                             uint32_t* ol = reinterpret_cast<uint32_t*>(&vl);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
+                                // the ReLU decision is taken on the hi plane alone -- the plane the backward kernels
+                                // read their masks from -- so forward and backward always agree on it (an element
+                                // within 2^-12 of the kink passes its tiny negative value instead of 0)
                                 const float2 a = h2_to_f2(x0[e]), l = h2_to_f2(x1[e]);
-                                const float r0 = fmaxf(fmaf(a.x + l.x, k0[2 * e], k1[2 * e]), 0.f);
-                                const float r1 = fmaxf(fmaf(a.y + l.y, k0[2 * e + 1], k1[2 * e + 1]), 0.f);
+                                const float r0 = fmaf(a.x, k0[2 * e], k1[2 * e]) > 0.f ? fmaf(a.x + l.x, k0[2 * e], k1[2 * e]) : 0.f;
+                                const float r1 = fmaf(a.y, k0[2 * e + 1], k1[2 * e + 1]) > 0.f
+                                                     ? fmaf(a.y + l.y, k0[2 * e + 1], k1[2 * e + 1]) : 0.f;
                                 o[e] = f2_to_h2(r0, r1);
                                 const float2 back = h2_to_f2(o[e]);
                                 ol[e] = f2_to_h2(r0 - back.x, r1 - back.y);

@@ -66,7 +66,13 @@ struct RowSrc {  // fp16 rows with an optional per-channel affine + ReLU ("still
 };
 __device__ __forceinline__ float row_val(const RowSrc& s, size_t row, int ch) {
     float v = h_to_f(s.p[row * s.ld + ch]);
-    if (s.lo) v += h_to_f(s.lo[row * s.ld + ch]);
+    if (s.lo) {
+        // two-plane rows: the ReLU decision is taken on the hi plane alone (what the backward kernels mask by)
+        const float full = v + h_to_f(s.lo[row * s.ld + ch]);
+        if (!s.scale) return full;
+        const float sc = __ldg(s.scale + ch), sh = __ldg(s.shift + ch);
+        return fmaf(v, sc, sh) > 0.f ? fmaf(full, sc, sh) : 0.f;
+    }
     if (s.scale) v = fmaxf(fmaf(v, __ldg(s.scale + ch), __ldg(s.shift + ch)), 0.f);
     return v;
 }
@@ -93,13 +99,24 @@ __device__ __forceinline__ void row_vals8(const RowSrc& s, size_t row, int ch, f
         v[2 * e] = f.x; v[2 * e + 1] = f.y;
     }
     if (s.lo) {
+        float l[8];
         const uint4 ql = __ldg(reinterpret_cast<const uint4*>(s.lo + row * s.ld + ch));
         const uint32_t* wl = reinterpret_cast<const uint32_t*>(&ql);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float2 f = h2_to_f2(wl[e]);
-            v[2 * e] += f.x; v[2 * e + 1] += f.y;
+            l[2 * e] = f.x; l[2 * e + 1] = f.y;
         }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (s.scale) {  // ReLU decided on the hi plane (see row_val)
+                const float sc = __ldg(s.scale + ch + e), sh = __ldg(s.shift + ch + e);
+                v[e] = fmaf(v[e], sc, sh) > 0.f ? fmaf(v[e] + l[e], sc, sh) : 0.f;
+            } else {
+                v[e] += l[e];
+            }
+        }
+        return;
     }
     if (s.scale) {
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(s.scale + ch)), s1 = __ldg(reinterpret_cast<const float4*>(s.scale + ch + 4));
@@ -301,12 +318,13 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
                 const act_t* yl = a.y_lo ? a.y_lo + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch : nullptr;
 #pragma unroll 4
                 for (int kk = 0; kk < a.k; ++kk) {
-                    float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
-                    if (yl) {
+                    const float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
+                    float r0 = fmaxf(fmaf(v.x, sc0, sh0), 0.f), r1 = fmaxf(fmaf(v.y, sc1, sh1), 0.f);
+                    if (yl) {  // two-plane rows: ReLU decided on the hi plane (what pool_bwd masks by), value from hi + lo
                         const float2 l = h2_to_f2(*reinterpret_cast<const uint32_t*>(yl + (size_t)kk * a.y_ld));
-                        v.x += l.x; v.y += l.y;
+                        r0 = r0 > 0.f ? fmaf(v.x + l.x, sc0, sh0) : 0.f;
+                        r1 = r1 > 0.f ? fmaf(v.y + l.y, sc1, sh1) : 0.f;
                     }
-                    const float r0 = fmaxf(fmaf(v.x, sc0, sh0), 0.f), r1 = fmaxf(fmaf(v.y, sc1, sh1), 0.f);
                     if (r0 > m0) { m0 = r0; i0 = kk; }
                     if (r1 > m1) { m1 = r1; i1 = kk; }
                 }
@@ -435,11 +453,12 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_grp_kernel(const PoolArgs a
                     const uint32_t* wl = reinterpret_cast<const uint32_t*>(&ql);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float2 f = h2_to_f2(w[e]);
+                        const float2 f = h2_to_f2(w[e]);
                         const float2 fl = h2_to_f2(wl[e]);
-                        f.x += fl.x; f.y += fl.y;
-                        const float r0 = fmaxf(fmaf(f.x, sc[2 * e], sh[2 * e]), 0.f);
-                        const float r1 = fmaxf(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]), 0.f);
+                        // ReLU decided on the hi plane (what pool_bwd masks by), value from hi + lo
+                        const float r0 = fmaf(f.x, sc[2 * e], sh[2 * e]) > 0.f ? fmaf(f.x + fl.x, sc[2 * e], sh[2 * e]) : 0.f;
+                        const float r1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]) > 0.f
+                                             ? fmaf(f.y + fl.y, sc[2 * e + 1], sh[2 * e + 1]) : 0.f;
                         if (r0 > m[2 * e]) { m[2 * e] = r0; mi[2 * e] = kk; }
                         if (r1 > m[2 * e + 1]) { m[2 * e + 1] = r1; mi[2 * e + 1] = kk; }
                     }
@@ -547,11 +566,12 @@ __global__ void __launch_bounds__(kThreads) rows_to_cm_kernel(const PoolArgs a) 
                 const uint32_t* vl = reinterpret_cast<const uint32_t*>(&ql);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float2 f = h2_to_f2(v[e]);
+                    const float2 f = h2_to_f2(v[e]);
                     const float2 fl = h2_to_f2(vl[e]);
-                    f.x += fl.x; f.y += fl.y;
-                    tile_dyn[r * ldt + (2 * e) * pieces + pc] = fmaxf(fmaf(f.x, sc[2 * e], sh[2 * e]), 0.f);
-                    tile_dyn[r * ldt + (2 * e + 1) * pieces + pc] = fmaxf(fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]), 0.f);
+                    tile_dyn[r * ldt + (2 * e) * pieces + pc] =
+                        fmaf(f.x, sc[2 * e], sh[2 * e]) > 0.f ? fmaf(f.x + fl.x, sc[2 * e], sh[2 * e]) : 0.f;
+                    tile_dyn[r * ldt + (2 * e + 1) * pieces + pc] =
+                        fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]) > 0.f ? fmaf(f.y + fl.y, sc[2 * e + 1], sh[2 * e + 1]) : 0.f;
                 }
             }
         }

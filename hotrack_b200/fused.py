@@ -65,6 +65,13 @@ def set_sparse_grad_sink(on):
     SPARSE_GRAD_SINK = bool(on)
 
 
+# Parameter gradients written straight into ``param.grad`` (atomics / "+=" inside the kernels) instead of being returned
+# to autograd.  Opt-in, for a training step that owns the whole backward pass and keeps plain fp32 .grad buffers
+# (train.TrainStep over flat.FlatParams sets it for the duration of its step): with it on, autograd hooks on the
+# parameters (DDP's reducer), torch.autograd.grad and backward(inputs=...) do not see these gradients.
+DIRECT_PARAM_GRADS = False
+
+
 class WeightPlan:
     """fp16 copies of the conv weights of a step, all converted by ONE launch at the top of the step.
 
@@ -129,14 +136,21 @@ ACTIVE_PLAN = None  # set by TrainStep around its forward pass
 # (hi, lo) fp16 pairs (include/pn2b200_mlp.h).  backbones.PointNet2Msg_fast asks for it on SA1-SA3 and FP3's first
 # layer: measured on BASELINE config 3 (tools/dev/emul_prec.py), plain fp16 rows in SA1 ALONE put 7 % on the last
 # module's output (FP3 normalises a broadcast global feature, x40 amplification by the end of the network), with those
-# stacks two-plane the whole path is within 4e-3 of strict fp32.  PRECISE_ENABLED = False ignores the requests (all
-# fp16, the round-1 engine) for A/B measurements.
-PRECISE_ENABLED = True
+# stacks two-plane the whole path is within 4e-3 of strict fp32.  PRECISE_MODE "off" ignores the requests (all fp16,
+# the round-1 engine), "all" runs every layer of every stack two-plane (fp32-class forward, for strict comparisons).
+PRECISE_MODE = "auto"   # "auto": as the modules ask | "off": never | "all": every layer of every stack
 
 
-def set_precise(on):
-    global PRECISE_ENABLED
-    PRECISE_ENABLED = bool(on)
+def set_precise(mode):
+    """'auto' (default) | 'off' | 'all'; booleans are accepted for on/off."""
+    global PRECISE_MODE
+    if mode is True:
+        mode = "auto"
+    elif mode is False:
+        mode = "off"
+    if mode not in ("auto", "off", "all"):
+        raise ValueError("precision mode must be 'auto', 'off' or 'all'")
+    PRECISE_MODE = mode
 
 
 class ZeroArena:
@@ -252,7 +266,8 @@ class _MlpStack(Function):
         dev = params[0].device
         st = _stream()
         nl = len(params) // 4
-        precise = min(int(precise), nl) if PRECISE_ENABLED else 0  # leading layers with two-plane operands
+        # leading layers with two-plane operands
+        precise = nl if PRECISE_MODE == "all" else (min(int(precise), nl) if PRECISE_MODE == "auto" else 0)
         two0 = precise > 0
         ra = rows_of(a, two0) if a is not None else None
         rb = rows_of(b, two0) if b is not None else None
@@ -458,12 +473,12 @@ class _MlpStack(Function):
         dx0 = None
         for l in range(nl - 1, -1, -1):
             L = layers[l]
-            # Parameter gradients go STRAIGHT into the parameters' .grad when those exist as plain fp32 buffers
-            # (FlatParams keeps them so): autograd's per-parameter "+=" kernels disappear.  Otherwise they
-            # are returned to autograd the usual way.
+            # Parameter gradients go STRAIGHT into the parameters' .grad when the step opted in (DIRECT_PARAM_GRADS) and
+            # those exist as plain fp32 buffers (FlatParams keeps them so): autograd's per-parameter "+=" kernels
+            # disappear.  Otherwise they are returned to autograd the usual way.
             pw, pb, pg, pbt = ctx.pobjs[4 * l: 4 * l + 4]
-            direct = all(q.grad is not None and q.grad.is_contiguous() and q.grad.dtype == torch.float32
-                         for q in (pw, pg, pbt))
+            direct = DIRECT_PARAM_GRADS and all(q.grad is not None and q.grad.is_contiguous() and q.grad.dtype == torch.float32
+                                                for q in (pw, pg, pbt))
             coefs = torch.empty(5, L.cout, dtype=torch.float32, device=dev)
             # the input-gradient GEMM multiplies dz and y as stored: the BatchNorm-backward coefficients are folded into
             # two copies of the weights (and a bias) by the same small kernel that derives them

@@ -18,7 +18,6 @@ class TrainStep:
     def __init__(self, model, loss_fn, lr=1e-4, weight_decay=1e-4, graph=True):
         self.model, self.loss_fn = model, loss_fn
         from . import fused
-        fused.set_sparse_grad_sink(True)  # whole-step backward: gather gradients travel in row form
         self._fused = fused
         self.weights = fused.WeightPlan()
         self.use_plan = os.environ.get("PN2_NO_WPLAN", "") == ""
@@ -38,13 +37,19 @@ class TrainStep:
 
     def _fwd_bwd(self, inputs):
         self.flat.zero_grad()
+        f = self._fused
+        saved = (f.SPARSE_GRAD_SINK, f.DIRECT_PARAM_GRADS)
+        # whole-step backward owned by this object: gather gradients travel in row form and parameter gradients are
+        # accumulated straight into the flat .grad buffer -- both only for the duration of the step
+        f.SPARSE_GRAD_SINK = f.DIRECT_PARAM_GRADS = True
         if self.arena is not None:
             self.arena.begin()
-            self._fused.ACTIVE_ARENA = self.arena
+            f.ACTIVE_ARENA = self.arena
         try:
             return self._fwd_bwd_inner(inputs)
         finally:
-            self._fused.ACTIVE_ARENA = None
+            f.ACTIVE_ARENA = None
+            f.SPARSE_GRAD_SINK, f.DIRECT_PARAM_GRADS = saved
 
     def _fwd_bwd_inner(self, inputs):
         if self.use_plan:
@@ -68,18 +73,28 @@ class TrainStep:
 
     def _capture(self, inputs):
         self._static_in = [t.clone() for t in inputs]
+        # The warm-up steps must leave no trace: the first call applies ONE optimiser update, like the eager path and the
+        # reference's Trainer.update.  Weights, Adam moments, the step counter and the BatchNorm buffers are restored
+        # afterwards (the centring constants the warm-up leaves on the BatchNorm modules stay: they do not enter the
+        # mathematics, and the captured step must be the steady-state one that reads them).
+        snap = [t.clone() for t in self._state_tensors()]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up on a side stream: lazy inits, allocator, cuDNN/cuBLAS handles
             for _ in range(3):
                 self._eager(self._static_in)
+            for t, s0 in zip(self._state_tensors(), snap):
+                t.copy_(s0)
         torch.cuda.current_stream().wait_stream(side)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._loss = self._fwd_bwd(self._static_in)
             if self.world == 1:
                 self._finish()
-        return 3
+        return 0
+
+    def _state_tensors(self):
+        return [self.flat.data, self.opt.exp_avg, self.opt.exp_avg_sq, self.opt.step_dev] + list(self.model.buffers())
 
     def __call__(self, *inputs):
         """inputs: CUDA tensors of the (static) shapes of the first call -> detached scalar loss tensor."""
