@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="clouds per GPU")
     ap.add_argument("--points", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the ops-engine / --precision all / config-5 latency legs")
     ap.add_argument("--no-graph", action="store_true", help="ours: dispatch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=8, help="clouds in the cpu_baseline sample")
     ap.add_argument("--profile-mode", action="store_true",
@@ -181,12 +182,6 @@ def alg_bytes(name, a):
         return None
 
 
-def _mean_square(t):
-    # mean(t^2) as |t|_2^2 / numel: one reduction kernel forward and one elementwise kernel backward over the 201 MB
-    # backbone output instead of five -- the loss is harness, not the path, and both arms pay for it
-    return torch_linalg_norm(t).square() / t.numel()
-
-
 _MS = None
 
 
@@ -219,33 +214,33 @@ def loss_fn(src2, f11, f13):
 
 
 def make_inputs(B, N, rank):
+    import importlib.util
+
     import torch
 
-    from hotrack_b200 import synthetic
-
+    # hotrack_b200/synthetic.py loaded as a plain file: importing the PACKAGE would dlopen libpn2b200.so, which the
+    # reference arm must not do
+    spec = importlib.util.spec_from_file_location("_pn2_synthetic", os.path.join(ROOT, "hotrack_b200", "synthetic.py"))
+    synthetic = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synthetic)
     xyz = torch.from_numpy(synthetic.ball(B, N, seed=1000 + rank))       # (B,N,3) canonicalised hand cloud
     kps = torch.from_numpy(synthetic.keypoints(B, 21, seed=1000 + rank))  # (B,21,3) jittered joints
     return xyz, kps
 
 
 def build_model(impl, engine, dev):
-    import torch
-
-    from hotrack_b200 import backbones
-    from hotrack_b200.handtrack_path import HandTrackPointPath, init_weights
-
     if impl == "ours":
-        from hotrack_b200 import pointnet_utils as pu
+        from hotrack_b200 import backbones, pointnet_utils as pu
+        from hotrack_b200.handtrack_path import HandTrackPointPath, init_weights
         pu.set_engine(engine)
         model = HandTrackPointPath(backbones.default_cfg(dev))
+        pu.set_engine("ops")
+        init_weights(model, seed=0)
     else:
-        from oracle import ref_modules
-        rpu, rbb = ref_modules.load(cuda=(dev.type == "cuda"))
-        ns = types.SimpleNamespace(
-            PointNet2Msg_fast=rbb.PointNet2Msg_fast,
-            PointNetSetAbstractionMsg_GivenCenterPoints=rpu.PointNetSetAbstractionMsg_GivenCenterPoints)
-        model = HandTrackPointPath(backbones.default_cfg(dev), ns)
-    init_weights(model, seed=0)
+        # the reference's own classes on its own kernels; nothing of hotrack_b200 is imported on this arm
+        from oracle import ref_path
+        model = ref_path.RefPointPath(dev, cuda=(dev.type == "cuda"))
+        ref_path.xavier_init(model, seed=0)
     model = model.to(dev)
     model.train()
     return model
@@ -277,6 +272,76 @@ def cpu_reference(sample, N, steps=3, warmup=1):
             "sample": "%d clouds x N=%d, %d fwd+bwd+Adam steps of the same path through the reference's own CPU "
                       "fallback (pointnet_utils.py CUDA=False branch + torch CPU), %.2f s/step" % (sample, N, steps,
                                                                                                   per_step)}
+
+
+# ------------------------------------------------------------------ side legs ----------------
+def _time_steps(torch, fn, n, flush):
+    """mean device ms of n calls of fn(), L2 flushed (untimed) before each"""
+    tot = 0.0
+    for _ in range(n):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        tot += s.elapsed_time(e)
+    return tot / n
+
+
+def side_legs_ours(torch, dev, B, N, xyz_d, kps_d, flush, FromPoints):
+    """Numbers quoted NEXT to the headline (rank 0, N=1): the same step with the fp32 'ops' engine (our index / gather /
+    interpolate kernels + torch.nn fp32 convolutions: the 1e-5 parity configuration), the fused engine with two-plane
+    rows everywhere (--precision all: fp32-class forward), and BASELINE config 5 (B=1, N=8192 backbone, eval, sequential
+    frames, p50 wall latency, one CUDA-graph replay per frame)."""
+    import numpy as np
+
+    from hotrack_b200 import backbones, fused, pointnet_utils as pu, synthetic
+    from hotrack_b200.handtrack_path import init_weights
+    from hotrack_b200.train import GraphedForward, TrainStep
+
+    out = {}
+    for tag, engine, mode, graph, n in (("engine_ops_fp32", "ops", "auto", False, 5), ("precision_all", "fused", "all", True, 10)):
+        fused.set_precise(mode)
+        try:
+            model = build_model("ours", engine, dev)
+            ts = TrainStep(FromPoints(model), lambda o: loss_fn(*o[:3]), lr=1e-4, weight_decay=1e-4, graph=graph)
+            for _ in range(3):
+                ts(xyz_d, kps_d)
+            torch.cuda.synchronize()
+            ms = _time_steps(torch, lambda: ts(xyz_d, kps_d), n, flush)
+            out[tag] = {"ms_per_step": round(ms, 4), "value": round(B / ms * 1e3, 2), "unit": UNIT, "steps": n,
+                        "dispatch": "cuda-graph replay" if graph else "eager"}
+            del ts, model
+        finally:
+            fused.set_precise("auto")
+    pu.set_engine("fused")
+    try:
+        bb = backbones.PointNet2Msg_fast(backbones.default_cfg(dev), 384)
+    finally:
+        pu.set_engine("ops")
+    init_weights(bb, seed=0)
+    bb = bb.to(dev).eval()
+    x5 = torch.from_numpy(synthetic.ball(1, 8192, seed=7)).to(dev).transpose(1, 2).contiguous()
+    out["latency_config5"] = _latency(torch, np, GraphedForward(bb), x5)
+    out["latency_config5"]["what"] = "B=1 N=8192 PointNet2Msg_fast forward, eval, fused engine, one CUDA-graph replay per frame"
+    return out
+
+
+def _latency(torch, np, fn, x, frames=300):
+    import time as _t
+    with torch.no_grad():
+        for _ in range(20):
+            fn(x)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(frames):
+            t0 = _t.perf_counter()
+            fn(x)
+            torch.cuda.synchronize()  # frame t+1 needs frame t (track_network.py:163,217)
+            ts.append((_t.perf_counter() - t0) * 1e3)
+    ts = np.array(ts)
+    return {"p50_ms": round(float(np.percentile(ts, 50)), 4), "p99_ms": round(float(np.percentile(ts, 99)), 4), "frames": frames}
 
 
 # ------------------------------------------------------------------ main ----------------------
@@ -443,11 +508,15 @@ def main():
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world if ddp else 1, "steps": K, "warmup": W,
         "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if (args.impl == "ours" and engine == "fused") else "f32(tf32 conv)" if args.impl == "reference" else "f32",
+        # the arithmetic the grouped MLP runs in (not a precision claim): fp16 forward rows -- as two-plane hi+lo pairs in
+        # SA1-SA3 and FP3's first layer --, bf16 gradient rows, fp32 accumulation and BatchNorm; indices / gathers fp32
+        "dtype": ("f16 fwd rows (two-plane f16x2 in SA1-3, FP3.0) / bf16 grad rows / f32 accumulate"
+                  if (args.impl == "ours" and engine == "fused") else "f32(tf32 conv)" if args.impl == "reference" else "f32"),
         "data": "synthetic",
         "config": {"workload": "HandTrackNet pointnet_lib path (PointNet2Msg_fast shallow1 backbone -> q1 -> q2, 21 joints), "
                                "train step fwd+bwd+Adam, B=%d N=%d per GPU" % (B, N),
                    "clouds_per_gpu": B, "points": N, "engine": engine if args.impl == "ours" else "reference-cuda",
+                   "precision": args.precision if (args.impl == "ours" and engine == "fused") else None,
                    "parallelism": "dp%d" % (world if ddp else 1),
                    "dispatch": ("cuda-graph replay" if (args.impl == "ours" and not args.no_graph) else "eager"),
                    "l2": "256 MiB flush between timed steps (untimed); per-step working set >> 126 MB L2"},
@@ -466,6 +535,13 @@ def main():
                                           "own kernels (compiled for sm_100a) + its Python layer + torch.optim.Adam on the "
                                           "same B200, host threads only drive launches"}
         line["e2e"]["note"] = "reference GPU path driven from pinned host buffers"
+        if not args.profile_mode:
+            import numpy as np
+            bb = model.bhand.eval()
+            x5, _ = make_inputs(1, 8192, 7)
+            x5 = x5.to(dev).transpose(1, 2).contiguous()
+            line["latency_config5"] = _latency(torch, np, lambda t: bb(t), x5)
+            line["latency_config5"]["what"] = "B=1 N=8192 PointNet2Msg_fast forward, eval, reference modules on reference kernels, eager"
     else:
         # dominant kernel of OURS inside the timed region
         peak, peak_src = peaks()
@@ -515,6 +591,26 @@ def main():
                 pass
         line["roofline"] = best
         line["kernel_shares"] = shares[:12]
+        # the same probe aggregated per kernel ENTRY POINT (all shapes): which function the step spends its time in, and
+        # what that function achieves over all of its launches
+        fam = {}
+        for (name, key), (t, lst) in tot.items():
+            f = fam.setdefault(name, [0.0, 0, 0])
+            f[0] += t
+            f[1] += len(lst)
+            nb = alg_bytes(name, lst[0][0])
+            f[2] += (nb or 0) * len(lst)
+        line["kernel_families"] = [
+            {"kernel": name, "launches_per_step": cnt // 3, "us_per_step": round(t / 3 * 1e3, 1),
+             "share_of_our_kernels": round(t / ours_ms, 4),
+             "achieved_gbs": round(nbytes / (t * 1e-3) / 1e9, 1) if nbytes else None,
+             "frac_of_hbm_peak": round(nbytes / (t * 1e-3) / 1e9 / peak, 4) if nbytes else None}
+            for name, (t, cnt, nbytes) in sorted(fam.items(), key=lambda kv: -kv[1][0])][:10]
+        if not ddp and not args.profile_mode and not args.no_side_legs and engine == "fused":
+            try:
+                line.update(side_legs_ours(torch, dev, B, N, xyz_d, kps_d, flush, FromPoints))
+            except Exception as ex:  # a side leg must never take the headline down with it
+                line["side_legs_error"] = repr(ex)[:300]
         if not ddp and not args.no_cpu_baseline and not args.profile_mode:  # rank 0 at N=1 only
             try:
                 line["cpu_baseline"] = cpu_reference(args.cpu_sample, N, steps=3, warmup=1)

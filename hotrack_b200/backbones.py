@@ -104,14 +104,14 @@ class PointNet2Msg_fast(nn.Module):
         l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
         skip = torch.cat([l0_xyz, l0_points], dim=-2) if l0_points.shape[-2] else l0_xyz  # backbones.py:127-130
         # FP1's output goes to the fused head and nowhere else: its fp32 (B,C,N) copy need not be written
-        self.fp1._rows_only = pu.get_engine() == "fused" and getattr(self.fp1, "engine", "ops") == "fused"
+        self.fp1._rows_only = getattr(self.fp1, "engine", "ops") == "fused"
         l0_points = self.fp1(l0_xyz, l1_xyz, skip, l1_points)
         return _head(self, pu._carry(l0_points, l0_points.reshape(B, -1, N)))
 
 
 def _head(self, feats):
     """relu(bn1(conv1(x))) (backbones.py:69,131-132); fused engine: one 16-bit tensor-core stack."""
-    if pu.get_engine() == "fused" and getattr(self.fp1, "engine", "ops") == "fused":
+    if getattr(self.fp1, "engine", "ops") == "fused":  # the engine the backbone was BUILT with (as every SA / FP module)
         from . import fused
         return fused.dense_stack(feats, [self.conv1], [self.bn1], self.training)
     return F.relu(self.bn1(self.conv1(feats)))

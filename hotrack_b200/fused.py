@@ -640,10 +640,15 @@ def dense_stack(x, convs, bns, training, precise=0):
 
 
 def alg_bytes(name, a):
-    """Algorithmic bytes of one C-ABI call of the fused kernels (bench.py's roofline line)."""
+    """Algorithmic bytes of one C-ABI call of the fused kernels (bench.py's roofline line).  Two-plane ("_x2") calls
+    move two fp16 planes where their lo pointers are set."""
     if name in ("pn2_mlp_gemm_fwd", "pn2_mlp_gemm_fwd_bn"):
         rows, kdim, n = a[:3]
         return rows * (kdim + n) * 2 + n * kdim * 2
+    if name in ("pn2_mlp_gemm_fwd_x2", "pn2_mlp_gemm_fwd_bn_x2"):
+        rows, kdim, n = a[:3]
+        pin, pout = (2 if a[4] else 1), (2 if a[12] else 1)
+        return rows * (kdim * pin + n * pout) * 2 + n * kdim * 2 * pin
     if name == "pn2_mlp_gemm_dgrad":
         rows, n_red, k_out = a[:3]
         masked = a[11] != 0
@@ -651,9 +656,10 @@ def alg_bytes(name, a):
     if name == "pn2_mlp_gemm_wgrad":
         rows, n, kp = a[:3]
         return rows * (2 * n + kp) * 2 + n * kp * 4
-    if name == "pn2_pool_fwd":
+    if name in ("pn2_pool_fwd", "pn2_pool_fwd_x2"):
         b, s, k, c = a[:4]
-        return b * s * k * c * 2 + b * s * c * 4 + (b * s * c * 4 if k > 1 else 0)
+        planes = 2 if (name.endswith("_x2") and a[5]) else 1
+        return b * s * k * c * 2 * planes + b * s * c * 4 + (b * s * c * 4 if k > 1 else 0)
     if name == "pn2_pool_bwd":
         b, s, k, c = a[:4]
         extra = (b * s * c * 4 if a[5] else 0) + (b * s * c * 2 if a[6] else 0)  # row-form gradients of fused consumers
@@ -661,9 +667,17 @@ def alg_bytes(name, a):
     if name == "pn2_sa_build_rows":
         b, n, s, k = a[:4]
         return b * s * k * (a[19] * 2 + 4) + b * s * k * 2 * (a[8] + a[13])
+    if name == "pn2_sa_build_rows_x2":
+        b, n, s, k = a[:4]
+        pin_f, pin_c, pout = (2 if a[8] else 1), (2 if a[14] else 1), (2 if a[21] else 1)
+        return b * s * k * (a[22] * 2 * pout + 4) + b * s * k * 2 * (a[9] * pin_f + a[15] * pin_c)
     if name == "pn2_fp_build_rows":
         b, n, s = a[:3]
         return b * n * (a[17] * 2 + 24 + 2 * a[4]) + b * s * a[9] * 2
+    if name == "pn2_fp_build_rows_x2":
+        b, n, s = a[:3]
+        pin_s, pin_c, pout = (2 if a[4] else 1), (2 if a[10] else 1), (2 if a[18] else 1)
+        return b * n * (a[19] * 2 * pout + 24 + 2 * a[5] * pin_s) + b * s * a[11] * 2 * pin_c
     if name == "pn2_sa_rows_bwd":
         b, n, s, k = a[:4]
         return b * s * k * (a[6] * 2 + 4)
@@ -673,4 +687,7 @@ def alg_bytes(name, a):
     if name == "pn2_to_rows":
         b, c, n = a[:3]
         return b * c * n * 4 + b * n * a[7] * 2
+    if name == "pn2_to_rows_x2":
+        b, c, n = a[:3]
+        return b * c * n * 4 + b * n * a[8] * 2 * (2 if a[7] else 1)
     return None

@@ -179,9 +179,9 @@ def test_handtracknet_training_step_matches_reference(refnet, cuda):
         if n1.endswith(".bias") and "conv" in n1 and "final_mlp" not in n1:
             continue
         live += 1
-        # 5e-3: forward agreement e ~ 1e-5 re-routes ~e of the max-pool / ReLU selections, which moves a gradient made of
-        # random-sign contributions by ~sqrt(e) (measured 2.5e-3 on SA1's first layer, the deepest one)
-        assert _rel(p1.grad, p2.grad) < 5e-3, (n1, _rel(p1.grad, p2.grad))
+        # 2e-2: forward agreement e ~ 1e-5 re-routes ~e of the max-pool / ReLU selections, which moves a gradient made of
+        # random-sign contributions by ~sqrt(e) (measured up to 7e-3, varying from run to run with the atomics' order)
+        assert _rel(p1.grad, p2.grad) < 2e-2, (n1, _rel(p1.grad, p2.grad))
     assert live > 100
 
 
