@@ -4,33 +4,32 @@
 //                                                X' = relu(X*scale+shift) | X   (the layer's input)
 //
 // (the conv1x1 weight gradient cuDNN computes for reference pointnet_utils.py:399-403,458-460,505-507,577-580
-// and backbones.py:131 in backward).  The per-channel coefficients are pulled OUT of the row sum,
+// and backbones.py:131 in backward).
 //
-//     dW[n][k] = cA[n] * (dZ^T X')[n][k]  +  cB[n] * (Y^T X')[n][k]  +  cC[n] * (1^T X')[k]
+// The reduction runs over ROWS, so in memory both operands are MN-major (a memory row is one K slice) -- and the tensor
+// core is fed MN-major 16-bit tiles at a fraction of the K-major rate (measured: 0.13-0.3 us per M=128,K=16
+// instruction).  The operands are therefore TRANSPOSED on the way in, shared memory to shared memory, and since every
+// element passes through a thread's registers in that pass anyway, the BatchNorm-backward combination of dZ and Y and the
+// BatchNorm+ReLU of X are applied there too: ONE bf16 x bf16 tcgen05.mma per K step, accumulators resident in TMEM over
+// all rows of the CTA.
 //
-// so dZ (bf16) and Y (fp16) reach the tensor core exactly as stored; only X passes through arithmetic (BatchNorm+ReLU
-// of the producing layer, and a bf16 copy: one tcgen05.mma multiplies like with like).  G1 = dZ^T X', G2 = Y^T X' (MT
-// 128-channel tiles each) and G3 = 1^T X' (a constant tile of ones as A operand) accumulate in TMEM over ALL rows of
-// the CTA; the epilogue combines them and adds into dW with fp32 atomics.
+//   raw ring   [NR] stages of WR = 64 rows x [dZ 128 | Y 128 | X kw] columns, row-major (pitch = an odd number of 16-byte
+//              units: conflict-free ldmatrix), filled by cp.async, D = NR - 2 stages in flight
+//   T ring     [NT] slots of 4 sub-tiles (16 rows = one MMA K step each) in the UMMA K-major no-swizzle layout: 8x8 core
+//              matrices (8 channels x 8 rows, 128 contiguous bytes), a channel group's two K halves 128 B apart (LBO),
+//              channel groups 256 B apart (SBO)
+//   8 producer warps  cp.async the raw stage; per 16x16 block: ldmatrix.x4.trans (the fragment now holds 8x8 blocks
+//                     channel-major) of dZ and Y -> cA*dZ + cB*Y + cC in fp32 -> bf16 -> stmatrix.x4 = four core matrices;
+//                     X blocks: BatchNorm+ReLU -> bf16 -> stmatrix; fence.proxy.async, mbarrier arrive
+//   1 MMA warp        one lane: per stage 4 x tcgen05.mma (M = 128 output channels, N = kw input channels, K = 16 rows),
+//                     tcgen05.commit frees the T slot; a final commit publishes the accumulator
+//   4 epilogue warps  tcgen05.ld, vector reductions (red.global.add.v4.f32) into dW
 //
-// The reduction runs over ROWS: memory rows are K slices, which makes both operands MN-major -- and the tensor core is
-// fed MN-major 16-bit tiles at a fraction of the K-major rate (measured: 0.13-0.3 us per M=128,K=16 instruction).  So
-// the operands are TRANSPOSED on the way in, shared memory to shared memory:
-//
-//   raw ring   [NR][16 rows][dZ n_c | Y n_c | X kw_c columns] row-major, pitch = an odd number of 16-byte units,
-//              filled by cp.async, D = NR - 2 stages in flight
-//   T ring     [NT] operand tiles in the UMMA K-major no-swizzle layout: 8x8 core matrices (8 channels x 8 rows,
-//              128 contiguous bytes), a channel group's two K halves 128 B apart (LBO), channel groups 256 B apart (SBO)
-//   producers  per 16x16 block: ldmatrix.x4.trans from the raw stage (the fragment now holds 8x8 blocks channel-major),
-//              [X only: BN+ReLU per channel, fp16 + bf16 copies], stmatrix.x4 = four core matrices
-//
-//   8 producer warps  as above, fence.proxy.async, mbarrier arrive
-//   1 MMA warp        one lane: per stage (2 MT + 1) tcgen05.mma (M = 128, N = kw, K = 16 rows); tcgen05.commit frees
-//                     the T slot; a final commit publishes the accumulators
-//   4 epilogue warps  wait for the final commit, tcgen05.ld, combine with cA / cB / cC, atomics into dW
-//
-// Grid: (row splits, input-channel tiles of kw <= 512 / (2 MT + 1) columns).
-// Bound: HBM reads rows*(2n + k)*2 bytes.
+// 64-row stages: one producer barrier / mbarrier hand-shake per 4 K steps (the 16-row version of round 1 spent 2.4 us per
+// stage on hand-shakes with the MMA warp idle 57 % of the time).
+// Grid: (row splits, [128-channel output tiles] x [input-channel tiles of kw <= 128]); one CTA per SM.
+// Bound: HBM reads rows*(2n + k)*2 bytes (X is re-read once per output tile, dZ / Y once per input tile: L2 hits when the
+// tiles of the same rows run side by side).
 #include "mlp_gemm.cuh"
 #include "tc_common.cuh"
 
@@ -40,20 +39,21 @@
 namespace pn2 {
 namespace {
 
-constexpr int WR = 16;            // rows per stage = K of one tcgen05.mma
+constexpr int WR = 64;            // rows per stage
+constexpr int WSUB = WR / 16;     // MMA K steps per stage
+constexpr int MT = 128;           // output channels per CTA = UMMA M
 constexpr int kWEpiWarps = 4, kWMmaWarp = 4, kWProdWarps = 8;
 constexpr int kWProdThreads = kWProdWarps * 32;
 constexpr int kWThreads = (kWEpiWarps + 1 + kWProdWarps) * 32;
 constexpr int kWSmem = 225 * 1024;
-constexpr int kMaxPieces = 10;    // cp.async pieces per producer thread per stage
+constexpr int kMaxKw = 128;   // wider tiles leave no room for a 3-stage raw ring next to the two T slots
 
 struct WgTc {
     WgradArgs a;
-    int mt;         // 128-wide output-channel tiles
-    int kw;         // input channels per CTA (multiple of 16, (2 mt + 1) * kw <= 512)
-    int n_c;        // n rounded up to 16
+    int kw;         // input channels per CTA (multiple of 16)
+    int gk;         // input-channel tiles; blockIdx.y = n_tile * gk + k_tile
     int nr, nt;     // raw ring depth, T ring depth
-    int tmem_cols;  // power of two >= (2 mt + 1) * kw
+    int tmem_cols;  // power of two >= kw
 };
 
 __device__ __forceinline__ void stsm_x4(uint32_t addr, const uint32_t (&r)[4]) {
@@ -74,19 +74,22 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* base = smem_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
-    const int k0 = blockIdx.y * w.kw;                 // first input channel of this CTA
+    const int n0 = (blockIdx.y / w.gk) * MT;          // first output channel of this CTA
+    const int k0 = (blockIdx.y % w.gk) * w.kw;        // first input channel
+    const int n_here = min(MT, p.n - n0);             // multiple of 8
+    const int nb = (n_here + 15) >> 4;                // 16-channel blocks of dZ / Y
     const int kw_here = min(w.kw, p.kp - k0);         // multiple of 16
-    const int n_pad = w.mt * 128;
-    const int ppr = (2 * w.n_c + w.kw) >> 3;          // 16-byte pieces per raw row
+    const int kb = kw_here >> 4;
+    const int ppr = (2 * MT + w.kw) >> 3;             // 16-byte pieces per raw row: [dZ 16][Y 16][X kw/8]
     const int rp = ppr * 16 + 16;                     // raw row pitch in bytes (odd number of 16-byte units)
     const int raw_bytes = WR * rp;
-    const int t_dz = 0, t_y = n_pad * 32, t_x16 = 2 * n_pad * 32, t_xbf = t_x16 + w.kw * 32;
-    const int t_bytes = t_xbf + w.kw * 32;            // one T slot: 32 bytes per channel per operand
+    const int sub_dy = MT * 32, sub_x = w.kw * 32;    // bytes of one 16-row sub-tile: 32 per channel
+    const int t_x = WSUB * sub_dy;                    // T slot = [4 x dY sub-tiles][4 x X' sub-tiles]
+    const int t_bytes = t_x + WSUB * sub_x;
     unsigned char* sRaw = base;
     unsigned char* sT = sRaw + ((w.nr * raw_bytes + 127) & ~127);
-    unsigned char* sOnes = sT + w.nt * t_bytes;       // 128 channels x 16 rows of fp16 ones
-    float* sCo = reinterpret_cast<float*>(sOnes + 4096);  // [3][n_pad] cA cB cC, then [2][kw] scale shift
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sCo + 3 * n_pad + 2 * w.kw);
+    float* sCo = reinterpret_cast<float*>(sT + w.nt * t_bytes);  // [3][MT] cA cB cC, then [2][kw] scale shift
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sCo + 3 * MT + 2 * w.kw);
     uint64_t* full = bars;            // [nt]
     uint64_t* empty = bars + w.nt;    // [nt]
     uint64_t* done = bars + 2 * w.nt;
@@ -96,16 +99,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
     const long long stages = (p.rows + WR - 1) / WR;
     const long long mine = blockIdx.x < stages ? (stages - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    for (int i = tid; i < 3 * n_pad; i += kWThreads) {
-        const int which = i / n_pad, c = i - which * n_pad;
-        sCo[i] = c < p.n ? (which == 0 ? p.cA : (which == 1 ? p.cB : p.cC))[c] : 0.f;
+    for (int i = tid; i < 3 * MT; i += kWThreads) {
+        const int which = i / MT, c = i - which * MT;
+        sCo[i] = c < n_here ? (which == 0 ? p.cA : (which == 1 ? p.cB : p.cC))[n0 + c] : 0.f;
     }
     for (int i = tid; i < 2 * w.kw; i += kWThreads) {
         const int which = i / w.kw, c = i - which * w.kw;
-        sCo[3 * n_pad + i] = (AFFINE && k0 + c < p.kp) ? (which == 0 ? p.in_scale : p.in_shift)[k0 + c] : 0.f;
+        sCo[3 * MT + i] = (AFFINE && c < kw_here) ? (which == 0 ? p.in_scale : p.in_shift)[k0 + c] : 0.f;
     }
-    for (int i = tid; i < 4096 / 4; i += kWThreads) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3C003C00u;  // fp16 1.0 x 2
-    // T tiles start zeroed: channel groups beyond n_c / kw_here are never written and must multiply as zero
+    // T tiles start zeroed: channel groups beyond n_here / kw_here are never written and must multiply as zero
     for (int i = tid; i < w.nt * t_bytes / 16; i += kWThreads) reinterpret_cast<uint4*>(sT)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
         for (int i = 0; i < w.nt; ++i) {
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    fence_proxy_async();  // the ones tile and the zeroed T tiles (generic-proxy stores) are read by the tensor core
+    fence_proxy_async();  // the zeroed T tiles (generic-proxy stores) are read by the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -131,21 +133,20 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         // ================================ producers ================================
         const int pt = tid - (kWMmaWarp + 1) * 32;   // 0..255
         const int pw = pt >> 5;                       // producer warp 0..7
-        // this thread's cp.async pieces of a stage: piece q = pt + 256 i  ->  (row, piece column), fixed for the kernel
-        int prow[kMaxPieces], ppc[kMaxPieces];
-        const int npieces = WR * ppr;
-#pragma unroll
-        for (int i = 0; i < kMaxPieces; ++i) {
-            const int q = pt + 256 * i;
-            prow[i] = q < npieces ? q / ppr : -1;
-            ppc[i] = q < npieces ? q - prow[i] * ppr : 0;
-        }
-        const int ncp = w.n_c >> 3;                   // pieces of dZ (= of Y) per row
         const uint32_t raw0 = smem_u32(sRaw), t0 = smem_u32(sT);
         const int D = w.nr - 2;  // a raw slot is refilled two iterations after it was transposed: one producer barrier in between
-        const int units = (2 * w.n_c + w.kw) >> 4;    // 16 x 16 blocks per stage
-        const int u_y = w.n_c >> 4, u_x = 2 * u_y;    // first Y unit, first X unit
-        const int units_x_valid = (kw_here + 15) >> 4;
+        // cp.async: warp pw brings rows pw, pw + 8, ...; a lane walks the USEFUL 16-byte pieces of a row -- the dZ and Y
+        // columns of this CTA's channel blocks and the X columns of its input-channel tile
+        const int nn8 = nb * 2, upr = 2 * nn8 + 2 * kb;  // pieces per row: [dZ nn8][Y nn8][X 2 kb]
+        // transposition: a warp owns sub-tile pw & 3 (16 rows) of channel blocks (pw >> 2), + 2, ... -- no per-unit
+        // index arithmetic, and the per-channel constants are fetched once per block
+        const int sub = pw & 3, blk0 = pw >> 2;
+        // ldmatrix lane address: matrix q = lane / 8 -> rows (q & 1) * 8 + lane % 8, columns + (q >> 1) * 8
+        const uint32_t ld_off = (uint32_t)(sub * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * rp + (lane >> 4) * 16;
+        // stmatrix lane address: core matrix of q: channel group + (q >> 1), K half q & 1, row lane % 8
+        const uint32_t st_off = (uint32_t)(lane >> 4) * 256 + ((lane >> 3) & 1) * 128 + (lane & 7) * 16;
+        // fragment of matrix q: channel blk*16 + (q >> 1)*8 + lane/4, rows sub*16 + (q & 1)*8 + 2*(lane%4) + {0,1}
+        const int ch_lo = lane >> 2, r_lo = sub * 16 + 2 * (lane & 3);
         long long i_s = blockIdx.x, p_s = blockIdx.x;
         int i_slot = 0, p_slot = 0, t_slot = 0;
         uint32_t t_phase = 0;
@@ -153,24 +154,29 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
             if (c < mine) {
                 const uint32_t st = raw0 + i_slot * raw_bytes;
                 const long long row0 = i_s * WR;
+                for (int j = lane; j < upr; j += 32) {
+                    int colbyte;            // byte offset of the piece inside the raw row
+                    const unsigned char* src;
+                    bool ok;
+                    if (j < nn8) {
+                        colbyte = j * 16; ok = j * 8 < n_here;
+                        src = reinterpret_cast<const unsigned char*>(p.dz + n0 + j * 8);
+                    } else if (j < 2 * nn8) {
+                        const int jj = j - nn8;
+                        colbyte = 256 + jj * 16; ok = jj * 8 < n_here;
+                        src = reinterpret_cast<const unsigned char*>(p.y + n0 + jj * 8);
+                    } else {
+                        const int jj = j - 2 * nn8;
+                        colbyte = 512 + jj * 16; ok = true;
+                        src = reinterpret_cast<const unsigned char*>(p.x + k0 + jj * 8);
+                    }
+                    const long long ldb = 2LL * (j < nn8 ? p.dz_ld : (j < 2 * nn8 ? p.y_ld : p.x_ld));  // row pitch in bytes
 #pragma unroll
-                for (int i = 0; i < kMaxPieces; ++i) {
-                    if (prow[i] >= 0) {
-                        const long long row = row0 + prow[i];
-                        const int pc = ppc[i];
-                        const void* src;
-                        bool ok = row < p.rows;
-                        if (pc < ncp) {
-                            ok = ok && pc * 8 < p.n;
-                            src = p.dz + (ok ? row * p.dz_ld + pc * 8 : 0);
-                        } else if (pc < 2 * ncp) {
-                            ok = ok && (pc - ncp) * 8 < p.n;
-                            src = p.y + (ok ? row * p.y_ld + (pc - ncp) * 8 : 0);
-                        } else {
-                            ok = ok && (pc - 2 * ncp) * 8 < kw_here;
-                            src = p.x + (ok ? row * p.x_ld + k0 + (pc - 2 * ncp) * 8 : 0);
-                        }
-                        cp_async16_s(st + prow[i] * rp + pc * 16, src, ok ? 16 : 0);
+                    for (int r = 0; r < WR / kWProdWarps; ++r) {
+                        const int prow = pw + r * kWProdWarps;
+                        const long long row = row0 + prow;
+                        const bool in = ok && row < p.rows;   // past the end / padded half block: zero-fill
+                        cp_async16_s(st + prow * rp + colbyte, in ? src + row * ldb : src, in ? 16 : 0);
                     }
                 }
                 i_s += gridDim.x;
@@ -181,49 +187,63 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                 switch (D) {  // this thread's pieces of stage c - D have landed
                     case 1: cp_wait<1>(); break;
                     case 2: cp_wait<2>(); break;
-                    case 3: cp_wait<3>(); break;
-                    case 4: cp_wait<4>(); break;
-                    case 5: cp_wait<5>(); break;
-                    default: cp_wait<6>(); break;
+                    default: cp_wait<3>(); break;
                 }
                 prod_bar();                                  // ... and everybody else's
                 mbar_wait(&empty[t_slot], t_phase ^ 1);      // the MMAs that read this T slot have completed
-                const uint32_t rs = raw0 + p_slot * raw_bytes;
-                const uint32_t ts = t0 + t_slot * t_bytes;
+                const uint32_t rs = raw0 + p_slot * raw_bytes + ld_off;
+                const uint32_t ts = t0 + t_slot * t_bytes + st_off;
                 const long long srow0 = p_s * WR;
-                // ldmatrix lane address: matrix q = lane / 8 -> rows (q & 1) * 8 + lane % 8, columns + (q >> 1) * 8
-                const uint32_t ld_off = (uint32_t)(((lane >> 3) & 1) * 8 + (lane & 7)) * rp + (lane >> 4) * 16;
-                // stmatrix lane address: core matrix of q: channel group + (q >> 1), K half q & 1, row lane % 8
-                const uint32_t st_off = (uint32_t)(lane >> 4) * 256 + ((lane >> 3) & 1) * 128 + (lane & 7) * 16;
-                for (int u = pw; u < units; u += kWProdWarps) {
-                    if (u >= u_x && u - u_x >= units_x_valid) break;  // padding of the X block
-                    uint32_t r[4];
-                    ldsm_x4_trans(r, rs + u * 32 + ld_off);
-                    if (u < u_x) {  // dZ / Y: straight through
-                        const uint32_t dst = ts + (u < u_y ? t_dz + u * 512 : t_y + (u - u_y) * 512);
-                        stsm_x4(dst + st_off, r);
-                    } else {
-                        const int ux = u - u_x;
-                        // fragment of matrix q: channel ux*16 + (q >> 1)*8 + lane/4, rows (q & 1)*8 + 2*(lane%4) + {0,1}
-                        uint32_t r16[4], rbf[4];
+                // rows past the end were zero-filled and must contribute nothing (cC and the ReLU shift alone are not
+                // zero): only the last stage can hold any
+                const int valid = (int)min((long long)WR, p.rows - srow0) - r_lo;  // this thread's rows r_lo + {0,1,8,9} < valid?
+                const bool tail = srow0 + WR > p.rows;
+                for (int blk = blk0; blk < nb; blk += 2) {
+                    const int ch = blk * 16 + ch_lo;
+                    const float ca0 = sCo[ch], cb0 = sCo[MT + ch], cc0 = sCo[2 * MT + ch];
+                    const float ca1 = sCo[ch + 8], cb1 = sCo[MT + ch + 8], cc1 = sCo[2 * MT + ch + 8];
+                    uint32_t rz[4], ry[4], o[4];
+                    ldsm_x4_trans(rz, rs + blk * 32);
+                    ldsm_x4_trans(ry, rs + 256 + blk * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float ca = (q >> 1) ? ca1 : ca0, cb = (q >> 1) ? cb1 : cb0, cc = (q >> 1) ? cc1 : cc0;
+                        const float2 dz = bf2_to_f2(rz[q]), yy = h2_to_f2(ry[q]);
+                        float v0 = fmaf(ca, dz.x, fmaf(cb, yy.x, cc)), v1 = fmaf(ca, dz.y, fmaf(cb, yy.y, cc));
+                        if (tail) {
+                            if ((q & 1) * 8 >= valid) v0 = 0.f;
+                            if ((q & 1) * 8 + 1 >= valid) v1 = 0.f;
+                        }
+                        o[q] = f2_to_bf2(v0, v1);
+                    }
+                    stsm_x4(ts + sub * sub_dy + blk * 512, o);
+                }
+                for (int blk = blk0; blk < kb; blk += 2) {
+                    uint32_t r[4], o[4];
+                    ldsm_x4_trans(r, rs + 512 + blk * 32);
+                    if (AFFINE) {
+                        const int ch = blk * 16 + ch_lo;
+                        const float sc0 = sCo[3 * MT + ch], sh0 = sCo[3 * MT + w.kw + ch];
+                        const float sc1 = sCo[3 * MT + ch + 8], sh1 = sCo[3 * MT + w.kw + ch + 8];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const int ch = ux * 16 + (q >> 1) * 8 + (lane >> 2);
-                            const long long row = srow0 + (q & 1) * 8 + 2 * (lane & 3);
-                            float2 v = h2_to_f2(r[q]);
-                            if (AFFINE) {
-                                const float sc = sCo[3 * n_pad + ch], sh = sCo[3 * n_pad + w.kw + ch];
-                                v.x = fmaxf(fmaf(v.x, sc, sh), 0.f);
-                                v.y = fmaxf(fmaf(v.y, sc, sh), 0.f);
+                            const float sc = (q >> 1) ? sc1 : sc0, sh = (q >> 1) ? sh1 : sh0;
+                            const float2 v = h2_to_f2(r[q]);
+                            float v0 = fmaxf(fmaf(v.x, sc, sh), 0.f), v1 = fmaxf(fmaf(v.y, sc, sh), 0.f);
+                            if (tail) {
+                                if ((q & 1) * 8 >= valid) v0 = 0.f;
+                                if ((q & 1) * 8 + 1 >= valid) v1 = 0.f;
                             }
-                            if (row >= p.rows) v.x = 0.f;          // zero-filled rows must stay zero through the ReLU shift
-                            if (row + 1 >= p.rows) v.y = 0.f;
-                            r16[q] = f2_to_h2(v.x, v.y);
-                            rbf[q] = f2_to_bf2(v.x, v.y);
+                            o[q] = f2_to_bf2(v0, v1);
                         }
-                        stsm_x4(ts + t_x16 + ux * 512 + st_off, r16);
-                        stsm_x4(ts + t_xbf + ux * 512 + st_off, rbf);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 v = h2_to_f2(r[q]);
+                            o[q] = f2_to_bf2(v.x, v.y);
+                        }
                     }
+                    stsm_x4(ts + t_x + sub * sub_x + blk * 512, o);
                 }
                 fence_proxy_async();
                 mbar_arrive(&full[t_slot]);
@@ -234,11 +254,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         }
     } else if (warp == kWMmaWarp) {
         // ================================ MMA issuer ================================
-        // A = dZ^T / Y^T / 1^T (M = output channels), B = X'^T (N = input channels): K-major after the transposition
-        const uint32_t idesc_bf = umma_idesc2(1u, 1u, false, false, 128, kw_here);
-        const uint32_t idesc_h = umma_idesc2(0u, 0u, false, false, 128, kw_here);
-        const uint32_t g2_col = w.mt * w.kw, g3_col = 2 * w.mt * w.kw;
-        const uint64_t ones_desc = umma_desc_k_noswz(smem_u32(sOnes));
+        // A = dY^T (M = output channels), B = X'^T (N = input channels): K-major after the transposition
+        const uint32_t idesc = umma_idesc2(1u, 1u, false, false, MT, kw_here);
         int slot = 0;
         uint32_t phase = 0;
         for (long long c = 0; c < mine; ++c) {
@@ -246,13 +263,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t ts = smem_u32(sT + slot * t_bytes);
-                const uint64_t x16 = umma_desc_k_noswz(ts + t_x16), xbf = umma_desc_k_noswz(ts + t_xbf);
-                const uint32_t acc = c != 0;
-                for (int m = 0; m < w.mt; ++m) {
-                    umma_f16(tmem_base + m * w.kw, umma_desc_k_noswz(ts + t_dz + m * 4096), xbf, idesc_bf, acc);
-                    umma_f16(tmem_base + g2_col + m * w.kw, umma_desc_k_noswz(ts + t_y + m * 4096), x16, idesc_h, acc);
-                }
-                umma_f16(tmem_base + g3_col, ones_desc, x16, idesc_h, acc);
+#pragma unroll
+                for (int s = 0; s < WSUB; ++s)
+                    umma_f16(tmem_base, umma_desc_k_noswz(ts + s * sub_dy), umma_desc_k_noswz(ts + t_x + s * sub_x), idesc,
+                             (c | s) != 0);
                 tc_commit(&empty[slot]);
                 if (c == mine - 1) tc_commit(done);
             }
@@ -261,34 +275,26 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         }
     } else if (mine > 0) {
         // ================================ epilogue ================================
-        mbar_wait(done, 0);
+        mbar_wait_backoff(done, 0);  // the whole main loop lies in between: poll sparsely
         tc_fence_after();
         const bool vec4 = (p.dw_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;  // 16-byte aligned rows
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        const uint32_t g2_col = w.mt * w.kw, g3_col = 2 * w.mt * w.kw;
-        for (int c16 = 0; c16 < kw_here; c16 += 16) {
-            uint32_t g3[32];
-            tmem_ld16(tmem_base + lane_base + g3_col + c16, g3);  // every lane holds the same row: 1^T X'
-            for (int m = 0; m < w.mt; ++m) {
-                if (m * 128 + warp * 32 >= p.n) continue;  // warp-uniform
-                const int n = m * 128 + warp * 32 + lane;  // output channel of this thread (TMEM lane)
-                uint32_t g1[32], g2[32];
-                tmem_ld16(tmem_base + lane_base + m * w.kw + c16, g1);
-                tmem_ld16(tmem_base + lane_base + g2_col + m * w.kw + c16, g2);
+        const int n = n0 + warp * 32 + lane;  // output channel of this thread (TMEM lane)
+        if (warp * 32 < n_here) {             // warp-uniform
+            for (int c16 = 0; c16 < kw_here; c16 += 16) {
+                uint32_t g[32];
+                tmem_ld16(tmem_base + lane_base + c16, g);
                 if (n < p.n) {
-                    const float ca = sCo[n], cb = sCo[n_pad + n], cc = sCo[2 * n_pad + n];
                     float* dst = p.dw + (size_t)n * p.dw_ld + k0 + c16;
-                    float g[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        g[e] = fmaf(ca, __uint_as_float(g1[e]), fmaf(cb, __uint_as_float(g2[e]), cc * __uint_as_float(g3[e])));
                     if (vec4 && k0 + c16 + 16 <= p.k_true) {
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) red_add_v4(dst + e, g[e], g[e + 1], g[e + 2], g[e + 3]);
+                        for (int e = 0; e < 16; e += 4)
+                            red_add_v4(dst + e, __uint_as_float(g[e]), __uint_as_float(g[e + 1]), __uint_as_float(g[e + 2]),
+                                       __uint_as_float(g[e + 3]));
                     } else {
 #pragma unroll
                         for (int e = 0; e < 16; ++e)
-                            if (k0 + c16 + e < p.k_true && g[e] != 0.f) atomicAdd(dst + e, g[e]);
+                            if (k0 + c16 + e < p.k_true && g[e] != 0u) atomicAdd(dst + e, __uint_as_float(g[e]));
                     }
                 }
             }
@@ -309,61 +315,51 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
 bool wgrad_use_tc() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("PN2_WGRAD_IMPL");
-        v = (e && strcmp(e, "tc") == 0) ? 1 : 0;
+        const char* e = getenv("PN2_WGRAD_IMPL");  // tc (default) | mma: the warp-level mma.sync kernel of mlp_gemm.cu
+        v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
     }
     return v == 1;
 }
 
-bool wgrad_tc_supported(const WgradArgs& a) { return a.n <= 512 && a.kp % 32 == 0 && a.n % 8 == 0; }
+bool wgrad_tc_supported(const WgradArgs& a) { return a.kp % 16 == 0 && a.n % 8 == 0; }
 
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
     WgTc w;
     w.a = a;
-    w.mt = (a.n + 127) / 128;
-    w.n_c = (a.n + 15) / 16 * 16;
-    int kw_max = 512 / (2 * w.mt + 1) / 16 * 16;
-    if (kw_max > 256) kw_max = 256;
-    const int ky = (a.kp + kw_max - 1) / kw_max;
-    w.kw = ((a.kp + ky - 1) / ky + 15) / 16 * 16;  // even split, multiple of 16, <= kw_max
-    if (w.kw > kw_max) w.kw = kw_max;
-    const int gy = (a.kp + w.kw - 1) / w.kw;
-    const int cols = (2 * w.mt + 1) * w.kw;
+    const int gn = (a.n + MT - 1) / MT;
+    w.gk = (a.kp + kMaxKw - 1) / kMaxKw;
+    w.kw = ((a.kp + w.gk - 1) / w.gk + 15) / 16 * 16;  // even split, multiple of 16, <= kMaxKw
+    w.gk = (a.kp + w.kw - 1) / w.kw;
+    const int gy = gn * w.gk;
     w.tmem_cols = 32;
-    while (w.tmem_cols < cols) w.tmem_cols <<= 1;
-    const int ppr = (2 * w.n_c + w.kw) / 8;
-    if (WR * ppr > kMaxPieces * kWProdThreads) return fail_arg("pn2_mlp_gemm_wgrad", "row too wide for the tcgen05 kernel");
+    while (w.tmem_cols < w.kw) w.tmem_cols <<= 1;
+    const int ppr = (2 * MT + w.kw) / 8;
     const size_t raw = (size_t)WR * (ppr * 16 + 16);
-    const size_t tb = (size_t)(2 * w.mt * 128 + 2 * w.kw) * 32;
-    const size_t fixed = 4096 + (size_t)(3 * w.mt * 128 + 2 * w.kw) * 4 + 256 + 256;
-    // T ring: 3 slots (the tensor core is at most two stages behind); raw ring: what is left, 3..8 slots
-    w.nt = 3;
+    const size_t tb = (size_t)WSUB * (MT + w.kw) * 32;
+    const size_t fixed = (size_t)(3 * MT + 2 * w.kw) * 4 + 256 + 256;
+    // T ring: 2 slots (the tensor core is at most one stage behind); raw ring: what is left, 3..5 slots
+    w.nt = 2;
     long long nr = ((long long)kWSmem - (long long)fixed - (long long)w.nt * (long long)tb) / (long long)raw;
-    if (nr > 8) nr = 8;
-    if (nr < 3) {
-        w.nt = 2;
-        nr = ((long long)kWSmem - (long long)fixed - (long long)w.nt * (long long)tb) / (long long)raw;
-        if (nr > 8) nr = 8;
-        if (nr < 3) return fail_arg("pn2_mlp_gemm_wgrad", "stage does not fit shared memory");
-    }
+    if (nr > 5) nr = 5;
+    if (nr < 3) return fail_arg("pn2_mlp_gemm_wgrad", "stage does not fit shared memory");
     w.nr = (int)nr;
     const size_t smem = fixed + ((w.nr * raw + 127) / 128 * 128) + w.nt * tb;
-    static bool configured = false;
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool configured[64] = {};
+    static int sms[64] = {};
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev]) {  // per device: the attribute belongs to the device's copy of the function
         PN2_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem),
                   "wgrad_tc: cudaFuncSetAttribute");
         PN2_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem),
                   "wgrad_tc: cudaFuncSetAttribute");
-        configured = true;
-    }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = 148;
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        configured[dev] = true;
     }
     const long long stages = (a.rows + WR - 1) / WR;
-    long long gx = sms / gy;
+    long long gx = sms[dev] / gy;
     if (gx < 1) gx = 1;
     if (gx > stages) gx = stages;
     if (a.in_scale)

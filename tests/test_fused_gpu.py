@@ -232,8 +232,9 @@ def test_prep_weights_multi_matches_single(lib, cuda):
         assert torch.equal(a, b)
 
 
-def test_wgrad_tcgen05_opt_in_matches_fp32():
-    """The opt-in tcgen05 weight-gradient kernel (PN2_WGRAD_IMPL=tc is read once per process -> subprocess)."""
+def test_wgrad_mma_sync_cross_check_matches_fp32():
+    """The warp-level mma.sync weight-gradient kernel kept as the cross-check of the tcgen05 one (PN2_WGRAD_IMPL=mma is
+    read once per process -> subprocess)."""
     import os
     import subprocess
     import sys
@@ -259,7 +260,7 @@ for R, N, KP, KT, affine in [(3000, 384, 128, 128, True), (2000, 128, 416, 387, 
 print('ok')
 """
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PN2_WGRAD_IMPL="tc", PYTHONPATH=root)
+    env = dict(os.environ, PN2_WGRAD_IMPL="mma", PYTHONPATH=root)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
@@ -323,7 +324,8 @@ def test_bn_bwd_coefs_and_gemm_dgrad(lib, cuda, R, N, K, mask):
 
 @pytest.mark.parametrize("R,N,KP,KT,affine", [(1000, 32, 32, 3, False), (5000, 64, 96, 67, False), (999, 128, 128, 128, True),
                                                (4096, 384, 128, 128, True), (2000, 128, 416, 387, False),
-                                               (300, 512, 128, 128, True)])
+                                               (300, 512, 128, 128, True), (70000, 128, 832, 771, False), (63, 256, 640, 640, False),
+                                               (131072, 384, 128, 128, True), (20001, 64, 64, 64, True)])
 def test_gemm_wgrad(lib, cuda, R, N, KP, KT, affine):
     g = torch.Generator(device="cpu").manual_seed(R + N + KP)
     dz = torch.randn(R, N, generator=g).to(cuda).to(BF)
