@@ -239,9 +239,16 @@ __device__ __forceinline__ void nn_weights(const float* d2, float (&w)[3]) {
     for (int j = 0; j < 3; ++j) w[j] = __fdiv_rn(r[j], norm);
 }
 
-__global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildArgs a) {
+// A (sub-)warp per row: lane l of the row's lane group owns 8-channel pieces l, l + lanes, ... of the COARSE feature rows --
+// three 16-byte gathers (the three neighbours) per piece, the producer's BatchNorm+ReLU applied on the fly, one
+// interpolation per channel (interpolate_gpu.cu:168 rounding order) -- and writes them at output columns
+// skip_c + 8 piece: one 16-byte store when skip_c is a multiple of 8, else eight 2-byte stores (FP1: the skip is the three
+// coordinates).  The skip columns and the zero padding are copied by the same lanes afterwards.
+__global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildArgs a, int lanes) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int rpw = 32 / lanes;                      // rows per warp
+    const int l = lane & (lanes - 1);
+    const long long row = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * rpw + lane / lanes;
     const long long total = (long long)a.b * a.n;
     if (row >= total) return;
     const int b = (int)(row / a.n);
@@ -253,12 +260,55 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
         nn_weights(a.dist2 + row * 3, w);
     }
     const int sc = a.skip.p ? a.skip.c : 0;
+    const int cc = a.coarse.c;
     act_t* o = a.out + (size_t)row * a.out_ld;
-    for (int col = lane; col < a.out_ld; col += 32) {
+    act_t* ol = a.out_lo ? a.out_lo + (size_t)row * a.out_ld : nullptr;
+    const bool cvec = (cc & 7) == 0 && (a.coarse.ld & 7) == 0;
+    if (cvec) {
+        const size_t r0 = (size_t)b * a.s + id[0], r1 = (size_t)b * a.s + id[1], r2 = (size_t)b * a.s + id[2];
+        for (int cp = l; cp < (cc >> 3); cp += lanes) {
+            float v[8];
+            if (a.s > 1) {
+                float p0[8], p1[8], p2[8];
+                row_vals8(a.coarse, r0, cp * 8, p0);
+                row_vals8(a.coarse, r1, cp * 8, p1);
+                row_vals8(a.coarse, r2, cp * 8, p2);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(w[2], p2[e], fmaf(w[0], p0[e], w[1] * p1[e]));
+            } else {
+                row_vals8(a.coarse, (size_t)b, cp * 8, v);
+            }
+            uint4 q, ql;
+            uint32_t* qq = reinterpret_cast<uint32_t*>(&q);
+            uint32_t* qlw = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                qq[e] = f2_to_h2(fminf(fmaxf(v[2 * e], -65504.f), 65504.f), fminf(fmaxf(v[2 * e + 1], -65504.f), 65504.f));
+                const float2 back = h2_to_f2(qq[e]);
+                qlw[e] = f2_to_h2(v[2 * e] - back.x, v[2 * e + 1] - back.y);
+            }
+            const int col = sc + cp * 8;
+            if ((sc & 7) == 0) {
+                *reinterpret_cast<uint4*>(o + col) = q;
+                if (ol) *reinterpret_cast<uint4*>(ol + col) = ql;
+            } else {
+                const act_t* qh = reinterpret_cast<const act_t*>(&q);
+                const act_t* qlh = reinterpret_cast<const act_t*>(&ql);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[col + e] = qh[e];
+                    if (ol) ol[col + e] = qlh[e];
+                }
+            }
+        }
+    }
+    // skip columns, (non-vectorisable coarse columns,) zero padding
+    for (int col = l; col < a.out_ld; col += lanes) {
         float v = 0.f;
         if (col < sc) {
             v = row_val(a.skip, (size_t)row, col);
-        } else if (col < sc + a.coarse.c) {
+        } else if (col < sc + cc) {
+            if (cvec) continue;
             const int ch = col - sc;
             if (a.s > 1) {
                 const float p0 = row_val(a.coarse, (size_t)b * a.s + id[0], ch);
@@ -271,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
         }
         const act_t h = f_to_h(v);
         o[col] = h;
-        if (a.out_lo) a.out_lo[(size_t)row * a.out_ld + col] = f_to_h(v - h_to_f(h));
+        if (ol) ol[col] = f_to_h(v - h_to_f(h));
     }
 }
 
@@ -296,13 +346,18 @@ struct PoolArgs {
 // (group-all, the 21 joints) so that the work still spreads over >= 256 CTAs.
 template <int GT>
 __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
+    // A warp reads a group's rows as 16-byte pieces: lane = (row lane rl = lane / 8, piece pc = lane % 8 of the 64-channel
+    // chunk); row lane rl takes rows rl, rl + 4, ... (8 independent 16-byte loads per plane in flight at K = 32), the four
+    // row lanes are combined by shuffles (first maximum in row order wins, as a sequential scan would have it).
     __shared__ float tile[GT][65];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pc = lane & 7, rl = lane >> 3;
     const int b = blockIdx.z, c0 = blockIdx.y * 64;
-    const int ch = c0 + lane * 2;
-    const bool ok = ch < a.c;  // c is even (multiple of 8)
-    float sc0 = 0.f, sc1 = 0.f, sh0 = 0.f, sh1 = 0.f;
-    if (ok) { sc0 = a.scale[ch]; sc1 = a.scale[ch + 1]; sh0 = a.shift[ch]; sh1 = a.shift[ch + 1]; }
+    const int ch = c0 + pc * 8;
+    const bool ok = ch < a.c;  // c is a multiple of 8
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = ok ? a.scale[ch + e] : 0.f; sh[e] = ok ? a.shift[ch + e] : 0.f; }
     float csum[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) csum[j] = 0.f;
@@ -311,27 +366,51 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
         const int s0 = t * GT;
         for (int gi = warp; gi < GT; gi += 8) {
             const int s = s0 + gi;
-            float m0 = -1.f, m1 = -1.f;  // below every ReLU output: the first row always wins
-            int i0 = 0, i1 = 0;
+            float m[8];
+            int mi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { m[e] = -1.f; mi[e] = 0x7fffffff; }  // below every ReLU output
             if (ok && s < a.s) {
                 const act_t* yr = a.y + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch;
                 const act_t* yl = a.y_lo ? a.y_lo + ((size_t)(b * a.s + s) * a.k) * a.y_ld + ch : nullptr;
 #pragma unroll 4
-                for (int kk = 0; kk < a.k; ++kk) {
-                    const float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
-                    float r0 = fmaxf(fmaf(v.x, sc0, sh0), 0.f), r1 = fmaxf(fmaf(v.y, sc1, sh1), 0.f);
-                    if (yl) {  // two-plane rows: ReLU decided on the hi plane (what pool_bwd masks by), value from hi + lo
-                        const float2 l = h2_to_f2(*reinterpret_cast<const uint32_t*>(yl + (size_t)kk * a.y_ld));
-                        r0 = r0 > 0.f ? fmaf(v.x + l.x, sc0, sh0) : 0.f;
-                        r1 = r1 > 0.f ? fmaf(v.y + l.y, sc1, sh1) : 0.f;
+                for (int kk = rl; kk < a.k; kk += 4) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(yr + (size_t)kk * a.y_ld));
+                    uint4 ql = make_uint4(0u, 0u, 0u, 0u);
+                    if (yl) ql = __ldg(reinterpret_cast<const uint4*>(yl + (size_t)kk * a.y_ld));
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(&q);
+                    const uint32_t* wl = reinterpret_cast<const uint32_t*>(&ql);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = h2_to_f2(w[e]);
+                        const float2 fl = h2_to_f2(wl[e]);
+                        // two-plane rows: ReLU decided on the hi plane (what pool_bwd masks by), value from hi + lo
+                        const float r0 = fmaf(f.x, sc[2 * e], sh[2 * e]) > 0.f ? fmaf(f.x + fl.x, sc[2 * e], sh[2 * e]) : 0.f;
+                        const float r1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]) > 0.f
+                                             ? fmaf(f.y + fl.y, sc[2 * e + 1], sh[2 * e + 1]) : 0.f;
+                        if (r0 > m[2 * e]) { m[2 * e] = r0; mi[2 * e] = kk; }
+                        if (r1 > m[2 * e + 1]) { m[2 * e + 1] = r1; mi[2 * e + 1] = kk; }
                     }
-                    if (r0 > m0) { m0 = r0; i0 = kk; }
-                    if (r1 > m1) { m1 = r1; i1 = kk; }
                 }
-                if (a.argmax) *reinterpret_cast<int2*>(a.argmax + ((size_t)b * a.s + s) * a.c + ch) = make_int2(i0, i1);
             }
-            tile[gi][lane * 2] = m0;
-            tile[gi][lane * 2 + 1] = m1;
+#pragma unroll
+            for (int o = 8; o < 32; o <<= 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float v = __shfl_xor_sync(kFull, m[e], o);
+                    const int vi = __shfl_xor_sync(kFull, mi[e], o);
+                    if (v > m[e] || (v == m[e] && vi < mi[e])) { m[e] = v; mi[e] = vi; }
+                }
+            }
+            if (rl == 0) {
+                if (ok && s < a.s && a.argmax) {
+                    int* am = a.argmax + ((size_t)b * a.s + s) * a.c + ch;
+                    *reinterpret_cast<int4*>(am) = make_int4(mi[0], mi[1], mi[2], mi[3]);
+                    *reinterpret_cast<int4*>(am + 4) = make_int4(mi[4], mi[5], mi[6], mi[7]);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) tile[gi][pc * 8 + e] = m[e];
+            }
         }
         __syncthreads();
         if (lane < GT) {
@@ -897,7 +976,9 @@ extern "C" int pn2_fp_build_rows_x2(int b, int n, int s, const void* skip, const
     a.skip = mk_src(skip, skip_lo, skip_c, skip_ld, skip_scale, skip_shift);
     a.coarse = mk_src(coarse, coarse_lo, coarse_c, coarse_ld, coarse_scale, coarse_shift);
     a.idx = idx; a.dist2 = dist2; a.out = (act_t*)out; a.out_lo = (act_t*)out_lo; a.out_ld = out_ld;
-    fp_build_rows_kernel<<<warp_blocks((long long)b * n), kThreads, 0, (cudaStream_t)stream>>>(a);
+    int lanes = 32;  // lanes per row: the smallest power of two covering the 8-channel pieces of a coarse row
+    while (lanes > 4 && lanes / 2 >= (coarse_c + 7) / 8) lanes >>= 1;
+    fp_build_rows_kernel<<<warp_blocks(((long long)b * n + 32 / lanes - 1) / (32 / lanes)), kThreads, 0, (cudaStream_t)stream>>>(a, lanes);
     PN2_CHECK_LAUNCH("fp_build_rows_kernel");
     return 0;
 }

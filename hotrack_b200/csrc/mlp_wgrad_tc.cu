@@ -39,7 +39,7 @@
 namespace pn2 {
 namespace {
 
-constexpr int WR = 64;            // rows per stage
+constexpr int WR = 64;            // rows per stage (32-row stages measured slower: the per-stage hand-shakes dominate)
 constexpr int WSUB = WR / 16;     // MMA K steps per stage
 constexpr int MT = 128;           // output channels per CTA = UMMA M
 constexpr int kWEpiWarps = 4, kWMmaWarp = 4, kWProdWarps = 8;
@@ -138,15 +138,18 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         // cp.async: warp pw brings rows pw, pw + 8, ...; a lane walks the USEFUL 16-byte pieces of a row -- the dZ and Y
         // columns of this CTA's channel blocks and the X columns of its input-channel tile
         const int nn8 = nb * 2, upr = 2 * nn8 + 2 * kb;  // pieces per row: [dZ nn8][Y nn8][X 2 kb]
-        // transposition: a warp owns sub-tile pw & 3 (16 rows) of channel blocks (pw >> 2), + 2, ... -- no per-unit
-        // index arithmetic, and the per-channel constants are fetched once per block
-        const int sub = pw & 3, blk0 = pw >> 2;
+        // transposition: a warp owns the sub-tile PAIR pw & 1 (2 x 16 rows) of channel blocks pw >> 1, + 4, ...: no per-unit
+        // index arithmetic, the per-channel constants are fetched once per block, and the two sub-tiles are two
+        // independent ldmatrix -> arithmetic -> stmatrix chains in flight per warp
+        static_assert(WSUB == 4 && kWProdWarps == 8, "the warp -> (sub-tile pair, block) map assumes 4 sub-tiles, 8 warps");
+        const int sub0 = (pw & 1) * 2, blk0 = pw >> 1;
+        constexpr int kBlkStep = 4;
         // ldmatrix lane address: matrix q = lane / 8 -> rows (q & 1) * 8 + lane % 8, columns + (q >> 1) * 8
-        const uint32_t ld_off = (uint32_t)(sub * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * rp + (lane >> 4) * 16;
+        const uint32_t ld_off = (uint32_t)(sub0 * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * rp + (lane >> 4) * 16;
         // stmatrix lane address: core matrix of q: channel group + (q >> 1), K half q & 1, row lane % 8
         const uint32_t st_off = (uint32_t)(lane >> 4) * 256 + ((lane >> 3) & 1) * 128 + (lane & 7) * 16;
         // fragment of matrix q: channel blk*16 + (q >> 1)*8 + lane/4, rows sub*16 + (q & 1)*8 + 2*(lane%4) + {0,1}
-        const int ch_lo = lane >> 2, r_lo = sub * 16 + 2 * (lane & 3);
+        const int ch_lo = lane >> 2, r_lo = sub0 * 16 + 2 * (lane & 3);
         long long i_s = blockIdx.x, p_s = blockIdx.x;
         int i_slot = 0, p_slot = 0, t_slot = 0;
         uint32_t t_phase = 0;
@@ -187,7 +190,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                 switch (D) {  // this thread's pieces of stage c - D have landed
                     case 1: cp_wait<1>(); break;
                     case 2: cp_wait<2>(); break;
-                    default: cp_wait<3>(); break;
+                    case 3: cp_wait<3>(); break;
+                    default: cp_wait<4>(); break;
                 }
                 prod_bar();                                  // ... and everybody else's
                 mbar_wait(&empty[t_slot], t_phase ^ 1);      // the MMAs that read this T slot have completed
@@ -198,52 +202,64 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                 // zero): only the last stage can hold any
                 const int valid = (int)min((long long)WR, p.rows - srow0) - r_lo;  // this thread's rows r_lo + {0,1,8,9} < valid?
                 const bool tail = srow0 + WR > p.rows;
-                for (int blk = blk0; blk < nb; blk += 2) {
+                for (int blk = blk0; blk < nb; blk += kBlkStep) {
                     const int ch = blk * 16 + ch_lo;
                     const float ca0 = sCo[ch], cb0 = sCo[MT + ch], cc0 = sCo[2 * MT + ch];
                     const float ca1 = sCo[ch + 8], cb1 = sCo[MT + ch + 8], cc1 = sCo[2 * MT + ch + 8];
-                    uint32_t rz[4], ry[4], o[4];
-                    ldsm_x4_trans(rz, rs + blk * 32);
-                    ldsm_x4_trans(ry, rs + 256 + blk * 32);
+                    uint32_t rz[2][4], ry[2][4], o[2][4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float ca = (q >> 1) ? ca1 : ca0, cb = (q >> 1) ? cb1 : cb0, cc = (q >> 1) ? cc1 : cc0;
-                        const float2 dz = bf2_to_f2(rz[q]), yy = h2_to_f2(ry[q]);
-                        float v0 = fmaf(ca, dz.x, fmaf(cb, yy.x, cc)), v1 = fmaf(ca, dz.y, fmaf(cb, yy.y, cc));
-                        if (tail) {
-                            if ((q & 1) * 8 >= valid) v0 = 0.f;
-                            if ((q & 1) * 8 + 1 >= valid) v1 = 0.f;
-                        }
-                        o[q] = f2_to_bf2(v0, v1);
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        ldsm_x4_trans(rz[s2], rs + s2 * 16 * rp + blk * 32);
+                        ldsm_x4_trans(ry[s2], rs + s2 * 16 * rp + 256 + blk * 32);
                     }
-                    stsm_x4(ts + sub * sub_dy + blk * 512, o);
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float ca = (q >> 1) ? ca1 : ca0, cb = (q >> 1) ? cb1 : cb0, cc = (q >> 1) ? cc1 : cc0;
+                            const float2 dz = bf2_to_f2(rz[s2][q]), yy = h2_to_f2(ry[s2][q]);
+                            float v0 = fmaf(ca, dz.x, fmaf(cb, yy.x, cc)), v1 = fmaf(ca, dz.y, fmaf(cb, yy.y, cc));
+                            if (tail) {
+                                if (s2 * 16 + (q & 1) * 8 >= valid) v0 = 0.f;
+                                if (s2 * 16 + (q & 1) * 8 + 1 >= valid) v1 = 0.f;
+                            }
+                            o[s2][q] = f2_to_bf2(v0, v1);
+                        }
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) stsm_x4(ts + (sub0 + s2) * sub_dy + blk * 512, o[s2]);
                 }
-                for (int blk = blk0; blk < kb; blk += 2) {
-                    uint32_t r[4], o[4];
-                    ldsm_x4_trans(r, rs + 512 + blk * 32);
+                for (int blk = blk0; blk < kb; blk += kBlkStep) {
+                    uint32_t r[2][4], o[2][4];
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) ldsm_x4_trans(r[s2], rs + s2 * 16 * rp + 512 + blk * 32);
                     if (AFFINE) {
                         const int ch = blk * 16 + ch_lo;
                         const float sc0 = sCo[3 * MT + ch], sh0 = sCo[3 * MT + w.kw + ch];
                         const float sc1 = sCo[3 * MT + ch + 8], sh1 = sCo[3 * MT + w.kw + ch + 8];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float sc = (q >> 1) ? sc1 : sc0, sh = (q >> 1) ? sh1 : sh0;
-                            const float2 v = h2_to_f2(r[q]);
-                            float v0 = fmaxf(fmaf(v.x, sc, sh), 0.f), v1 = fmaxf(fmaf(v.y, sc, sh), 0.f);
-                            if (tail) {
-                                if ((q & 1) * 8 >= valid) v0 = 0.f;
-                                if ((q & 1) * 8 + 1 >= valid) v1 = 0.f;
+                        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float sc = (q >> 1) ? sc1 : sc0, sh = (q >> 1) ? sh1 : sh0;
+                                const float2 v = h2_to_f2(r[s2][q]);
+                                float v0 = fmaxf(fmaf(v.x, sc, sh), 0.f), v1 = fmaxf(fmaf(v.y, sc, sh), 0.f);
+                                if (tail) {
+                                    if (s2 * 16 + (q & 1) * 8 >= valid) v0 = 0.f;
+                                    if (s2 * 16 + (q & 1) * 8 + 1 >= valid) v1 = 0.f;
+                                }
+                                o[s2][q] = f2_to_bf2(v0, v1);
                             }
-                            o[q] = f2_to_bf2(v0, v1);
-                        }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 v = h2_to_f2(r[q]);
-                            o[q] = f2_to_bf2(v.x, v.y);
-                        }
+                        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 v = h2_to_f2(r[s2][q]);
+                                o[s2][q] = f2_to_bf2(v.x, v.y);
+                            }
                     }
-                    stsm_x4(ts + t_x + sub * sub_x + blk * 512, o);
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) stsm_x4(ts + t_x + (sub0 + s2) * sub_x + blk * 512, o[s2]);
                 }
                 fence_proxy_async();
                 mbar_arrive(&full[t_slot]);
@@ -273,14 +289,20 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
             __syncwarp();
             if (++slot == w.nt) { slot = 0; phase ^= 1; }
         }
-    } else if (mine > 0) {
+        // the epilogue warps sleep in a named barrier for the whole main loop (a spinning mbarrier wait would take issue
+        // slots from the producers); this warp wakes them once the last MMA has completed
+        if (mine > 0) mbar_wait(done, 0);
+        tc_fence_after();
+        tc_fence_before();  // order the completed MMAs before the barrier the epilogue warps leave through
+        asm volatile("bar.sync 3, 160;" ::: "memory");
+    } else {
         // ================================ epilogue ================================
-        mbar_wait_backoff(done, 0);  // the whole main loop lies in between: poll sparsely
+        asm volatile("bar.sync 3, 160;" ::: "memory");
         tc_fence_after();
         const bool vec4 = (p.dw_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;  // 16-byte aligned rows
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         const int n = n0 + warp * 32 + lane;  // output channel of this thread (TMEM lane)
-        if (warp * 32 < n_here) {             // warp-uniform
+        if (mine > 0 && warp * 32 < n_here) {  // warp-uniform
             for (int c16 = 0; c16 < kw_here; c16 += 16) {
                 uint32_t g[32];
                 tmem_ld16(tmem_base + lane_base + c16, g);
@@ -337,10 +359,10 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
     const size_t raw = (size_t)WR * (ppr * 16 + 16);
     const size_t tb = (size_t)WSUB * (MT + w.kw) * 32;
     const size_t fixed = (size_t)(3 * MT + 2 * w.kw) * 4 + 256 + 256;
-    // T ring: 2 slots (the tensor core is at most one stage behind); raw ring: what is left, 3..5 slots
-    w.nt = 2;
+    // T ring: 2 slots (the tensor core is at most one stage behind), 3 with 32-row stages; raw ring: what is left, 3..6 slots
+    w.nt = WR >= 64 ? 2 : 3;
     long long nr = ((long long)kWSmem - (long long)fixed - (long long)w.nt * (long long)tb) / (long long)raw;
-    if (nr > 5) nr = 5;
+    if (nr > 6) nr = 6;
     if (nr < 3) return fail_arg("pn2_mlp_gemm_wgrad", "stage does not fit shared memory");
     w.nr = (int)nr;
     const size_t smem = fixed + ((w.nr * raw + 127) / 128 * 128) + w.nt * tb;
