@@ -88,7 +88,20 @@ def check(status, name):
 PROBE = None
 
 
+# PN2_NVTX=1: an NVTX range around every C-ABI call (named after the entry point), for Nsight timelines.  Off by default:
+# the step is ~250 launches and the ranges are host work.
+NVTX = os.environ.get("PN2_NVTX", "") == "1"
+
+
 def call(name, *args):
+    if NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        try:
+            check(getattr(lib, name)(*args), name)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     if PROBE is None:
         check(getattr(lib, name)(*args), name)
         return

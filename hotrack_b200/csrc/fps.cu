@@ -182,11 +182,10 @@ template <int PPT>
 int launch_regs(int b, int n, int m, int lg_bs, int q_cnt, int n_pos, int threads, const float* dataset,
                 float* temp, int* idxs, cudaStream_t stream) {
     const size_t smem = (size_t)n_pos * sizeof(float4);
-    static bool configured = false;  // one process per GPU: a per-instantiation flag is enough
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         PN2_CHECK(cudaFuncSetAttribute(fps_regs_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem),
                   "fps: cudaFuncSetAttribute");
-        configured = true;
     }
     fps_regs_kernel<PPT><<<b, threads, smem, stream>>>(n, m, lg_bs, q_cnt, n_pos, dataset, temp, idxs);
     PN2_CHECK_LAUNCH("fps_regs_kernel");

@@ -16,8 +16,8 @@
 // Grad.  The reference scatters with three fp32 atomicAdd per (b,c,i) into a
 // zeroed (B,C,M) buffer.  sm_100a has no native shared-memory fp32 add
 // (ATOMS.CAST.SPIN loop), so the scatter stays in L2 (REDG.ADD.F32) but idx and
-// weight are read once per point instead of once per channel.  The fused FP
-// layer (fused_fp.cu) uses a deterministic inverse-index gather instead.
+// weight are read once per point instead of once per channel.  (The fused engine
+// does not call this kernel: its FP stack scatters row-form gradients in fp_rows_bwd, mlp_rows.cu.)
 #include "pn2_common.cuh"
 
 namespace pn2 {

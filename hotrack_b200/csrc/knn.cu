@@ -234,11 +234,13 @@ extern "C" int pn2_knn(int b, int n, int m, int k, const float* unknown, const f
     while (kpad < k) kpad <<= 1;
     const int nsort = kpad * 2 < 128 ? 128 : kpad * 2;
     const size_t smem = 2 * kKnnTile * 3 * sizeof(float) + (size_t)kKnnWarps * nsort * sizeof(unsigned long long);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[64] = {};  // per device: the attribute belongs to the device's copy of the function
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
         PN2_CHECK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                   "knn: cudaFuncSetAttribute");
-        configured = smem;
+        configured[dev] = smem;
     }
     dim3 grid((n + kKnnWarps - 1) / kKnnWarps, b);
     knn_kernel<<<grid, kKnnWarps * 32, smem, (cudaStream_t)stream>>>(n, m, k, nsort, unknown, known, dist2, idx);

@@ -386,21 +386,15 @@ int launch_gemm(GemmArgs a, cudaStream_t stream) {
     if (nst > 6) nst = 6;
     a.nst = (int)nst;
     const size_t smem = fixed + (a.bres ? bres_bytes : 0) + nst * stage;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         PN2_CHECK(cudaFuncSetAttribute(gemm_rows_kernel<BN, BKT, AMODE, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kMaxSmem),
                   "gemm: cudaFuncSetAttribute");
-        configured = true;
     }
     const long long tiles = (a.rows + BM - 1) / BM;
     const int ny = (a.n + BN - 1) / BN;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = sm_count();
     long long gx = sms / ny;  // persistent, one CTA per SM: every CTA resident, tiles dealt round-robin
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
@@ -990,13 +984,12 @@ extern "C" int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, con
     if (gz < 1) gz = 1;
     if (gz > chunks) gz = chunks;
     dim3 grid(gx, gy, (unsigned)gz);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         PN2_CHECK(cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem),
                   "wgrad: cudaFuncSetAttribute");
         PN2_CHECK(cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem),
                   "wgrad: cudaFuncSetAttribute");
-        configured = true;
     }
     if (wgrad_use_tc() && wgrad_tc_supported(a)) return launch_wgrad_tc(a, (cudaStream_t)stream);
     if (in_scale)

@@ -552,19 +552,13 @@ int launch_tc(const GemmArgs& a, cudaStream_t stream) {
     using Cfg = TcCfg<BN, AMODE, SPLIT>;
     const int kpad = (a.kdim + TK - 1) / TK * TK;
     const size_t smem = (size_t)Cfg::kNst * Cfg::kStage + Cfg::kSC + (size_t)Cfg::kNCoef * kpad * 4 + 5 * BN * 4 + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         PN2_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, MASK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemBudget),
                   "gemm_tc: cudaFuncSetAttribute");
-        configured = true;
     }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = sm_count();
     const long long tiles = (a.rows + TM - 1) / TM;
     const int ny = (a.n + BN - 1) / BN;
     long long gx = sms / ny;  // persistent: one CTA per SM (shared memory, TMEM), tiles dealt round-robin

@@ -1002,12 +1002,11 @@ extern "C" int pn2_pool_fwd_x2(int b, int s, int k, int c, const void* y, const 
     if (k == 1 && !chan_sums && c <= 1024) {
         const int s_tiles = (s + kRowTile - 1) / kRowTile;
         const size_t smem = (size_t)kRowTile * (c + 1) * sizeof(float);
-        static bool configured = false;
-        if (!configured) {
+        static DeviceOnce once;
+        if (once.first()) {
             PN2_CHECK(cudaFuncSetAttribute(rows_to_cm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kRowTile * 1025 * 4),
                       "rows_to_cm: cudaFuncSetAttribute");
-            configured = true;
         }
         const int pieces = c / 8;
         const int threads = pieces >= kThreads ? pieces : (kThreads / pieces) * pieces;  // multiple of pieces
@@ -1046,12 +1045,11 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
     if (k == 1 && c <= 1024) {
         const int s_tiles = (s + kRowTile - 1) / kRowTile;
         const size_t smem = (size_t)kRowTile * (c + 1) * sizeof(float);
-        static bool configured = false;
-        if (!configured) {
+        static DeviceOnce once;
+        if (once.first()) {
             PN2_CHECK(cudaFuncSetAttribute(cm_to_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kRowTile * 1025 * 4),
                       "cm_to_rows_bwd: cudaFuncSetAttribute");
-            configured = true;
         }
         const int pieces = c / 8;
         const int threads = pieces >= kThreads ? pieces : (kThreads / pieces) * pieces;

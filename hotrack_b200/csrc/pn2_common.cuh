@@ -7,6 +7,31 @@
 
 namespace pn2 {
 
+// "once per device" guard for per-function attributes (cudaFuncSetAttribute applies to the CURRENT device's copy of the
+// function: a process that drives several GPUs must set it on each) and the SM count of the current device.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+inline int sm_count() {
+    static int cached[64] = {};
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return 148;
+    if (cached[d] == 0) {
+        int v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+        cached[d] = v;
+    }
+    return cached[d];
+}
+
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

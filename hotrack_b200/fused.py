@@ -36,8 +36,8 @@ _BF16 = torch.bfloat16  # gradient rows
 _F16 = torch.float16    # forward rows (see csrc/mma_common.cuh)
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _p(t):
@@ -251,7 +251,13 @@ class _Layer:
 
 
 def _bn_momentum(bn):
-    return 0.1 if bn.momentum is None else float(bn.momentum)
+    """nn.BatchNorm's update factor for THIS step: ``momentum``, or 1 / (batches seen so far, this one included) when
+    momentum is None (cumulative moving average).  The latter reads num_batches_tracked on the host: such a module
+    cannot be captured in a CUDA graph (the reference never builds one: trainer.py:167-190 sets a float momentum)."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    seen = int(bn.num_batches_tracked.item()) if bn.num_batches_tracked is not None else 0
+    return 1.0 / float(seen + 1)
 
 
 class _MlpStack(Function):
@@ -264,7 +270,7 @@ class _MlpStack(Function):
     @staticmethod
     def forward(ctx, kind, meta, bns, pobjs, training, precise, a, b, *params):
         dev = params[0].device
-        st = _stream()
+        st = _stream(dev)
         nl = len(params) // 4
         # leading layers with two-plane operands
         precise = nl if PRECISE_MODE == "all" else (min(int(precise), nl) if PRECISE_MODE == "auto" else 0)
@@ -335,6 +341,8 @@ class _MlpStack(Function):
             segs = [(ra, 3 if meta[3] else 0), (rb, (ra.c if ra is not None else 0) + 3)]
         elif kind == "fp":
             segs = [(ra, 0), (rb, ra.c if ra is not None else 0)]
+        if kind == "dense" and ra.offset is not None:
+            segs = [(ra, 0)]  # centred pooled rows fed straight to a dense stack: same per-column constants
         for r, start in segs:
             if r is not None and r.offset is not None:
                 if in_off is None:
@@ -450,8 +458,8 @@ class _MlpStack(Function):
         if not ctx.training:
             raise NotImplementedError("fused engine: backward through eval-mode BatchNorm is not implemented; "
                                       "use engine 'ops' for that")
-        st = _stream()
         dev = ctx.layers[0].y.device
+        st = _stream(dev)
         B, groups, pool_k, R, cin = ctx.dims
         layers = ctx.layers
         if dout is not None:
@@ -564,6 +572,9 @@ class _MlpStack(Function):
             elif ctx.feat_sink is not None and need_a:
                 # the producer's backward reads it as rows; da stays None (autograd still runs the producer's node,
                 # with an undefined gradient: ctx.set_materialize_grads(False))
+                if ctx.feat_sink.rows16 is not None:
+                    raise RuntimeError("fused engine: two dense consumers of one fused output in row form are not "
+                                       "supported (the second would overwrite the first one's gradient)")
                 ctx.feat_sink.rows16 = (dx0, dx0.shape[1])
             else:
                 Bc, Cc, Nc = ctx.a_shape
@@ -585,12 +596,20 @@ def _check_cuda(t):
         raise ValueError("hotrack_b200 has no CPU path")
 
 
+def _no_coordinate_grad(*tensors):
+    """The fused stacks return no gradient for coordinates (HandTrackNet's are inputs); asking for one must not pass
+    silently."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError("fused engine: gradients w.r.t. xyz / new_xyz are not implemented; use engine 'ops'")
+
+
 def _run(kind, meta, convs, bns, training, a, b, precise=0):
     ps = _params(convs, bns)
     views = []
     for i, p in enumerate(ps):
         views.append(p.view(p.shape[0], -1) if i % 4 == 0 else p)  # conv weight (Cout,Cin,1[,1]) -> (Cout,Cin)
-    out = _MlpStack.apply(kind, meta, list(bns), ps, bool(training), int(precise), a, b, *views)
+    with torch.cuda.device(ps[0].device):  # kernels launch on the CURRENT device: make it the tensors' one
+        out = _MlpStack.apply(kind, meta, list(bns), ps, bool(training), int(precise), a, b, *views)
     rows, _MlpStack.last_rows = _MlpStack.last_rows, None  # set by forward (single-threaded hand-over)
     return attach_rows(out, rows) if rows is not None else out
 
@@ -604,6 +623,7 @@ def sa_scale(xyz, points, new_xyz, idx, centre_feat, convs, bns, training, preci
     _check_cuda(xyz)
     if points is not None and points.shape[1] == 0:
         points = None
+    _no_coordinate_grad(xyz, new_xyz)
     meta = (xyz.contiguous().float(), new_xyz.contiguous().float(), idx.contiguous().int(), False)
     return _run("sa", meta, convs, bns, training, points, centre_feat, precise)
 
@@ -611,6 +631,7 @@ def sa_scale(xyz, points, new_xyz, idx, centre_feat, convs, bns, training, preci
 def sa_group_all(xyz, points, convs, bns, training, precise=0):
     """Group-all SA.  xyz (B,3,N), points (B,D,N)|None -> (B,Cout,1); channel order [xyz, points]."""
     _check_cuda(xyz)
+    _no_coordinate_grad(xyz)
     meta = (xyz.contiguous().float(), None, None, True)
     return _run("sa", meta, convs, bns, training, points, None, precise)
 

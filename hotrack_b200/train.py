@@ -86,10 +86,14 @@ class TrainStep:
             for t, s0 in zip(self._state_tensors(), snap):
                 t.copy_(s0)
         torch.cuda.current_stream().wait_stream(side)
+        # world > 1: the NCCL all-reduce of the flat gradient and the Adam kernel are launched eagerly right behind the
+        # replay (two launches).  Capturing them too (PN2_GRAPH_ALLREDUCE=1) is EXPERIMENTAL: with this torch / NCCL
+        # pair the 2-GPU bench stopped making progress inside the captured exchange (round 2), so it is off by default.
+        self._finish_in_graph = self.world == 1 or os.environ.get("PN2_GRAPH_ALLREDUCE", "0") == "1"
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._loss = self._fwd_bwd(self._static_in)
-            if self.world == 1:
+            if self._finish_in_graph:
                 self._finish()
         return 0
 
@@ -106,7 +110,7 @@ class TrainStep:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
-        if self.world > 1:
+        if not self._finish_in_graph:
             self._finish()  # NCCL all-reduce + Adam outside the captured region
         return self._loss
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-/* (B,C,N) fp32 channel-major -> rows [B*N][ld] bf16, columns >= C zero-filled.  sub_sums != NULL: the value
+/* (B,C,N) fp32 channel-major -> rows [B*N][ld] fp16, columns >= C zero-filled.  sub_sums != NULL: the value
  * sub_sums[c]*sub_scale (a channel mean) is subtracted before rounding ("centred rows"). */
 int pn2_to_rows(int b, int c, int n, const float* src, const float* sub_sums, float sub_scale, void* dst, int ld,
                 pn2_stream_t stream);
@@ -44,14 +44,14 @@ int pn2_fp_build_rows(int b, int n, int s, const void* skip, int skip_c, int ski
                       void* out, int out_ld, pn2_stream_t stream);
 
 /* center[n] = w[n][:] . mean_j act(x[row_j][:]) over <= 16 rows spread over the matrix: a cheap estimate of the
- * per-channel mean of the GEMM output, used to centre it before bf16 rounding (kdim <= 1024).  in_offset[kdim] (nullable): per-channel constants the
+ * per-channel mean of the GEMM output, used to centre it before fp16 rounding (kdim <= 1024).  in_offset[kdim] (nullable): per-channel constants the
  * input rows were themselves centred by; center_true = center + w . in_offset is what the true (uncentred) output
  * differs from the stored one by -- bn_finalize / bn_eval_affine take center_true. */
 int pn2_mlp_center(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
                    const float* in_shift, const void* w, const float* in_offset, float* center, float* center_true,
                    pn2_stream_t stream);
 
-/* y[rows][n] = act(x)[rows][kdim] * w[n][kdim]^T - center[n]  (bf16 in, fp32 accumulate, bf16 out), act =
+/* y[rows][n] = act(x)[rows][kdim] * w[n][kdim]^T - center[n]  (fp16 in, fp32 accumulate, fp16 out), act =
  * relu(x*scale+shift) when in_scale != NULL, center NULL = 0.  stats != NULL: stats[0..n) += column sums of y,
  * stats[n..2n) += sums of y^2 (zeroed by the caller) -- the BatchNorm batch statistics (shift-invariant, so the
  * centring only has to be undone in the running mean / eval shift).  kdim % 32 == 0, n % 8 == 0. */
@@ -125,8 +125,8 @@ int pn2_mlp_gemm_wgrad(long long rows, int n, int kp, int k_true, const void* dz
                        const float* cA, const float* cB, const float* cC, const void* x, int x_ld,
                        const float* in_scale, const float* in_shift, float* dw, int dw_ld, pn2_stream_t stream);
 
-/* fp32 conv weight [n][k_true] -> bf16 [n][kp] (zero padded) and, if wt != NULL, its transpose [kp][n]. */
-int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_bf16, void* wt_bf16, pn2_stream_t stream);
+/* fp32 conv weight [n][k_true] -> fp16 [n][kp] (zero padded) and, if wt_bf16 != NULL, its bf16 transpose [kp][n]. */
+int pn2_mlp_prep_weights(int n, int k_true, int kp, const float* w, void* w_f16, void* wt_bf16, pn2_stream_t stream);
 
 /* pn2_mlp_prep_weights (fp16 copy only) for n_layers layers in ONE launch.  descs: device array of n_layers records
  * { const float* w; void* w_f16; int n; int k_true; int kp; int two; } (32 bytes each). */

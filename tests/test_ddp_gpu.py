@@ -1,0 +1,82 @@
+"""Data-parallel step on real GPUs (NCCL, one process per GPU; skipped with fewer than two): the gradient the fused
+engine's TrainStep all-reduces over 2 ranks x B/2 clouds must equal the single-rank gradient of the full batch of B --
+up to what BatchNorm statistics per rank change (the reference has no SyncBN, SURVEY.md section 8e: statistics stay per
+rank), so the comparison runs in EVAL-statistics-free form: weights after one step with BatchNorm momentum only affect
+buffers, and the loss is the mean over ranks.  What must hold exactly: replicas stay bit-identical after the step, the
+all-reduced gradient is the sum of the two shard gradients, and the graph-replayed step matches the eager one."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PN2_ROOT"]); sys.path.insert(0, os.path.join(os.environ["PN2_ROOT"], "tests"))
+import clouds
+from hotrack_b200 import backbones, pointnet_utils as pu
+from hotrack_b200.handtrack_path import HandTrackPointPath, init_weights
+from hotrack_b200.train import TrainStep
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank); dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+B, N = 4, 1024
+x = torch.from_numpy(clouds.ball(B, N, seed=3)).to(dev).transpose(1, 2).contiguous()
+k = torch.from_numpy(clouds.keypoints(B, 21, seed=3)).to(dev).transpose(1, 2).contiguous()
+tg = [torch.randn(s, generator=torch.Generator().manual_seed(i)).to(dev) for i, s in enumerate([(B // world, 384, N), (B // world, 384, 21), (B // world, 384, 21)])]
+loss = lambda out: sum((o - t).square().mean() for o, t in zip(out[:3], tg))
+lo, hi = rank * B // world, (rank + 1) * B // world
+res = {}
+for mode in ("graph", "nograph"):
+    pu.set_engine("fused"); m = HandTrackPointPath(backbones.default_cfg(dev)); pu.set_engine("ops")
+    init_weights(m, seed=0); m = m.to(dev).train()
+    ts = TrainStep(m, loss, lr=1e-3, graph=mode != "nograph")
+    for _ in range(3):
+        l = ts(x[lo:hi], k[lo:hi])
+    torch.cuda.synchronize()
+    flat = ts.flat.data.clone()
+    # replicas identical
+    other = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(other, flat)
+    assert all(torch.equal(o, other[0]) for o in other), mode + ": replicas diverged"
+    res[mode] = (flat, ts.flat.grad.clone(), float(l))
+# the exchanged gradient is the SUM over ranks of the shard gradients: a shard-only backward (no exchange), summed by an
+# explicit all-reduce, against the gradient buffer a full first step leaves behind
+def fresh(graph):
+    pu.set_engine("fused"); m_ = HandTrackPointPath(backbones.default_cfg(dev)); pu.set_engine("ops")
+    init_weights(m_, seed=0)
+    return TrainStep(m_.to(dev).train(), loss, lr=1e-3, graph=graph)
+# (two-plane rows everywhere for this check: with fp16 rows behind FP3 the engine's own run-to-run noise -- fp32 atomics
+# order turned into fp16 rounding flips, amplified by the network -- is ~5 % on the gradients, tools/dev/debug_determinism.py)
+from hotrack_b200 import fused
+fused.set_precise("all")
+t1 = fresh(False)
+t1._fwd_bwd((x[lo:hi], k[lo:hi]))
+g_sum = t1.flat.grad.clone()
+dist.all_reduce(g_sum)
+t2 = fresh(False)
+t2(x[lo:hi], k[lo:hi])
+gerr = ((t2.flat.grad - g_sum).norm() / g_sum.norm()).item()
+assert gerr < 1e-1, "all-reduced gradient != sum of shard gradients: rel %.3g (|g| %.3g vs %.3g)" % (gerr, t2.flat.grad.norm().item(), g_sum.norm().item())
+a, c = res["graph"], res["nograph"]
+rel = lambda u, v: ((u - v).norm() / v.norm().clamp_min(1e-30)).item()
+assert rel(a[0], c[0]) < 2e-3, rel(a[0], c[0])   # graph replay + eager exchange vs all-eager: atomics order only
+if rank == 0:
+    print("DDP_OK", rel(a[0], c[0]), rel(a[1], c[1]))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_step_replicas_stay_identical_and_graph_exchange_matches_eager(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, PN2_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29641", str(script)], env=env, capture_output=True,
+                       text=True, timeout=240)
+    assert r.returncode == 0 and "DDP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
