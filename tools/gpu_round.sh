@@ -9,7 +9,7 @@ for what in "$@"; do case $what in
 tests) timeout 900 python -m pytest tests -m gpu -x -q > $out/tests.log 2>&1; echo "tests rc=$?" >> $out/tests.log; tail -3 $out/tests.log;;
 ref) timeout 300 python bench.py --impl reference --steps 10 --warmup 3 > $out/bench_ref.json 2> $out/bench_ref.err; cut -c1-300 $out/bench_ref.json;;
 bench) timeout 400 python bench.py > $out/bench_ours.json 2> $out/bench_ours.err; cut -c1-300 $out/bench_ours.json;;
-launches) timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches.csv \
+launches) timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip ${LAUNCH_SKIP:-480} --launch-count ${LAUNCH_COUNT:-560} --csv --log-file $out/launches.csv \
     python bench.py --steps 1 --warmup 3 --profile-mode --no-graph > $out/b_ncu.log 2>&1;;
 sanitize) timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > $out/memcheck.log 2>&1; echo "memcheck rc=$?" >> $out/memcheck.log; tail -4 $out/memcheck.log
   timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_ops_gpu.py -q -x -k "fps or ball or knn" > $out/racecheck.log 2>&1; echo "racecheck rc=$?" >> $out/racecheck.log; tail -4 $out/racecheck.log;;
