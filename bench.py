@@ -328,6 +328,113 @@ def side_legs_ours(torch, dev, B, N, xyz_d, kps_d, flush, FromPoints):
     return out
 
 
+def _palm(B):
+    """a hand-sized 6-point palm template (wrist + five finger bases), metres -- what the reference takes from the MANO
+    layer at zero pose (track_network.py:151-153)"""
+    import numpy as np
+    import torch
+    base = np.array([[0, 0, 0], [0.03, 0.02, 0.005], [0.09, 0.03, 0.0], [0.095, 0.01, 0.002], [0.09, -0.01, 0.0],
+                     [0.08, -0.03, -0.003]], dtype=np.float32)
+    return torch.from_numpy(np.repeat(base[None], B, 0))
+
+
+def full_network_legs(torch, dev, impl, B, N, flush):
+    """The network AROUND the path, timed on both arms: (1) a full HandTrackNet training
+    step -- handframe 'kp', loss = 10 kp + r + t as handtracknet_train_SimGrasp.yml:25-30, Adam -- at B x N; (2) one tracked
+    frame (B=1, N=8192, eval, recurrence of track_network.py:159-217), p50 wall latency with a synchronisation per frame.
+    Reference arm: its own hand_network.py on its own kernels, eager, CPU SVD and discarded attention included."""
+    import numpy as np
+
+    xyz, kps = make_inputs(B, N, 0)
+    hp = (xyz * 0.1 + 0.3).to(dev)                       # metres, as the loader delivers them (scale 0.2: hand_network.py:99)
+    jk = (kps * 0.1 + 0.3).to(dev)
+    gk = (make_inputs(B, N, 1)[1] * 0.1 + 0.3).to(dev)
+    palm = _palm(B).to(dev)
+    flags = {"track_flag": False, "IKNet_flag": False}
+    out = {}
+    if impl == "ours":
+        from hotrack_b200 import hand_network, pointnet_utils as pu
+        from hotrack_b200.handtrack_path import init_weights
+        from hotrack_b200.track import HandTracker
+        from hotrack_b200.train import TrainStep
+        from hotrack_b200.backbones import default_cfg
+        cfg = default_cfg(dev)
+        cfg["network"]["handframe"] = "kp"
+        pu.set_engine("fused")
+        try:
+            net = hand_network.HandTrackNet(cfg)
+        finally:
+            pu.set_engine("ops")
+        init_weights(net, seed=0)
+        net = net.to(dev).train()
+
+        class Full(torch.nn.Module):
+            def __init__(self, net):
+                super().__init__()
+                self.net = net
+
+            def forward(self, hp, jk, gk, palm):
+                data = {"hand_points": hp, "jittered_hand_kp": jk, "gt_hand_kp": gk, "gt_hand_pose": {"palm_template": palm}}
+                ret = self.net(data, flags)
+                loss, _ = self.net.compute_loss(data, ret, flags)
+                return 10 * loss["hand_pred_kp_loss"] + loss["hand_pred_r_loss"] + loss["hand_pred_t_loss"]
+
+        ts = TrainStep(Full(net), lambda total: total, lr=1e-4, weight_decay=1e-4, graph=True)
+        for _ in range(3):
+            ts(hp, jk, gk, palm)
+        torch.cuda.synchronize()
+        ms = _time_steps(torch, lambda: ts(hp, jk, gk, palm), 10, flush)
+        out["handtracknet_step"] = {"ms_per_step": round(ms, 4), "value": round(B / ms * 1e3, 2), "unit": UNIT, "steps": 10,
+                                    "what": "full HandTrackNet (handframe kp) fwd + loss (10 kp + r + t) + bwd + Adam, B=%d N=%d, "
+                                            "fused engine, CUDA-graph replay, GPU Kabsch" % (B, N)}
+        net.eval()
+        x1, k1 = make_inputs(1, 8192, 7)
+        pts = (x1 * 0.1 + 0.3).to(dev)
+        tr = HandTracker(net, _palm(1).to(dev), graph=True)
+        tr.reset((k1 * 0.1 + 0.3).to(dev), pts)
+        out["tracker_frame"] = _latency(torch, np, lambda t: tr.step(t), pts)
+        out["tracker_frame"]["what"] = "one tracked frame: recurrence + full HandTrackNet forward, B=1 N=8192, one CUDA-graph replay"
+    else:
+        from oracle import ref_modules, ref_path
+        _, _, rhn = ref_modules.load_full("ref")
+        net = rhn.HandTrackNet(ref_modules.handtracknet_cfg(dev, "kp"))
+        ref_path.xavier_init(net, seed=0)
+        net = net.to(dev).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=1e-4)
+        data = {"hand_points": hp, "jittered_hand_kp": jk, "gt_hand_kp": gk, "gt_hand_pose": {"palm_template": palm}}
+
+        def step():
+            opt.zero_grad(set_to_none=False)
+            ret = net(data, flags)
+            loss, _ = net.compute_loss(data, ret, flags)
+            (10 * loss["hand_pred_kp_loss"] + loss["hand_pred_r_loss"] + loss["hand_pred_t_loss"]).backward()
+            opt.step()
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        ms = _time_steps(torch, step, 3, flush)
+        out["handtracknet_step"] = {"ms_per_step": round(ms, 4), "value": round(B / ms * 1e3, 2), "unit": UNIT, "steps": 3,
+                                    "what": "full HandTrackNet (handframe kp) fwd + loss + bwd + Adam, B=%d N=%d, reference "
+                                            "hand_network.py on reference kernels, eager" % (B, N)}
+        net.eval()
+        x1, k1 = make_inputs(1, 8192, 7)
+        pts = (x1 * 0.1 + 0.3).to(dev)
+        state = {"last": (k1 * 0.1 + 0.3).to(dev) - pts.mean(dim=-2, keepdim=True)}
+        palm1 = _palm(1).to(dev)
+
+        def frame(t):  # track_network.py:159-217, branch without IKNet
+            c = t.mean(dim=-2, keepdim=True)
+            ret = net({"pred_palm_template": palm1, "hand_points": t, "jittered_hand_kp": state["last"] + c},
+                      {"track_flag": True, "test_flag": True, "IKNet_flag": False})
+            state["last"] = ret["pred_kp"] - c
+            return ret["pred_kp"]
+
+        out["tracker_frame"] = _latency(torch, np, frame, pts, frames=100)
+        out["tracker_frame"]["what"] = "one tracked frame: recurrence + full HandTrackNet forward, B=1 N=8192, reference, eager"
+    return out
+
+
 def _latency(torch, np, fn, x, frames=300):
     import time as _t
     with torch.no_grad():
@@ -542,6 +649,13 @@ def main():
             x5 = x5.to(dev).transpose(1, 2).contiguous()
             line["latency_config5"] = _latency(torch, np, lambda t: bb(t), x5)
             line["latency_config5"]["what"] = "B=1 N=8192 PointNet2Msg_fast forward, eval, reference modules on reference kernels, eager"
+            if not args.no_side_legs:
+                try:
+                    del model, opt
+                    torch.cuda.empty_cache()
+                    line.update(full_network_legs(torch, dev, "reference", B, N, flush))
+                except Exception as ex:
+                    line["side_legs_error"] = repr(ex)[:300]
     else:
         # dominant kernel of OURS inside the timed region
         peak, peak_src = peaks()
@@ -580,9 +694,13 @@ def main():
                             "timing": "CUDA events around each launch, eager probe pass after the timed region"}
         if best is not None:
             # dram__bytes_read + write of the same kernel / shape from the committed ncu --set full capture
-            # (profiles/r01_traffic.json: "<entry point>:<size args>" -> bytes per launch), null when not captured
+            # (profiles/rNN_traffic.json: "<entry point>:<size args>" -> bytes per launch), null when not captured
             try:
-                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+                tr = {}
+                for tag in ("r01", "r02"):  # later rounds override
+                    fn = os.path.join(ROOT, "profiles", tag + "_traffic.json")
+                    if os.path.exists(fn):
+                        tr.update(json.load(open(fn)))
                 key = "%s:%s" % (best["kernel"], ",".join(str(v) for v in best["shape"]))
                 if key in tr:
                     best["traffic"] = tr[key]["dram_bytes"]
@@ -609,6 +727,7 @@ def main():
         if not ddp and not args.profile_mode and not args.no_side_legs and engine == "fused":
             try:
                 line.update(side_legs_ours(torch, dev, B, N, xyz_d, kps_d, flush, FromPoints))
+                line.update(full_network_legs(torch, dev, "ours", B, N, flush))
             except Exception as ex:  # a side leg must never take the headline down with it
                 line["side_legs_error"] = repr(ex)[:300]
         if not ddp and not args.no_cpu_baseline and not args.profile_mode:  # rank 0 at N=1 only

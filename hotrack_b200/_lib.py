@@ -60,6 +60,11 @@ SIGNATURES = {
                                _p, _p, _p, _p, _p, _p, _p],
     "pn2_pool_fwd_x2": [_i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "pn2_mlp_prep_weights_x2": [_i, _i, _i, _p, _p, _p, _p],
+    # max-pool in the GEMM epilogue
+    "pn2_mlp_gemm_fwd_pool": [_ll, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p],
+    "pn2_mlp_gemm_fwd_bn_pool": [_ll, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p,
+                                 _p, _p, _p, _p, _p, _p, _i, _p, _p, _p],
+    "pn2_pool_finalize": [_i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p],
     # include/pn2b200_hand.h
     "pn2_kabsch_fwd": [_i, _i, _p, _i, _p, _p, _p, _p, _p],
     "pn2_kabsch_bwd": [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],

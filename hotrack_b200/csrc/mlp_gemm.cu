@@ -839,9 +839,25 @@ extern "C" int pn2_mlp_center(long long rows, int kdim, int n, const void* x, in
     return 0;
 }
 
+struct PoolOut {
+    int k = 0;
+    const float* gamma = nullptr;
+    float* val = nullptr;
+    int* arg = nullptr;
+};
+static int check_pool(const char* who, const PoolOut& po, long long rows) {
+    if (po.k == 0) return 0;
+    if (po.k != 16 && po.k != 32 && po.k != 64 && po.k != 128) return fail_arg(who, "epilogue pooling needs pool_k in {16, 32, 64, 128}");
+    if (rows % po.k) return fail_arg(who, "rows must be a multiple of pool_k");
+    if (!po.gamma || !po.val || !po.arg) return fail_arg(who, "null pooling pointer");
+    return 0;
+}
+
 static int gemm_fwd_impl(const char* who, long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
                          const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
-                         const float* center, void* y, void* y_lo, int y_ld, float* stats, pn2_stream_t stream) {
+                         const float* center, void* y, void* y_lo, int y_ld, float* stats, pn2_stream_t stream,
+                         const PoolOut& po = PoolOut()) {
+    if (int e = check_pool(who, po, rows)) return e;
     if (int e = check_common(who, rows, kdim, n)) return e;
     if (rows == 0) return 0;
     if (!x || !w || !y) return fail_arg(who, "null pointer");
@@ -856,7 +872,8 @@ static int gemm_fwd_impl(const char* who, long long rows, int kdim, int n, const
     a.center = center;
     a.out = (uint16_t*)y; a.out_ld = y_ld; a.out_lo = (uint16_t*)y_lo;
     a.sums = stats;
-    if (gemm_use_tc() || x_lo) return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
+    a.pool_k = po.k; a.pool_gamma = po.gamma; a.pool_val = po.val; a.pool_arg = po.arg;
+    if (gemm_use_tc() || x_lo || po.k) return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
     if (in_scale) return dispatch_bn<A_AFFINE, false>(a, (cudaStream_t)stream);
     return dispatch_bn<A_PLAIN, false>(a, (cudaStream_t)stream);
 }
@@ -882,8 +899,9 @@ static int gemm_fwd_bn_impl(const char* who, long long rows, int kdim, int n, co
                             const float* gamma, const float* beta, const float* conv_bias, const float* center_true,
                             float momentum, float eps, float* running_mean, float* running_var,
                             long long* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
-                            float* next_center, pn2_stream_t stream) {
+                            float* next_center, pn2_stream_t stream, const PoolOut& po = PoolOut()) {
     if (int e = check_common(who, rows, kdim, n)) return e;
+    if (int e = check_pool(who, po, rows)) return e;
     if (rows == 0) return fail_arg(who, "BatchNorm statistics of zero rows");
     if (!x || !w || !y || !stats || !counter || !gamma || !beta || !scale || !shift || !mean || !rstd)
         return fail_arg(who, "null pointer");
@@ -905,6 +923,7 @@ static int gemm_fwd_bn_impl(const char* who, long long rows, int kdim, int n, co
     a.fin_running_mean = running_mean; a.fin_running_var = running_var; a.fin_nbt = num_batches_tracked;
     a.fin_scale = scale; a.fin_shift = shift; a.fin_mean = mean; a.fin_rstd = rstd;
     a.fin_next_center = next_center;
+    a.pool_k = po.k; a.pool_gamma = po.gamma; a.pool_val = po.val; a.pool_arg = po.arg;
     return launch_gemm_tc(a, in_scale ? A_AFFINE : A_PLAIN, false, (cudaStream_t)stream);
 }
 
@@ -931,6 +950,31 @@ extern "C" int pn2_mlp_gemm_fwd_bn_x2(long long rows, int kdim, int n, const voi
     return gemm_fwd_bn_impl("pn2_mlp_gemm_fwd_bn_x2", rows, kdim, n, x, x_lo, x_ld, in_scale, in_shift, w, w_lo, center, y,
                             y_lo, y_ld, stats, counter, gamma, beta, conv_bias, center_true, momentum, eps, running_mean,
                             running_var, num_batches_tracked, scale, shift, mean, rstd, next_center, stream);
+}
+
+extern "C" int pn2_mlp_gemm_fwd_pool(long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                                     const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                                     const float* center, void* y, void* y_lo, int y_ld, float* stats, int pool_k,
+                                     const float* pool_gamma, float* pool_val, int* pool_arg, pn2_stream_t stream) {
+    PoolOut po;
+    po.k = pool_k; po.gamma = pool_gamma; po.val = pool_val; po.arg = pool_arg;
+    return gemm_fwd_impl("pn2_mlp_gemm_fwd_pool", rows, kdim, n, x, x_lo, x_ld, in_scale, in_shift, w, w_lo, center, y, y_lo,
+                         y_ld, stats, stream, po);
+}
+
+extern "C" int pn2_mlp_gemm_fwd_bn_pool(long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                                        const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                                        const float* center, void* y, void* y_lo, int y_ld, float* stats,
+                                        unsigned int* counter, const float* gamma, const float* beta,
+                                        const float* conv_bias, const float* center_true, float momentum, float eps,
+                                        float* running_mean, float* running_var, long long* num_batches_tracked,
+                                        float* scale, float* shift, float* mean, float* rstd, float* next_center,
+                                        int pool_k, float* pool_val, int* pool_arg, pn2_stream_t stream) {
+    PoolOut po;
+    po.k = pool_k; po.gamma = gamma; po.val = pool_val; po.arg = pool_arg;
+    return gemm_fwd_bn_impl("pn2_mlp_gemm_fwd_bn_pool", rows, kdim, n, x, x_lo, x_ld, in_scale, in_shift, w, w_lo, center, y,
+                            y_lo, y_ld, stats, counter, gamma, beta, conv_bias, center_true, momentum, eps, running_mean,
+                            running_var, num_batches_tracked, scale, shift, mean, rstd, next_center, stream, po);
 }
 
 extern "C" int pn2_mlp_gemm_dgrad(long long rows, int n_red, int k_out, const void* dz, int dz_ld, const void* y,

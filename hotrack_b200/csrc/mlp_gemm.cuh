@@ -32,6 +32,14 @@ struct GemmArgs {
     long long* fin_nbt;
     float *fin_scale, *fin_shift, *fin_mean, *fin_rstd;
     float* fin_next_center;          // nullable: [n] <- batch mean of the un-centred output (next step's centre)
+    // forward, last layer of a pooled stack: max over the pool_k rows of each group taken in the EPILOGUE (no pool_fwd
+    // launch, no second pass over y).  BatchNorm's scale has the sign of gamma, known before the statistics are:
+    // max_k relu(s*y_k + t) = relu(s * (gamma >= 0 ? max_k y_k : min_k y_k) + t), so one extreme per (group, column)
+    // suffices.  pool_k in {16, 32, 64, 128} (divides the 128-row tile); pool_val / pool_arg [rows / pool_k][n].
+    int pool_k;
+    const float* pool_gamma;         // [n] sign source
+    float* pool_val;                 // the selected extreme of (acc - center)
+    int* pool_arg;                   // its row inside the group (first one in row order)
 };
 
 // BatchNorm finalisation of one channel from the column sums (shared by bn_finalize_kernel and the GEMM tail)

@@ -78,7 +78,8 @@ struct TcCfg {
     static constexpr int kSC = TM * kCLD * 2 * (SPLIT ? 2 : 1);  // SPLIT: hi tile + lo tile
     static constexpr int kNCoef = AMODE == A_AFFINE ? 2 : 0;
     static constexpr int kCoefK = SPLIT ? kMaxKSplit : kMaxK;
-    static constexpr int kFixed = kSC + kNCoef * kCoefK * 4 + 5 * BN * 4 + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int kPool = AMODE != A_BNBWD ? 9 * BN * 4 : 0;  // epilogue pooling: [BN] sign flags + [4][BN] values + [4][BN] rows
+    static constexpr int kFixed = kSC + kNCoef * kCoefK * 4 + 5 * BN * 4 + kPool + 256 + 1024;  // + barriers + alignment slack
     static constexpr int kNstRaw = (kSmemBudget - kFixed) / kStage;
     static constexpr int kNst = kNstRaw > 6 ? 6 : kNstRaw;
     // chunks in flight per producer thread.  NST - 2, not NST - 1: refilling a slot waits for the MMAs of the chunk that
@@ -113,7 +114,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     const int kpad = (p.kdim + TK - 1) / TK * TK;
     float* sPrev = sCoef + NCOEF * kpad;        // [4][BN], MASK only
     float* sCen = sPrev + 4 * BN;               // [BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sCen + BN);  // 8-byte aligned: every size above is a multiple of 8
+    uint32_t* sNeg = reinterpret_cast<uint32_t*>(sCen + BN);   // [BN] pooling: all-ones where gamma < 0 (the minimum is wanted)
+    uint32_t* sPoolV = sNeg + (FWD ? BN : 0);                   // [4][BN] per-quarter extremes (ordered-uint form), pool_k > 32
+    int* sPoolA = reinterpret_cast<int*>(sPoolV + (FWD ? 4 * BN : 0));  // [4][BN] their rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPoolA + (FWD ? 4 * BN : 0));  // 8-byte aligned: every size above is a multiple of 8
     uint64_t* full = bars;                      // [NST] producers -> MMA
     uint64_t* empty = bars + NST;               // [NST] MMA -> producers
     uint64_t* tfull = bars + 2 * NST;           // [2]   MMA -> epilogue
@@ -133,6 +137,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
         sCoef[i] = c < p.kdim ? src[c] : 0.f;
     }
     for (int i = tid; i < BN; i += kTcThreads) sCen[i] = (p.center && n0 + i < p.n) ? p.center[n0 + i] : 0.f;
+    if (FWD && p.pool_k)
+        for (int i = tid; i < BN; i += kTcThreads) sNeg[i] = (n0 + i < p.n && p.pool_gamma[n0 + i] < 0.f) ? 0xFFFFFFFFu : 0u;
     if (MASK) {
         for (int i = tid; i < 4 * BN; i += kTcThreads) {
             const int which = i / BN, c = n0 + (i - which * BN);
@@ -370,6 +376,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
 #pragma unroll
                             for (int e = 0; e < LDW; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * yscale);
                         }
+                        if (FWD && p.pool_k) {
+                            // max-pool in the epilogue: this warp holds 32 consecutive rows (lane = row) of LDW columns.
+                            // Values go to an order-preserving unsigned form (inverted where gamma < 0), one
+                            // redux.sync.max per column, the first row holding it by ballot.
+                            const long long grow = tile * TM + q4 * 32 + lane;
+                            const bool live = grow < p.rows;
+                            const int k16 = p.pool_k == 16;
+                            uint32_t keep_m = 0u;  // the result this lane writes out: column cb + (lane % LDW') of group lane / 16 (k16)
+                            int keep_a = 0;
+#pragma unroll
+                            for (int e = 0; e < LDW; ++e) {
+                                uint32_t u = __float_as_uint(__uint_as_float(v[e]) - sCen[h * EBN + cb + e]);
+                                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                                u ^= sNeg[h * EBN + cb + e];
+                                if (!live) u = 0u;
+                                if (!k16) {
+                                    const uint32_t m = __reduce_max_sync(kFull, u);
+                                    const int a = __ffs(__ballot_sync(kFull, u == m)) - 1;
+                                    if (lane == e) { keep_m = m; keep_a = a; }
+                                } else {  // two 16-row groups per warp
+                                    const bool hi16 = lane >= 16;
+                                    const uint32_t m0 = __reduce_max_sync(kFull, hi16 ? 0u : u);
+                                    const uint32_t m1 = __reduce_max_sync(kFull, hi16 ? u : 0u);
+                                    const uint32_t b0 = __ballot_sync(kFull, !hi16 && u == m0);
+                                    const uint32_t b1 = __ballot_sync(kFull, hi16 && u == m1);
+                                    if (LDW == 16) {  // lanes 0..15 <- group 0, lanes 16..31 <- group 1, column lane % 16
+                                        if ((lane & 15) == e) { keep_m = hi16 ? m1 : m0; keep_a = hi16 ? __ffs(b1) - 17 : __ffs(b0) - 1; }
+                                    } else {          // 32 columns x 2 groups: stored right away by lanes 0 / 16
+                                        if ((lane & 15) == 0) {
+                                            const long long g = grow >> 4;
+                                            const int col = n0 + h * EBN + cb + e;
+                                            uint32_t mm = (hi16 ? m1 : m0) ^ sNeg[h * EBN + cb + e];
+                                            mm = (mm & 0x80000000u) ? (mm & 0x7FFFFFFFu) : ~mm;
+                                            if (live && col < p.n) {
+                                                p.pool_val[g * p.n + col] = __uint_as_float(mm);
+                                                p.pool_arg[g * p.n + col] = hi16 ? __ffs(b1) - 17 : __ffs(b0) - 1;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                            if (!k16 || LDW == 16) {
+                                const int e = k16 ? (lane & 15) : lane;
+                                const int colb = h * EBN + cb + e;           // column inside this CTA's BN-wide tile
+                                if (e < LDW) {
+                                    if (p.pool_k <= 32) {
+                                        const long long g = k16 ? (tile * TM + q4 * 32 + (lane & 16)) >> 4 : (tile * TM + q4 * 32) >> 5;
+                                        const bool glive = k16 ? (tile * TM + q4 * 32 + (lane & 16)) < p.rows : (tile * TM + q4 * 32) < p.rows;
+                                        uint32_t mm = keep_m ^ sNeg[colb];
+                                        mm = (mm & 0x80000000u) ? (mm & 0x7FFFFFFFu) : ~mm;
+                                        if (glive && n0 + colb < p.n) {
+                                            p.pool_val[g * p.n + n0 + colb] = __uint_as_float(mm);
+                                            p.pool_arg[g * p.n + n0 + colb] = keep_a;
+                                        }
+                                    } else {  // groups span quarters: combined after the pass barrier
+                                        sPoolV[q4 * BN + colb] = keep_m;
+                                        sPoolA[q4 * BN + colb] = keep_a;
+                                    }
+                                }
+                            }
+                        }
                         const int r = q4 * 32 + lane;
 #pragma unroll
                         for (int g8 = 0; g8 < LDW / 8; ++g8) {
@@ -406,6 +473,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                     mbar_arrive(&tempty[as]);
                 }
                 epi_bar();
+                if (FWD && p.pool_k > 32) {
+                    // groups of 64 / 128 rows: combine the quarters' extremes (earlier quarter wins ties: first row in order)
+                    const int qpg = p.pool_k >> 5;  // quarters per group: 2 or 4
+                    for (int i = tid; i < EBN * (4 / qpg); i += kEpiThreads) {
+                        const int gi = i / EBN, colb = h * EBN + (i - gi * EBN);
+                        uint32_t best = 0u;
+                        int arg = 0;
+                        for (int qq = 0; qq < qpg; ++qq) {
+                            const uint32_t m = sPoolV[(gi * qpg + qq) * BN + colb];
+                            if (m > best) { best = m; arg = qq * 32 + sPoolA[(gi * qpg + qq) * BN + colb]; }
+                        }
+                        const long long grow0 = tile * TM + gi * p.pool_k;
+                        if (grow0 < p.rows && n0 + colb < p.n) {
+                            uint32_t mm = best ^ sNeg[colb];
+                            mm = (mm & 0x80000000u) ? (mm & 0x7FFFFFFFu) : ~mm;
+                            const long long g = grow0 / p.pool_k;
+                            p.pool_val[g * p.n + n0 + colb] = __uint_as_float(mm);
+                            p.pool_arg[g * p.n + n0 + colb] = arg;
+                        }
+                    }
+                }
                 // pass 2: 16-byte pieces, coalesced stores, column sums in registers
                 if (col0 < p.n) {
                     float ps_[8], ph_[8];
@@ -551,7 +639,7 @@ template <int BN, int AMODE, bool MASK, bool SPLIT = false>
 int launch_tc(const GemmArgs& a, cudaStream_t stream) {
     using Cfg = TcCfg<BN, AMODE, SPLIT>;
     const int kpad = (a.kdim + TK - 1) / TK * TK;
-    const size_t smem = (size_t)Cfg::kNst * Cfg::kStage + Cfg::kSC + (size_t)Cfg::kNCoef * kpad * 4 + 5 * BN * 4 + 256 + 1024;
+    const size_t smem = (size_t)Cfg::kNst * Cfg::kStage + Cfg::kSC + (size_t)Cfg::kNCoef * kpad * 4 + 5 * BN * 4 + Cfg::kPool + 256 + 1024;
     static DeviceOnce once;
     if (once.first()) {
         PN2_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, MASK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,

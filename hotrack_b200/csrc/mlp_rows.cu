@@ -498,6 +498,52 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
     }
 }
 
+// ---- pooled values already taken in the GEMM epilogue (pn2_mlp_gemm_fwd[_bn]_pool): BatchNorm + ReLU of the selected
+// extreme, (groups, C) -> channel-major (B, C, S), channel sums.  The ReLU decision is taken on the stored (hi plane) y of
+// the selected row -- what pool_bwd masks by --, the value comes from the fp32 accumulator.
+__global__ void __launch_bounds__(256) pool_finalize_kernel(int s_count, int k, int c, const float* __restrict__ val,
+                                                             const int* __restrict__ arg, const act_t* __restrict__ y, int y_ld,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             float* __restrict__ out_cm, float* __restrict__ chan_sums) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int ch = c0 + tx;
+    float sc = 0.f, sh = 0.f;
+    if (ch < c) { sc = scale[ch]; sh = shift[ch]; }
+    for (int j = ty; j < 32; j += 8) {
+        const int s = s0 + j;
+        float r = 0.f;
+        if (s < s_count && ch < c) {
+            const size_t g = (size_t)b * s_count + s;
+            const float yv = h_to_f(y[(g * k + arg[g * c + ch]) * y_ld + ch]);
+            r = fmaf(yv, sc, sh) > 0.f ? fmaxf(fmaf(val[g * c + ch], sc, sh), 0.f) : 0.f;
+        }
+        tile[j][tx] = r;
+    }
+    __syncthreads();
+    float csum = 0.f;
+    for (int j = ty; j < 32; j += 8) {
+        const int cc = c0 + j, s = s0 + tx;
+        if (cc < c && s < s_count) {
+            const float v = tile[tx][j];
+            out_cm[((size_t)b * c + cc) * s_count + s] = v;
+            csum += v;
+        }
+    }
+    if (chan_sums) {  // lanes of a warp hold 32 groups of channel c0 + ty (+ 8, ...): one row j per iteration, summed per j
+        // csum mixes the rows j = ty, ty + 8, ...; redo it per channel
+        for (int j = ty; j < 32; j += 8) {
+            const int cc = c0 + j, s = s0 + tx;
+            float v = (cc < c && s < s_count) ? tile[tx][j] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            if (tx == 0 && cc < c && v != 0.f) atomicAdd(chan_sums + cc, v);
+        }
+    }
+    (void)csum;
+}
+
 // ---- few groups (given-centre SA: 21 joints; group-all): one CTA per group at a time, the K rows of the group split
 // over the 8 warps, a lane owning 8 consecutive channels (16-byte row pieces), slabs of 256 channels.
 constexpr int kSlab = 256;
@@ -1020,6 +1066,20 @@ extern "C" int pn2_pool_fwd_x2(int b, int s, int k, int c, const void* y, const 
         pool_fwd_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
     }
     PN2_CHECK_LAUNCH("pool_fwd_kernel");
+    return 0;
+}
+
+extern "C" int pn2_pool_finalize(int b, int s, int k, int c, const float* pool_val, const int* pool_arg, const void* y,
+                                 int y_ld, const float* scale, const float* shift, float* out_cm, float* chan_sums,
+                                 pn2_stream_t stream) {
+    if (b < 0 || s <= 0 || k <= 0 || c <= 0) return fail_arg("pn2_pool_finalize", "bad size");
+    if (b == 0) return 0;
+    if (b > 65535) return fail_arg("pn2_pool_finalize", "b > 65535");
+    if (!pool_val || !pool_arg || !y || !scale || !shift || !out_cm) return fail_arg("pn2_pool_finalize", "null pointer");
+    dim3 grid((s + 31) / 32, (c + 31) / 32, b);
+    pool_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(s, k, c, pool_val, pool_arg, (const act_t*)y, y_ld, scale, shift,
+                                                                  out_cm, chan_sums);
+    PN2_CHECK_LAUNCH("pool_finalize_kernel");
     return 0;
 }
 

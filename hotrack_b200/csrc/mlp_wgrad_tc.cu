@@ -14,19 +14,23 @@
 // all rows of the CTA.
 //
 //   raw ring   [NR] stages of WR = 64 rows x [dZ 128 | Y 128 | X kw] columns, row-major (pitch = an odd number of 16-byte
-//              units: conflict-free ldmatrix), filled by cp.async, D = NR - 2 stages in flight
+//              units: conflict-free ldmatrix)
 //   T ring     [NT] slots of 4 sub-tiles (16 rows = one MMA K step each) in the UMMA K-major no-swizzle layout: 8x8 core
 //              matrices (8 channels x 8 rows, 128 contiguous bytes), a channel group's two K halves 128 B apart (LBO),
 //              channel groups 256 B apart (SBO)
-//   8 producer warps  cp.async the raw stage; per 16x16 block: ldmatrix.x4.trans (the fragment now holds 8x8 blocks
-//                     channel-major) of dZ and Y -> cA*dZ + cB*Y + cC in fp32 -> bf16 -> stmatrix.x4 = four core matrices;
-//                     X blocks: BatchNorm+ReLU -> bf16 -> stmatrix; fence.proxy.async, mbarrier arrive
+//   4 loader warps    cp.async of the raw stages as far ahead as there are free slots; the copies report their own
+//                     completion to the stage's mbarrier (cp.async.mbarrier.arrive.noinc): nobody who computes waits on
+//                     memory it has just asked for
+//   8 transposer warps  per 16x16 block: ldmatrix.x4.trans (the fragment now holds 8x8 blocks channel-major) of dZ and Y
+//                     -> cA*dZ + cB*Y + cC in fp32 -> bf16 -> stmatrix.x4 = four core matrices; X blocks: BatchNorm+ReLU ->
+//                     bf16 -> stmatrix; fence.proxy.async, mbarrier arrive; the raw slot goes back to the loaders
 //   1 MMA warp        one lane: per stage 4 x tcgen05.mma (M = 128 output channels, N = kw input channels, K = 16 rows),
 //                     tcgen05.commit frees the T slot; a final commit publishes the accumulator
-//   4 epilogue warps  tcgen05.ld, vector reductions (red.global.add.v4.f32) into dW
+//   4 epilogue warps  parked in a named barrier during the main loop (a spinning mbarrier wait took 15 % of the issue
+//                     slots), then tcgen05.ld and vector reductions (red.global.add.v4.f32) into dW
 //
-// 64-row stages: one producer barrier / mbarrier hand-shake per 4 K steps (the 16-row version of round 1 spent 2.4 us per
-// stage on hand-shakes with the MMA warp idle 57 % of the time).
+// 64-row stages: one hand-shake per 4 K steps (the 16-row version of round 1 spent 2.4 us per stage on hand-shakes with
+// the MMA warp idle 57 % of the time; 32-row stages measured slower than 64 here too).
 // Grid: (row splits, [128-channel output tiles] x [input-channel tiles of kw <= 128]); one CTA per SM.
 // Bound: HBM reads rows*(2n + k)*2 bytes (X is re-read once per output tile, dZ / Y once per input tile: L2 hits when the
 // tiles of the same rows run side by side).
@@ -42,9 +46,11 @@ namespace {
 constexpr int WR = 64;            // rows per stage (32-row stages measured slower: the per-stage hand-shakes dominate)
 constexpr int WSUB = WR / 16;     // MMA K steps per stage
 constexpr int MT = 128;           // output channels per CTA = UMMA M
-constexpr int kWEpiWarps = 4, kWMmaWarp = 4, kWProdWarps = 8;
-constexpr int kWProdThreads = kWProdWarps * 32;
-constexpr int kWThreads = (kWEpiWarps + 1 + kWProdWarps) * 32;
+constexpr int kWEpiWarps = 4, kWMmaWarp = 4, kWProdWarps = 8, kWLoadWarps = 4;
+constexpr int kWProdThreads = kWProdWarps * 32;   // transposers: warps 5..12
+constexpr int kWLoadThreads = kWLoadWarps * 32;   // loaders: warps 13..16
+constexpr int kWLoadWarp0 = kWEpiWarps + 1 + kWProdWarps;
+constexpr int kWThreads = (kWEpiWarps + 1 + kWProdWarps + kWLoadWarps) * 32;
 constexpr int kWSmem = 225 * 1024;
 constexpr int kMaxKw = 128;   // wider tiles leave no room for a 3-stage raw ring next to the two T slots
 
@@ -90,10 +96,12 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
     unsigned char* sT = sRaw + ((w.nr * raw_bytes + 127) & ~127);
     float* sCo = reinterpret_cast<float*>(sT + w.nt * t_bytes);  // [3][MT] cA cB cC, then [2][kw] scale shift
     uint64_t* bars = reinterpret_cast<uint64_t*>(sCo + 3 * MT + 2 * w.kw);
-    uint64_t* full = bars;            // [nt]
-    uint64_t* empty = bars + w.nt;    // [nt]
+    uint64_t* full = bars;            // [nt]  transposers -> MMA
+    uint64_t* empty = bars + w.nt;    // [nt]  MMA -> transposers
     uint64_t* done = bars + 2 * w.nt;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * w.nt + 1);
+    uint64_t* rfull = done + 1;       // [nr]  loaders (cp.async completion) -> transposers
+    uint64_t* rempty = rfull + w.nr;  // [nr]  transposers -> loaders
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + w.nr);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long stages = (p.rows + WR - 1) / WR;
@@ -115,6 +123,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
             mbar_init(&empty[i], 1);
         }
         mbar_init(done, 1);
+        for (int i = 0; i < w.nr; ++i) {
+            mbar_init(&rfull[i], kWLoadThreads);
+            mbar_init(&rempty[i], kWProdWarps);
+        }
         mbar_fence_init();
     }
     if (warp == kWMmaWarp) {
@@ -129,18 +141,60 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp > kWMmaWarp) {
-        // ================================ producers ================================
-        const int pt = tid - (kWMmaWarp + 1) * 32;   // 0..255
-        const int pw = pt >> 5;                       // producer warp 0..7
-        const uint32_t raw0 = smem_u32(sRaw), t0 = smem_u32(sT);
-        const int D = w.nr - 2;  // a raw slot is refilled two iterations after it was transposed: one producer barrier in between
-        // cp.async: warp pw brings rows pw, pw + 8, ...; a lane walks the USEFUL 16-byte pieces of a row -- the dZ and Y
-        // columns of this CTA's channel blocks and the X columns of its input-channel tile
+    if (warp >= kWLoadWarp0) {
+        // ================================ loaders ================================
+        // cp.async of the raw stages, as far ahead as there are free slots; the copies report their own completion to the
+        // stage's mbarrier (cp.async.mbarrier.arrive.noinc), these warps never wait for data.  Warp lw brings rows lw,
+        // lw + 4, ...; a lane walks the USEFUL 16-byte pieces of a row -- the dZ and Y columns of this CTA's channel blocks
+        // and the X columns of its input-channel tile.
+        const int lw = warp - kWLoadWarp0;
+        const uint32_t raw0 = smem_u32(sRaw);
         const int nn8 = nb * 2, upr = 2 * nn8 + 2 * kb;  // pieces per row: [dZ nn8][Y nn8][X 2 kb]
-        // transposition: a warp owns the sub-tile PAIR pw & 1 (2 x 16 rows) of channel blocks pw >> 1, + 4, ...: no per-unit
-        // index arithmetic, the per-channel constants are fetched once per block, and the two sub-tiles are two
-        // independent ldmatrix -> arithmetic -> stmatrix chains in flight per warp
+        long long i_s = blockIdx.x;
+        int slot = 0;
+        uint32_t phase = 0;
+        for (long long c = 0; c < mine; ++c) {
+            mbar_wait(&rempty[slot], phase ^ 1);  // the transposers have read this slot's previous stage
+            const uint32_t st = raw0 + slot * raw_bytes;
+            const long long row0 = i_s * WR;
+            for (int j = lane; j < upr; j += 32) {
+                int colbyte;            // byte offset of the piece inside the raw row
+                const unsigned char* src;
+                bool ok;
+                if (j < nn8) {
+                    colbyte = j * 16; ok = j * 8 < n_here;
+                    src = reinterpret_cast<const unsigned char*>(p.dz + n0 + j * 8);
+                } else if (j < 2 * nn8) {
+                    const int jj = j - nn8;
+                    colbyte = 256 + jj * 16; ok = jj * 8 < n_here;
+                    src = reinterpret_cast<const unsigned char*>(p.y + n0 + jj * 8);
+                } else {
+                    const int jj = j - 2 * nn8;
+                    colbyte = 512 + jj * 16; ok = true;
+                    src = reinterpret_cast<const unsigned char*>(p.x + k0 + jj * 8);
+                }
+                const long long ldb = 2LL * (j < nn8 ? p.dz_ld : (j < 2 * nn8 ? p.y_ld : p.x_ld));  // row pitch in bytes
+#pragma unroll 4
+                for (int r = 0; r < WR / kWLoadWarps; ++r) {
+                    const int prow = lw + r * kWLoadWarps;
+                    const long long row = row0 + prow;
+                    const bool in = ok && row < p.rows;   // past the end / padded half block: zero-fill
+                    cp_async16_s(st + prow * rp + colbyte, in ? src + row * ldb : src, in ? 16 : 0);
+                }
+            }
+            cp_async_mbar_arrive_noinc(&rfull[slot]);
+            i_s += gridDim.x;
+            if (++slot == w.nr) { slot = 0; phase ^= 1; }
+        }
+        cp_async_wait_all();  // nothing of this thread's may be in flight when the CTA's shared memory goes away
+    } else if (warp > kWMmaWarp) {
+        // ================================ transposers ================================
+        const int pt = tid - (kWMmaWarp + 1) * 32;   // 0..255
+        const int pw = pt >> 5;                       // transposer warp 0..7
+        const uint32_t raw0 = smem_u32(sRaw), t0 = smem_u32(sT);
+        // a warp owns the sub-tile PAIR pw & 1 (2 x 16 rows) of channel blocks pw >> 1, + 4, ...: no per-unit index
+        // arithmetic, the per-channel constants are fetched once per block, and the two sub-tiles are two independent
+        // ldmatrix -> arithmetic -> stmatrix chains in flight per warp
         static_assert(WSUB == 4 && kWProdWarps == 8, "the warp -> (sub-tile pair, block) map assumes 4 sub-tiles, 8 warps");
         const int sub0 = (pw & 1) * 2, blk0 = pw >> 1;
         constexpr int kBlkStep = 4;
@@ -150,50 +204,12 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         const uint32_t st_off = (uint32_t)(lane >> 4) * 256 + ((lane >> 3) & 1) * 128 + (lane & 7) * 16;
         // fragment of matrix q: channel blk*16 + (q >> 1)*8 + lane/4, rows sub*16 + (q & 1)*8 + 2*(lane%4) + {0,1}
         const int ch_lo = lane >> 2, r_lo = sub0 * 16 + 2 * (lane & 3);
-        long long i_s = blockIdx.x, p_s = blockIdx.x;
-        int i_slot = 0, p_slot = 0, t_slot = 0;
-        uint32_t t_phase = 0;
-        for (long long c = 0; c < mine + D; ++c) {
-            if (c < mine) {
-                const uint32_t st = raw0 + i_slot * raw_bytes;
-                const long long row0 = i_s * WR;
-                for (int j = lane; j < upr; j += 32) {
-                    int colbyte;            // byte offset of the piece inside the raw row
-                    const unsigned char* src;
-                    bool ok;
-                    if (j < nn8) {
-                        colbyte = j * 16; ok = j * 8 < n_here;
-                        src = reinterpret_cast<const unsigned char*>(p.dz + n0 + j * 8);
-                    } else if (j < 2 * nn8) {
-                        const int jj = j - nn8;
-                        colbyte = 256 + jj * 16; ok = jj * 8 < n_here;
-                        src = reinterpret_cast<const unsigned char*>(p.y + n0 + jj * 8);
-                    } else {
-                        const int jj = j - 2 * nn8;
-                        colbyte = 512 + jj * 16; ok = true;
-                        src = reinterpret_cast<const unsigned char*>(p.x + k0 + jj * 8);
-                    }
-                    const long long ldb = 2LL * (j < nn8 ? p.dz_ld : (j < 2 * nn8 ? p.y_ld : p.x_ld));  // row pitch in bytes
-#pragma unroll
-                    for (int r = 0; r < WR / kWProdWarps; ++r) {
-                        const int prow = pw + r * kWProdWarps;
-                        const long long row = row0 + prow;
-                        const bool in = ok && row < p.rows;   // past the end / padded half block: zero-fill
-                        cp_async16_s(st + prow * rp + colbyte, in ? src + row * ldb : src, in ? 16 : 0);
-                    }
-                }
-                i_s += gridDim.x;
-                if (++i_slot == w.nr) i_slot = 0;
-            }
-            cp_async_commit();
-            if (c >= D) {
-                switch (D) {  // this thread's pieces of stage c - D have landed
-                    case 1: cp_wait<1>(); break;
-                    case 2: cp_wait<2>(); break;
-                    case 3: cp_wait<3>(); break;
-                    default: cp_wait<4>(); break;
-                }
-                prod_bar();                                  // ... and everybody else's
+        long long p_s = blockIdx.x;
+        int p_slot = 0, t_slot = 0;
+        uint32_t p_phase = 0, t_phase = 0;
+        for (long long c = 0; c < mine; ++c) {
+            {
+                mbar_wait(&rfull[p_slot], p_phase);          // every copy of this raw stage has landed
                 mbar_wait(&empty[t_slot], t_phase ^ 1);      // the MMAs that read this T slot have completed
                 const uint32_t rs = raw0 + p_slot * raw_bytes + ld_off;
                 const uint32_t ts = t0 + t_slot * t_bytes + st_off;
@@ -263,8 +279,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                 }
                 fence_proxy_async();
                 mbar_arrive(&full[t_slot]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rempty[p_slot]);  // this warp has read everything it needs from the raw slot
                 p_s += gridDim.x;
-                if (++p_slot == w.nr) p_slot = 0;
+                if (++p_slot == w.nr) { p_slot = 0; p_phase ^= 1; }
                 if (++t_slot == w.nt) { t_slot = 0; t_phase ^= 1; }
             }
         }
@@ -358,12 +376,13 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
     const int ppr = (2 * MT + w.kw) / 8;
     const size_t raw = (size_t)WR * (ppr * 16 + 16);
     const size_t tb = (size_t)WSUB * (MT + w.kw) * 32;
-    const size_t fixed = (size_t)(3 * MT + 2 * w.kw) * 4 + 256 + 256;
-    // T ring: 2 slots (the tensor core is at most one stage behind), 3 with 32-row stages; raw ring: what is left, 3..6 slots
-    w.nt = WR >= 64 ? 2 : 3;
+    const size_t fixed = (size_t)(3 * MT + 2 * w.kw) * 4 + 256 + 256;  // constants, barriers (<= 19 x 8 bytes), alignment slack
+    // T ring: 2 slots (the tensor core is at most one stage behind); raw ring: what is left, 2..6 slots (the loaders run
+    // ahead by as many stages as there are free slots)
+    w.nt = 2;
     long long nr = ((long long)kWSmem - (long long)fixed - (long long)w.nt * (long long)tb) / (long long)raw;
     if (nr > 6) nr = 6;
-    if (nr < 3) return fail_arg("pn2_mlp_gemm_wgrad", "stage does not fit shared memory");
+    if (nr < 2) return fail_arg("pn2_mlp_gemm_wgrad", "stage does not fit shared memory");
     w.nr = (int)nr;
     const size_t smem = fixed + ((w.nr * raw + 127) / 128 * 128) + w.nt * tb;
     int dev = 0;

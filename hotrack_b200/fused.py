@@ -140,6 +140,10 @@ ACTIVE_PLAN = None  # set by TrainStep around its forward pass
 # the round-1 engine), "all" runs every layer of every stack two-plane (fp32-class forward, for strict comparisons).
 PRECISE_MODE = "auto"   # "auto": as the modules ask | "off": never | "all": every layer of every stack
 
+# Max-pool of the SA stacks taken in the last layer's GEMM epilogue (pn2_mlp_gemm_fwd[_bn]_pool + pn2_pool_finalize) instead of
+# a pn2_pool_fwd pass over the layer's output; False = the separate pooling kernel (cross-check).
+EPILOGUE_POOL = True
+
 
 def set_precise(mode):
     """'auto' (default) | 'off' | 'all'; booleans are accepted for on/off."""
@@ -353,6 +357,9 @@ class _MlpStack(Function):
         arena = _zeros(2 * sum(widths) + widths[-1] + nl, dev)
         counters = arena[2 * sum(widths) + widths[-1]:]  # one zeroed word per layer (GEMM tail: BatchNorm finalisation)
         a_off = 0
+        # last layer of a pooled stack: the max over the pool_k rows of a group is taken in the GEMM's epilogue
+        epi_pool = EPILOGUE_POOL and pool_k in (16, 32, 64, 128) and R % pool_k == 0
+        pool_val = pool_arg = None
         for l in range(nl):
             w, bias, gamma, beta = params[4 * l: 4 * l + 4]
             bn = bns[l]
@@ -366,8 +373,14 @@ class _MlpStack(Function):
                 x_lo = torch.zeros_like(x)
             wbuf = ACTIVE_PLAN.lookup(w, kp, two) if (ACTIVE_PLAN is not None and training) else _prep_weight(w, kp, two)
             L.w, w_lo = wbuf[0], (wbuf[1] if two else None)
-            yp = torch.empty(2 if two else 1, R, L.cout, dtype=_F16, device=dev)
-            L.y, y_lo = yp[0], (yp[1] if two else None)
+            pooled_here = epi_pool and l == nl - 1
+            # (the pooled layer's lo plane would only feed the pooling: the epilogue pools the fp32 accumulators instead)
+            keep_lo = two and not pooled_here
+            yp = torch.empty(2 if keep_lo else 1, R, L.cout, dtype=_F16, device=dev)
+            L.y, y_lo = yp[0], (yp[1] if keep_lo else None)
+            if pooled_here:
+                pool_val = torch.empty(R // pool_k, L.cout, dtype=torch.float32, device=dev)
+                pool_arg = torch.empty(B, groups, L.cout, dtype=torch.int32, device=dev)
             consts = torch.empty(6, L.cout, dtype=torch.float32, device=dev)
             L.scale, L.shift, L.mean, L.rstd, cen, cen_true = (consts[i] for i in range(6))
             # Centring constant.  Training keeps it as state on the BatchNorm module: the GEMM tail of step t leaves the
@@ -390,21 +403,31 @@ class _MlpStack(Function):
                 stats = arena[a_off:a_off + 2 * L.cout]
                 a_off += 2 * L.cout
                 track = bn.track_running_stats and bn.running_mean is not None
-                _lib.call("pn2_mlp_gemm_fwd_bn_x2", R, kp, L.cout, x.data_ptr(), _p(x_lo) if two else 0, x_ld, _p(xs), _p(xh),
-                          L.w.data_ptr(), _p(w_lo), cen.data_ptr(), L.y.data_ptr(), _p(y_lo), L.cout, stats.data_ptr(),
-                          counters[l].data_ptr(),
-                          bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias), cen_true.data_ptr(), _bn_momentum(bn),
-                          float(bn.eps), _p(bn.running_mean) if track else 0, _p(bn.running_var) if track else 0,
-                          _p(bn.num_batches_tracked) if track else 0, L.scale.data_ptr(), L.shift.data_ptr(),
-                          L.mean.data_ptr(), L.rstd.data_ptr(), _p(next_cen), st)
+                args = (R, kp, L.cout, x.data_ptr(), _p(x_lo) if two else 0, x_ld, _p(xs), _p(xh),
+                        L.w.data_ptr(), _p(w_lo), cen.data_ptr(), L.y.data_ptr(), _p(y_lo), L.cout, stats.data_ptr(),
+                        counters[l].data_ptr(),
+                        bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias), cen_true.data_ptr(), _bn_momentum(bn),
+                        float(bn.eps), _p(bn.running_mean) if track else 0, _p(bn.running_var) if track else 0,
+                        _p(bn.num_batches_tracked) if track else 0, L.scale.data_ptr(), L.shift.data_ptr(),
+                        L.mean.data_ptr(), L.rstd.data_ptr(), _p(next_cen))
+                if pooled_here:
+                    _lib.call("pn2_mlp_gemm_fwd_bn_pool", *args, pool_k, pool_val.data_ptr(), pool_arg.data_ptr(), st)
+                else:
+                    _lib.call("pn2_mlp_gemm_fwd_bn_x2", *args, st)
             else:
                 _lib.call("pn2_bn_eval_affine", L.cout, bn.weight.data_ptr(), bn.bias.data_ptr(), _p(bias),
                           cen_true.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps),
                           L.scale.data_ptr(), L.shift.data_ptr(), st)
-                _lib.call("pn2_mlp_gemm_fwd_x2", R, kp, L.cout, x.data_ptr(), _p(x_lo) if two else 0, x_ld, _p(xs), _p(xh),
-                          L.w.data_ptr(), _p(w_lo), cen.data_ptr(), L.y.data_ptr(), _p(y_lo), L.cout, 0, st)
+                args = (R, kp, L.cout, x.data_ptr(), _p(x_lo) if two else 0, x_ld, _p(xs), _p(xh),
+                        L.w.data_ptr(), _p(w_lo), cen.data_ptr(), L.y.data_ptr(), _p(y_lo), L.cout, 0)
+                if pooled_here:
+                    _lib.call("pn2_mlp_gemm_fwd_pool", *args, pool_k, bn.weight.data_ptr(), pool_val.data_ptr(),
+                              pool_arg.data_ptr(), st)
+                else:
+                    _lib.call("pn2_mlp_gemm_fwd_x2", *args, st)
             layers.append(L)
             x, x_lo, x_ld, xs, xh, kp = L.y, y_lo, L.cout, L.scale, L.shift, L.cout
+            last_two = two
 
         # ---- BN + ReLU (+ max over the group) -> module output
         last = layers[-1]
@@ -414,14 +437,18 @@ class _MlpStack(Function):
         chan_sums = argmax = None
         if pool_k > 1:
             chan_sums = arena[2 * sum(widths):2 * sum(widths) + widths[-1]]
-            argmax = torch.empty(B, groups, C, dtype=torch.int32, device=dev) if training else None
-        if not rows_only:  # rows_only: the caller promises that only the attached row form is read (backbone FP1 -> head)
+            argmax = pool_arg if pool_arg is not None else (torch.empty(B, groups, C, dtype=torch.int32, device=dev)
+                                                            if training else None)
+        if pool_val is not None:
+            _lib.call("pn2_pool_finalize", B, groups, pool_k, C, pool_val.data_ptr(), pool_arg.data_ptr(), last.y.data_ptr(), C,
+                      last.scale.data_ptr(), last.shift.data_ptr(), out.data_ptr(), _p(chan_sums), st)
+        elif not rows_only:  # rows_only: the caller promises that only the attached row form is read (backbone FP1 -> head)
             _lib.call("pn2_pool_fwd_x2", B, groups, pool_k, C, last.y.data_ptr(), _p(x_lo), C, last.scale.data_ptr(),
                       last.shift.data_ptr(), out.data_ptr(), _p(chan_sums), _p(argmax), st)
         if pool_k > 1:
             # pooled features go to the next fused consumer as bf16 rows centred on their channel mean
             inv = 1.0 / (B * groups)
-            two_out = x_lo is not None  # the last layer was two-plane: so are the pooled rows
+            two_out = last_two  # the last layer was two-plane: so are the pooled rows
             out_rows = torch.empty(2 if two_out else 1, B * groups, C, dtype=_F16, device=dev)
             _lib.call("pn2_to_rows_x2", B, C, groups, out.data_ptr(), chan_sums.data_ptr(), inv, out_rows[0].data_ptr(),
                       out_rows[1].data_ptr() if two_out else 0, C, st)
@@ -666,7 +693,7 @@ def alg_bytes(name, a):
     if name in ("pn2_mlp_gemm_fwd", "pn2_mlp_gemm_fwd_bn"):
         rows, kdim, n = a[:3]
         return rows * (kdim + n) * 2 + n * kdim * 2
-    if name in ("pn2_mlp_gemm_fwd_x2", "pn2_mlp_gemm_fwd_bn_x2"):
+    if name in ("pn2_mlp_gemm_fwd_x2", "pn2_mlp_gemm_fwd_bn_x2", "pn2_mlp_gemm_fwd_pool", "pn2_mlp_gemm_fwd_bn_pool"):
         rows, kdim, n = a[:3]
         pin, pout = (2 if a[4] else 1), (2 if a[12] else 1)
         return rows * (kdim * pin + n * pout) * 2 + n * kdim * 2 * pin

@@ -181,6 +181,29 @@ int pn2_pool_fwd_x2(int b, int s, int k, int c, const void* y, const void* y_lo,
  * record whose last int ("two") is non-zero writes the lo plane right behind the hi plane (w_f16 + n*kp). */
 int pn2_mlp_prep_weights_x2(int n, int k_true, int kp, const float* w, void* w_hi, void* w_lo, pn2_stream_t stream);
 
+/* ---- MAX-POOL IN THE GEMM EPILOGUE ---------------------------------------------------------------------------------
+ * Last layer of a pooled stack (SA scales: pool_k neighbours per group): pn2_mlp_gemm_fwd[_bn]_x2 that additionally takes,
+ * per (group, column), the extreme over the group's pool_k rows of (accumulator - center) -- the maximum where gamma >= 0,
+ * the minimum where gamma < 0, since BatchNorm's scale has gamma's sign and max_k relu(s*y_k + t) = relu(s*extreme + t) --
+ * and the row that holds it (first in row order).  pool_k in {16, 32, 64, 128}, rows % pool_k == 0;
+ * pool_val / pool_arg: [rows / pool_k][n].  No pn2_pool_fwd launch, no second pass over y.  (_pool: pool_gamma given
+ * explicitly; _bn_pool: the BatchNorm gamma.) */
+int pn2_mlp_gemm_fwd_pool(long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                          const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                          const float* center, void* y, void* y_lo, int y_ld, float* stats, int pool_k,
+                          const float* pool_gamma, float* pool_val, int* pool_arg, pn2_stream_t stream);
+int pn2_mlp_gemm_fwd_bn_pool(long long rows, int kdim, int n, const void* x, const void* x_lo, int x_ld,
+                             const float* in_scale, const float* in_shift, const void* w, const void* w_lo,
+                             const float* center, void* y, void* y_lo, int y_ld, float* stats, unsigned int* counter,
+                             const float* gamma, const float* beta, const float* conv_bias, const float* center_true,
+                             float momentum, float eps, float* running_mean, float* running_var,
+                             long long* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
+                             float* next_center, int pool_k, float* pool_val, int* pool_arg, pn2_stream_t stream);
+/* BatchNorm + ReLU of the pooled extremes -> out_cm (B,C,S) fp32 and optional channel sums; y: the layer's stored (hi
+ * plane) output, read at the selected rows for the ReLU decision the backward pass will repeat. */
+int pn2_pool_finalize(int b, int s, int k, int c, const float* pool_val, const int* pool_arg, const void* y, int y_ld,
+                      const float* scale, const float* shift, float* out_cm, float* chan_sums, pn2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

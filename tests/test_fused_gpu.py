@@ -128,6 +128,56 @@ def test_gemm_fwd_two_plane(lib, cuda, R, K, N, affine):
     assert torch.equal(y1, y2)
 
 
+@pytest.mark.parametrize("G,K,Kd,N,two,affine", [(300, 32, 32, 64, True, True), (131, 32, 64, 128, True, False),
+                                                    (50, 16, 448, 192, False, False), (77, 64, 128, 192, False, True),
+                                                    (33, 128, 128, 512, True, True), (40, 16, 32, 32, True, False),
+                                                    (21, 64, 832, 128, False, False)])
+def test_gemm_epilogue_pooling(lib, cuda, G, K, Kd, N, two, affine):
+    """pn2_mlp_gemm_fwd_pool: the extreme of (accumulator - centre) over each group's K rows, taken in the GEMM epilogue
+    (maximum where gamma >= 0, minimum where gamma < 0) and the row holding it, against the same GEMM's stored output;
+    then pn2_pool_finalize against pn2_pool_fwd on that output."""
+    g = torch.Generator(device="cpu").manual_seed(G + K + N)
+    R = G * K
+    x32 = torch.randn(R, Kd, generator=g).to(cuda)
+    w32 = (torch.randn(N, Kd, generator=g) / Kd ** 0.5).to(cuda)
+    xh, xl = _split(x32)
+    wh, wl = _split(w32)
+    sc = sh = None
+    if affine:
+        sc = (torch.rand(Kd, generator=g) + 0.5).to(cuda)
+        sh = (torch.randn(Kd, generator=g) * 0.3).to(cuda)
+    cen = (torch.randn(N, generator=g) * 0.2).to(cuda)
+    gamma = torch.randn(N, generator=g).to(cuda)          # both signs
+    yh = torch.empty(R, N, dtype=HF, device=cuda)
+    yl = torch.empty(R, N, dtype=HF, device=cuda) if two else None
+    val = torch.full((G, N), float("nan"), device=cuda)
+    arg = torch.full((G, N), -1, dtype=torch.int32, device=cuda)
+    stats = torch.zeros(2, N, device=cuda)
+    lib.call("pn2_mlp_gemm_fwd_pool", R, Kd, N, xh.data_ptr(), xl.data_ptr() if two else 0, Kd, 0 if sc is None else sc.data_ptr(),
+             0 if sh is None else sh.data_ptr(), wh.data_ptr(), wl.data_ptr() if two else 0, cen.data_ptr(), yh.data_ptr(),
+             yl.data_ptr() if two else 0, N, stats.data_ptr(), K, gamma.data_ptr(), val.data_ptr(), arg.data_ptr(), _st())
+    y = (yh.float() + (yl.float() if two else 0)).view(G, K, N)   # what the epilogue pooled, up to the storage rounding
+    signed = torch.where(gamma >= 0, y, -y)
+    want_val = torch.where(gamma >= 0, signed.max(1)[0], -signed.max(1)[0])
+    assert torch.isfinite(val).all() and (arg >= 0).all() and (arg < K).all()
+    tol = 1e-5 if two else 2e-3
+    torch.testing.assert_close(val, want_val, rtol=tol, atol=tol)
+    picked = signed.gather(1, arg.long().unsqueeze(1)).squeeze(1)      # the row the kernel names holds (nearly) the extreme
+    torch.testing.assert_close(picked, signed.max(1)[0], rtol=tol, atol=tol)
+    # finalize vs the separate pooling kernel on the stored output (B = 1, S = G)
+    scale = gamma * (torch.rand(N, generator=g).to(cuda) + 0.5)
+    shift = (torch.randn(N, generator=g) * 0.2).to(cuda)
+    out_a, out_b = torch.empty(1, N, G, device=cuda), torch.empty(1, N, G, device=cuda)
+    cs_a, cs_b = torch.zeros(N, device=cuda), torch.zeros(N, device=cuda)
+    am = torch.empty(1, G, N, dtype=torch.int32, device=cuda)
+    lib.call("pn2_pool_finalize", 1, G, K, N, val.data_ptr(), arg.data_ptr(), yh.data_ptr(), N, scale.data_ptr(), shift.data_ptr(),
+             out_a.data_ptr(), cs_a.data_ptr(), _st())
+    lib.call("pn2_pool_fwd_x2", 1, G, K, N, yh.data_ptr(), yl.data_ptr() if two else 0, N, scale.data_ptr(), shift.data_ptr(),
+             out_b.data_ptr(), cs_b.data_ptr(), am.data_ptr(), _st())
+    torch.testing.assert_close(out_a, out_b, rtol=tol * 5, atol=tol * 5)
+    torch.testing.assert_close(cs_a, cs_b, rtol=1e-3, atol=tol * 5 * G ** 0.5 + 1e-3)
+
+
 def test_two_plane_row_kernels(lib, cuda):
     """to_rows / sa_build_rows / fp_build_rows / pool_fwd / prep_weights in two-plane form: hi + lo reproduces the fp32
     value to ~2^-21, and the hi plane equals the one-plane output."""

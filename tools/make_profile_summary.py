@@ -69,6 +69,8 @@ def main():
         # kernels bench.py can name as dominant: (ncu name fragment, grid) -> bench key
         wanted = {
             ("wgrad_kernel<1>", "(6, 1, 49)"): "pn2_mlp_gemm_wgrad:131072,384,128,128,384,384",
+            ("wgrad_tc_kernel<1>", "(49, 3, 1)"): "pn2_mlp_gemm_wgrad:131072,384,128,128,384,384",
+            ("wgrad_tc_kernel<(bool)1>", "(49, 3, 1)"): "pn2_mlp_gemm_wgrad:131072,384,128,128,384,384",
             ("cm_to_rows_bwd_kernel", "(32, 32, 1)"): "pn2_pool_bwd:32,4096,1,384,0,0",
         }
         for (name, grid), v in seen.items():
