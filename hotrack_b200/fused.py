@@ -141,8 +141,11 @@ ACTIVE_PLAN = None  # set by TrainStep around its forward pass
 PRECISE_MODE = "auto"   # "auto": as the modules ask | "off": never | "all": every layer of every stack
 
 # Max-pool of the SA stacks taken in the last layer's GEMM epilogue (pn2_mlp_gemm_fwd[_bn]_pool + pn2_pool_finalize) instead of
-# a pn2_pool_fwd pass over the layer's output; False = the separate pooling kernel (cross-check).
-EPILOGUE_POOL = True
+# a pn2_pool_fwd pass over the layer's output.  Validated (tests/test_fused_gpu.py::test_gemm_epilogue_pooling) but OFF by
+# default: measured on B200 it LOSES 0.33 ms per step -- these last layers have K = 32..128, their tiles are epilogue-bound
+# already, and one redux.sync + ballot per column per 32-row quarter (512 of each per 128x128 tile) more than doubles the
+# epilogue's issue time, while the vectorised pool_fwd pass it saves costs 0.17 ms in total.
+EPILOGUE_POOL = False
 
 
 def set_precise(mode):
