@@ -36,7 +36,7 @@ SIGNATURES = {
     "pn2_to_rows": [_i, _i, _i, _p, _p, _f, _p, _i, _p],
     "pn2_sa_build_rows": [_i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p],
     "pn2_fp_build_rows": [_i, _i, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p],
-    "pn2_mlp_center": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p],
+    "pn2_mlp_center": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _f, _i, _i, _p, _f, _i, _i, _p, _p, _p],
     "pn2_mlp_gemm_fwd": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p],
     "pn2_mlp_gemm_fwd_bn": [_ll, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p,
                             _p, _p],

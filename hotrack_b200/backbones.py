@@ -113,7 +113,10 @@ def _head(self, feats):
     """relu(bn1(conv1(x))) (backbones.py:69,131-132); fused engine: one 16-bit tensor-core stack."""
     if getattr(self.fp1, "engine", "ops") == "fused":  # the engine the backbone was BUILT with (as every SA / FP module)
         from . import fused
-        return fused.dense_stack(feats, [self.conv1], [self.bn1], self.training)
+        # rows_only_output (set by a caller that hands the features to fused gather stacks only -- HandTrackNet's q1 / q2):
+        # the 201 MB fp32 channel-major copy of the output is then never written
+        return fused.dense_stack(feats, [self.conv1], [self.bn1], self.training,
+                                 rows_only=getattr(self, "rows_only_output", False))
     return F.relu(self.bn1(self.conv1(feats)))
 
 

@@ -610,7 +610,9 @@ __global__ void __launch_bounds__(kWgradThreads, 2) wgrad_kernel(const WgradArgs
 __global__ void __launch_bounds__(256) center_kernel(long long rows, int kdim, int n, const act_t* __restrict__ x,
                                                       int x_ld, const float* __restrict__ sc,
                                                       const float* __restrict__ sh, const act_t* __restrict__ w,
-                                                      const float* __restrict__ in_offset, float* __restrict__ c,
+                                                      const float* __restrict__ off0, float off0_scale, int off0_start,
+                                                      int off0_count, const float* __restrict__ off1, float off1_scale,
+                                                      int off1_start, int off1_count, float* __restrict__ c,
                                                       float* __restrict__ c_true) {
     __shared__ float sM[1024];
     __shared__ float sO[1024];
@@ -637,7 +639,12 @@ __global__ void __launch_bounds__(256) center_kernel(long long rows, int kdim, i
         for (int j = 0; j < 16; ++j)
             if (j < ns) m += sc ? fmaxf(fmaf(v[j], a, b), 0.f) : v[j];
         sM[k] = m * inv;
-        sO[k] = in_offset ? in_offset[k] : 0.f;
+        // per-column constants the input rows were centred by: up to two column segments (the feature and the centre-feature
+        // segment of grouped rows), each sums[] * scale = a channel mean
+        float o = 0.f;
+        if (off0 && k >= off0_start && k < off0_start + off0_count) o = off0[k - off0_start] * off0_scale;
+        else if (off1 && k >= off1_start && k < off1_start + off1_count) o = off1[k - off1_start] * off1_scale;
+        sO[k] = o;
     }
     __syncthreads();
     if (col >= n) return;
@@ -827,14 +834,16 @@ extern "C" int pn2_mlp_prep_weights_multi(int n_layers, const void* descs, pn2_s
 }
 
 extern "C" int pn2_mlp_center(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
-                              const float* in_shift, const void* w, const float* in_offset, float* center,
-                              float* center_true, pn2_stream_t stream) {
+                              const float* in_shift, const void* w, const float* off0, float off0_scale, int off0_start,
+                              int off0_count, const float* off1, float off1_scale, int off1_start, int off1_count,
+                              float* center, float* center_true, pn2_stream_t stream) {
     if (int e = check_common("pn2_mlp_center", rows, kdim, n)) return e;
     if (rows == 0) return 0;
     if (kdim > 1024) return fail_arg("pn2_mlp_center", "kdim > 1024");
     if (!x || !w || !center || !center_true) return fail_arg("pn2_mlp_center", "null pointer");
     center_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rows, kdim, n, (const act_t*)x, x_ld, in_scale, in_shift,
-                                                                  (const act_t*)w, in_offset, center, center_true);
+                                                                  (const act_t*)w, off0, off0_scale, off0_start, off0_count, off1,
+                                                                  off1_scale, off1_start, off1_count, center, center_true);
     PN2_CHECK_LAUNCH("center_kernel");
     return 0;
 }

@@ -244,39 +244,87 @@ __device__ __forceinline__ void nn_weights(const float* d2, float (&w)[3]) {
 // interpolation per channel (interpolate_gpu.cu:168 rounding order) -- and writes them at output columns
 // skip_c + 8 piece: one 16-byte store when skip_c is a multiple of 8, else eight 2-byte stores (FP1: the skip is the three
 // coordinates).  The skip columns and the zero padding are copied by the same lanes afterwards.
-__global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildArgs a, int lanes) {
-    const int lane = threadIdx.x & 31;
-    const int rpw = 32 / lanes;                      // rows per warp
-    const int l = lane & (lanes - 1);
-    const long long row = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * rpw + lane / lanes;
-    const long long total = (long long)a.b * a.n;
-    if (row >= total) return;
-    const int b = (int)(row / a.n);
-    int id[3] = {0, 0, 0};
-    float w[3] = {1.f, 0.f, 0.f};
-    if (a.s > 1) {
+// 8 consecutive channels of a feature row with the per-channel constants already in registers (the three neighbours of an
+// interpolated point share them)
+__device__ __forceinline__ void row_vals8_pre(const RowSrc& s, size_t row, int ch, const float (&sc)[8], const float (&sh)[8],
+                                              float (&v)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(s.p + row * s.ld + ch));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&q);
+    float l[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 3; ++j) id[j] = a.idx[row * 3 + j];
-        nn_weights(a.dist2 + row * 3, w);
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = h2_to_f2(w[e]);
+        v[2 * e] = f.x; v[2 * e + 1] = f.y;
     }
+    if (s.lo) {
+        const uint4 ql = __ldg(reinterpret_cast<const uint4*>(s.lo + row * s.ld + ch));
+        const uint32_t* wl = reinterpret_cast<const uint32_t*>(&ql);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = h2_to_f2(wl[e]);
+            l[2 * e] = f.x; l[2 * e + 1] = f.y;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (s.scale) v[e] = fmaf(v[e], sc[e], sh[e]) > 0.f ? fmaf(v[e] + l[e], sc[e], sh[e]) : 0.f;  // ReLU decided on the hi plane
+        else v[e] += l[e];
+    }
+}
+
+constexpr int kFpStageLd = 256;  // widest output row the misaligned-store staging buffer holds
+
+__global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildArgs a, int lanes) {
+    // misaligned coarse segment (skip_c % 8 != 0) of a narrow row: the row is assembled in shared memory (2-byte stores)
+    // and leaves as 16-byte pieces
+    __shared__ __align__(16) act_t s_row[kThreads / 32][2][2][kFpStageLd];  // [warp][row of the warp][plane][column]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rpw = 32 / lanes;                      // rows per warp
+    const int l = lane & (lanes - 1), rsub = lane / lanes;
+    const long long row = ((long long)blockIdx.x * (kThreads / 32) + warp) * rpw + rsub;
+    const long long total = (long long)a.b * a.n;
+    const bool live = row < total;
     const int sc = a.skip.p ? a.skip.c : 0;
     const int cc = a.coarse.c;
-    act_t* o = a.out + (size_t)row * a.out_ld;
-    act_t* ol = a.out_lo ? a.out_lo + (size_t)row * a.out_ld : nullptr;
     const bool cvec = (cc & 7) == 0 && (a.coarse.ld & 7) == 0;
-    if (cvec) {
+    const bool staged = cvec && (sc & 7) != 0 && a.out_ld <= kFpStageLd && rpw <= 2;  // warp-uniform
+    act_t* o = nullptr;
+    act_t* ol = nullptr;
+    int b = 0;
+    int id[3] = {0, 0, 0};
+    float w[3] = {1.f, 0.f, 0.f};
+    if (live) {
+        b = (int)(row / a.n);
+        if (a.s > 1) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) id[j] = a.idx[row * 3 + j];
+            nn_weights(a.dist2 + row * 3, w);
+        }
+        o = staged ? &s_row[warp][rsub][0][0] : a.out + (size_t)row * a.out_ld;
+        ol = a.out_lo ? (staged ? &s_row[warp][rsub][1][0] : a.out_lo + (size_t)row * a.out_ld) : nullptr;
+    }
+    if (live && cvec) {
         const size_t r0 = (size_t)b * a.s + id[0], r1 = (size_t)b * a.s + id[1], r2 = (size_t)b * a.s + id[2];
         for (int cp = l; cp < (cc >> 3); cp += lanes) {
-            float v[8];
+            float ks[8], kh[8], v[8];
+            if (a.coarse.scale) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.coarse.scale + cp * 8)), s1 = __ldg(reinterpret_cast<const float4*>(a.coarse.scale + cp * 8 + 4));
+                const float4 h0 = __ldg(reinterpret_cast<const float4*>(a.coarse.shift + cp * 8)), h1 = __ldg(reinterpret_cast<const float4*>(a.coarse.shift + cp * 8 + 4));
+                ks[0] = s0.x; ks[1] = s0.y; ks[2] = s0.z; ks[3] = s0.w; ks[4] = s1.x; ks[5] = s1.y; ks[6] = s1.z; ks[7] = s1.w;
+                kh[0] = h0.x; kh[1] = h0.y; kh[2] = h0.z; kh[3] = h0.w; kh[4] = h1.x; kh[5] = h1.y; kh[6] = h1.z; kh[7] = h1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { ks[e] = 1.f; kh[e] = 0.f; }
+            }
             if (a.s > 1) {
                 float p0[8], p1[8], p2[8];
-                row_vals8(a.coarse, r0, cp * 8, p0);
-                row_vals8(a.coarse, r1, cp * 8, p1);
-                row_vals8(a.coarse, r2, cp * 8, p2);
+                row_vals8_pre(a.coarse, r0, cp * 8, ks, kh, p0);
+                row_vals8_pre(a.coarse, r1, cp * 8, ks, kh, p1);
+                row_vals8_pre(a.coarse, r2, cp * 8, ks, kh, p2);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(w[2], p2[e], fmaf(w[0], p0[e], w[1] * p1[e]));
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(w[2], p2[e], fmaf(w[0], p0[e], w[1] * p1[e]));  // interpolate_gpu.cu:168 order
             } else {
-                row_vals8(a.coarse, (size_t)b, cp * 8, v);
+                row_vals8_pre(a.coarse, (size_t)b, cp * 8, ks, kh, v);
             }
             uint4 q, ql;
             uint32_t* qq = reinterpret_cast<uint32_t*>(&q);
@@ -303,25 +351,39 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
         }
     }
     // skip columns, (non-vectorisable coarse columns,) zero padding
-    for (int col = l; col < a.out_ld; col += lanes) {
-        float v = 0.f;
-        if (col < sc) {
-            v = row_val(a.skip, (size_t)row, col);
-        } else if (col < sc + cc) {
-            if (cvec) continue;
-            const int ch = col - sc;
-            if (a.s > 1) {
-                const float p0 = row_val(a.coarse, (size_t)b * a.s + id[0], ch);
-                const float p1 = row_val(a.coarse, (size_t)b * a.s + id[1], ch);
-                const float p2 = row_val(a.coarse, (size_t)b * a.s + id[2], ch);
-                v = fmaf(w[2], p2, fmaf(w[0], p0, w[1] * p1));  // interpolate_gpu.cu:168 rounding order
-            } else {
-                v = row_val(a.coarse, (size_t)b, ch);
+    if (live) {
+        for (int col = l; col < a.out_ld; col += lanes) {
+            float v = 0.f;
+            if (col < sc) {
+                v = row_val(a.skip, (size_t)row, col);
+            } else if (col < sc + cc) {
+                if (cvec) continue;
+                const int ch = col - sc;
+                if (a.s > 1) {
+                    const float p0 = row_val(a.coarse, (size_t)b * a.s + id[0], ch);
+                    const float p1 = row_val(a.coarse, (size_t)b * a.s + id[1], ch);
+                    const float p2 = row_val(a.coarse, (size_t)b * a.s + id[2], ch);
+                    v = fmaf(w[2], p2, fmaf(w[0], p0, w[1] * p1));  // interpolate_gpu.cu:168 rounding order
+                } else {
+                    v = row_val(a.coarse, (size_t)b, ch);
+                }
+            }
+            const act_t h = f_to_h(v);
+            o[col] = h;
+            if (ol) ol[col] = f_to_h(v - h_to_f(h));
+        }
+    }
+    if (staged) {
+        __syncwarp();
+        if (live) {
+            act_t* go = a.out + (size_t)row * a.out_ld;
+            for (int g = l; g < (a.out_ld >> 3); g += lanes) {
+                *reinterpret_cast<uint4*>(go + g * 8) = *reinterpret_cast<const uint4*>(&s_row[warp][rsub][0][g * 8]);
+                if (a.out_lo)
+                    *reinterpret_cast<uint4*>(a.out_lo + (size_t)row * a.out_ld + g * 8) =
+                        *reinterpret_cast<const uint4*>(&s_row[warp][rsub][1][g * 8]);
             }
         }
-        const act_t h = f_to_h(v);
-        o[col] = h;
-        if (ol) ol[col] = f_to_h(v - h_to_f(h));
     }
 }
 

@@ -185,6 +185,29 @@ class ZeroArena:
 
 ACTIVE_ARENA = None  # set by TrainStep for the whole step (forward and backward)
 
+# Weight gradients on a side stream.  A layer's weight gradient feeds nothing but the optimiser, while the backward pass
+# proper is a CHAIN (coefficients -> input gradient -> next layer's coefficients ...) full of small latency-bound launches
+# that leave most SMs idle; with this on (TrainStep sets it for its step; needs DIRECT_PARAM_GRADS) every
+# pn2_mlp_gemm_wgrad is forked onto a second stream and joined once, before the optimiser (join_wgrad()).  The operands
+# of the in-flight kernels are kept alive until the join.
+WGRAD_SIDE_STREAM = False
+_WGRAD_SIDE = {}  # device index -> [stream, keep-alive list]
+
+
+def _wgrad_side(dev):
+    e = _WGRAD_SIDE.get(dev.index)
+    if e is None:
+        e = _WGRAD_SIDE[dev.index] = [torch.cuda.Stream(device=dev), []]
+    return e
+
+
+def join_wgrad():
+    """Make the current stream of every device wait for the weight-gradient stream (call once after backward)."""
+    for idx, (side, keep) in _WGRAD_SIDE.items():
+        if keep:
+            torch.cuda.current_stream(torch.device("cuda", idx)).wait_stream(side)
+            keep.clear()
+
 
 def _zeros(n, dev):
     if ACTIVE_ARENA is not None and ACTIVE_ARENA.buf.device == dev:
@@ -218,7 +241,7 @@ class Rows:
 
     def __init__(self, y, c, ld, scale=None, shift=None, offset=None, sink=None, lo=None):
         self.lo = lo  # second fp16 plane of two-plane rows (value = y + lo), same shape; None for plain rows
-        # offset (fp32 [c]): the rows are stored CENTRED, true value = y + offset (pooled features)
+        # offset ((fp32 sums [c], scale)): the rows are stored CENTRED, true value = y + sums * scale (pooled features)
         self.y, self.c, self.ld, self.scale, self.shift, self.offset = y, c, ld, scale, shift, offset
         self.sink = sink  # _Sink of the producing K=1 stack (row-form gradient hand-over), or None
         self.numel = self.version = None
@@ -341,20 +364,17 @@ class _MlpStack(Function):
                 xs = torch.cat([xs, xs.new_zeros(kp - xs.numel())])
                 xh = torch.cat([xh, xh.new_zeros(kp - xh.numel())])
         in0 = (x, x_ld, xs, xh)
-        # per-channel constants the layer-0 input rows were centred by (pooled features), by column
-        in_off = None
+        # per-channel constants the layer-0 input rows were centred by (pooled features): up to two column segments, each
+        # (sums, scale, first column, channels) -- handed to pn2_mlp_center as they are (no assembly kernels)
         segs = []
         if kind == "sa":
             segs = [(ra, 3 if meta[3] else 0), (rb, (ra.c if ra is not None else 0) + 3)]
         elif kind == "fp":
             segs = [(ra, 0), (rb, ra.c if ra is not None else 0)]
-        if kind == "dense" and ra.offset is not None:
-            segs = [(ra, 0)]  # centred pooled rows fed straight to a dense stack: same per-column constants
-        for r, start in segs:
-            if r is not None and r.offset is not None:
-                if in_off is None:
-                    in_off = torch.zeros(kp, dtype=torch.float32, device=dev)
-                in_off[start:start + r.c] = r.offset
+        elif ra.offset is not None:
+            segs = [(ra, 0)]  # centred pooled rows fed straight to a dense stack
+        in_off = [(r.offset[0], float(r.offset[1]), start, r.c) for r, start in segs if r is not None and r.offset is not None]
+        in_off = in_off or None
         # one zero-filled arena for every accumulator of the forward pass (one memset per stack)
         widths = [params[4 * l].shape[0] for l in range(nl)]
         arena = _zeros(2 * sum(widths) + widths[-1] + nl, dev)
@@ -398,8 +418,10 @@ class _MlpStack(Function):
             if state is not None:
                 cen = cen_true = next_cen = state
             else:
+                o0 = in_off[0] if (l == 0 and in_off) else (None, 0.0, 0, 0)
+                o1 = in_off[1] if (l == 0 and in_off and len(in_off) > 1) else (None, 0.0, 0, 0)
                 _lib.call("pn2_mlp_center", R, kp, L.cout, x.data_ptr(), x_ld, _p(xs), _p(xh), L.w.data_ptr(),
-                          _p(in_off) if l == 0 else 0, cen.data_ptr(), cen_true.data_ptr(), st)
+                          _p(o0[0]), o0[1], o0[2], o0[3], _p(o1[0]), o1[1], o1[2], o1[3], cen.data_ptr(), cen_true.data_ptr(), st)
                 if stateful:
                     next_cen = bn._pn2_center = torch.empty(L.cout, dtype=torch.float32, device=dev)
             if training:
@@ -436,7 +458,7 @@ class _MlpStack(Function):
         last = layers[-1]
         C = last.cout
         out = torch.empty(B, C, groups, dtype=torch.float32, device=dev)
-        rows_only = kind == "fp" and len(meta) > 4 and meta[4] and pool_k == 1
+        rows_only = pool_k == 1 and ((kind == "fp" and len(meta) > 4 and meta[4]) or (kind == "dense" and bool(meta and meta[0])))
         chan_sums = argmax = None
         if pool_k > 1:
             chan_sums = arena[2 * sum(widths):2 * sum(widths) + widths[-1]]
@@ -455,7 +477,7 @@ class _MlpStack(Function):
             out_rows = torch.empty(2 if two_out else 1, B * groups, C, dtype=_F16, device=dev)
             _lib.call("pn2_to_rows_x2", B, C, groups, out.data_ptr(), chan_sums.data_ptr(), inv, out_rows[0].data_ptr(),
                       out_rows[1].data_ptr() if two_out else 0, C, st)
-            _MlpStack.last_rows = Rows(out_rows[0], C, C, offset=chan_sums * inv, lo=out_rows[1] if two_out else None)
+            _MlpStack.last_rows = Rows(out_rows[0], C, C, offset=(chan_sums, inv), lo=out_rows[1] if two_out else None)
             ctx.out_sink = None
         else:
             ctx.out_sink = _Sink(R, C) if (training and C <= 1024) else None
@@ -538,9 +560,17 @@ class _MlpStack(Function):
             else:
                 x, x_ld, xs, xh = ctx.in0
             dw = None if direct else torch.zeros(L.cout, L.cin, dtype=torch.float32, device=dev)
-            _lib.call("pn2_mlp_gemm_wgrad", R, L.cout, L.kp, L.cin, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
-                      coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), x.data_ptr(), x_ld, _p(xs), _p(xh),
-                      pw.grad.data_ptr() if direct else dw.data_ptr(), L.cin, st)
+            wargs = (R, L.cout, L.kp, L.cin, dz.data_ptr(), L.cout, L.y.data_ptr(), L.cout,
+                     coefs[0].data_ptr(), coefs[1].data_ptr(), coefs[2].data_ptr(), x.data_ptr(), x_ld, _p(xs), _p(xh),
+                     pw.grad.data_ptr() if direct else dw.data_ptr(), L.cin)
+            if direct and WGRAD_SIDE_STREAM:
+                side, keep = _wgrad_side(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))  # dz, the coefficients and everything before them
+                with torch.cuda.stream(side):
+                    _lib.call("pn2_mlp_gemm_wgrad", *wargs, side.cuda_stream)
+                keep.extend((dz, L.y, x, xs, xh, coefs))
+            else:
+                _lib.call("pn2_mlp_gemm_wgrad", *wargs, st)
             if not direct:
                 grads[4 * l] = dw
                 grads[4 * l + 2] = coefs[3]
@@ -684,10 +714,11 @@ def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1, row
     return _run("fp", (idx, dist2, N, S, bool(rows_only)), convs, bns, training, points1, points2, precise)
 
 
-def dense_stack(x, convs, bns, training, precise=0):
-    """relu(bn(conv1x1(x))) stack on (B,C,N) -> (B,Cout,N)."""
+def dense_stack(x, convs, bns, training, precise=0, rows_only=False):
+    """relu(bn(conv1x1(x))) stack on (B,C,N) -> (B,Cout,N).  rows_only: as in fp_layer -- the returned fp32 tensor is left
+    UNINITIALISED and only its attached row form is valid (a caller whose consumers are all fused stacks)."""
     _check_cuda(x)
-    return _run("dense", None, convs, bns, training, x, None, precise)
+    return _run("dense", (bool(rows_only),), convs, bns, training, x, None, precise)
 
 
 def alg_bytes(name, a):

@@ -51,6 +51,9 @@ class HandTrackNet(nn.Module):
         c = cfg['network']['backbone_out_dim']
         assert c % 6 == 0
         self.bhand = PointNet2Msg_fast(cfg, c)
+        # fused engine: the point features go to q1 / q2 (which read their row form) and to nothing else here -- TransT's
+        # point-cloud branch is skipped --, so their fp32 (B,384,N) copy need not be written
+        self.bhand.rows_only_output = getattr(self.bhand.fp1, "engine", "ops") == "fused"
         self.r1 = rearrange_module(channel=c)
         self.r2 = rearrange_module(channel=c)
         self.positionEmbedding = PositionEmbeddingSine(num_pos_feats=c // 6)

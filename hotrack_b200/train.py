@@ -38,18 +38,21 @@ class TrainStep:
     def _fwd_bwd(self, inputs):
         self.flat.zero_grad()
         f = self._fused
-        saved = (f.SPARSE_GRAD_SINK, f.DIRECT_PARAM_GRADS)
-        # whole-step backward owned by this object: gather gradients travel in row form and parameter gradients are
-        # accumulated straight into the flat .grad buffer -- both only for the duration of the step
+        saved = (f.SPARSE_GRAD_SINK, f.DIRECT_PARAM_GRADS, f.WGRAD_SIDE_STREAM)
+        # whole-step backward owned by this object: gather gradients travel in row form, parameter gradients are
+        # accumulated straight into the flat .grad buffer and the weight-gradient kernels run on a side stream beside
+        # the backward chain -- all only for the duration of the step
         f.SPARSE_GRAD_SINK = f.DIRECT_PARAM_GRADS = True
+        f.WGRAD_SIDE_STREAM = os.environ.get("PN2_WGRAD_STREAM", "1") != "0"
         if self.arena is not None:
             self.arena.begin()
             f.ACTIVE_ARENA = self.arena
         try:
             return self._fwd_bwd_inner(inputs)
         finally:
+            f.join_wgrad()
             f.ACTIVE_ARENA = None
-            f.SPARSE_GRAD_SINK, f.DIRECT_PARAM_GRADS = saved
+            f.SPARSE_GRAD_SINK, f.DIRECT_PARAM_GRADS, f.WGRAD_SIDE_STREAM = saved
 
     def _fwd_bwd_inner(self, inputs):
         if self.use_plan:
@@ -61,6 +64,7 @@ class TrainStep:
             self._fused.ACTIVE_PLAN = None
             self.weights.finish()
         loss.backward()
+        self._fused.join_wgrad()  # the weight-gradient stream rejoins before anything reads .grad
         return loss.detach()
 
     def _finish(self):

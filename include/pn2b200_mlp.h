@@ -44,12 +44,14 @@ int pn2_fp_build_rows(int b, int n, int s, const void* skip, int skip_c, int ski
                       void* out, int out_ld, pn2_stream_t stream);
 
 /* center[n] = w[n][:] . mean_j act(x[row_j][:]) over <= 16 rows spread over the matrix: a cheap estimate of the
- * per-channel mean of the GEMM output, used to centre it before fp16 rounding (kdim <= 1024).  in_offset[kdim] (nullable): per-channel constants the
- * input rows were themselves centred by; center_true = center + w . in_offset is what the true (uncentred) output
- * differs from the stored one by -- bn_finalize / bn_eval_affine take center_true. */
+ * per-channel mean of the GEMM output, used to centre it before fp16 rounding (kdim <= 1024).  off0 / off1 (nullable): up to
+ * two column segments [start, start + count) whose input rows were themselves stored centred by the per-channel constants
+ * off[i] * off_scale (channel sums and 1 / count, as pn2_to_rows takes them); center_true = center + w . offset is what the
+ * true (uncentred) output differs from the stored one by -- bn_finalize / bn_eval_affine take center_true. */
 int pn2_mlp_center(long long rows, int kdim, int n, const void* x, int x_ld, const float* in_scale,
-                   const float* in_shift, const void* w, const float* in_offset, float* center, float* center_true,
-                   pn2_stream_t stream);
+                   const float* in_shift, const void* w, const float* off0, float off0_scale, int off0_start,
+                   int off0_count, const float* off1, float off1_scale, int off1_start, int off1_count, float* center,
+                   float* center_true, pn2_stream_t stream);
 
 /* y[rows][n] = act(x)[rows][kdim] * w[n][kdim]^T - center[n]  (fp16 in, fp32 accumulate, fp16 out), act =
  * relu(x*scale+shift) when in_scale != NULL, center NULL = 0.  stats != NULL: stats[0..n) += column sums of y,

@@ -61,9 +61,12 @@ def test_gemm_fwd_and_stats(lib, cuda, R, K, N, affine):
     if affine:  # centred store: y - c with c ~ the channel mean
         ct = torch.zeros(N, device=cuda)
         off = torch.randn(K, device=cuda)
-        lib.call("pn2_mlp_center", R, K, N, x.data_ptr(), K, sc.data_ptr(), sh.data_ptr(), w.data_ptr(), off.data_ptr(),
-                 cen.data_ptr(), ct.data_ptr(), _st())
-        torch.testing.assert_close(ct - cen, w.float() @ off, rtol=1e-3, atol=1e-3)
+        # two centred column segments: columns [0, K/2) by off[:K/2] * 0.5, columns [K/2, K) by off[K/2:] * 2
+        h2 = K // 2
+        lib.call("pn2_mlp_center", R, K, N, x.data_ptr(), K, sc.data_ptr(), sh.data_ptr(), w.data_ptr(), off.data_ptr(), 0.5, 0,
+                 h2, off[h2:].data_ptr(), 2.0, h2, K - h2, cen.data_ptr(), ct.data_ptr(), _st())
+        eff = torch.cat([off[:h2] * 0.5, off[h2:] * 2.0])
+        torch.testing.assert_close(ct - cen, w.float() @ eff, rtol=1e-3, atol=1e-3)
         assert ((cen - want.mean(0)).abs() < 1.5 * want.std(0) + 1e-3).all()
     lib.call("pn2_mlp_gemm_fwd", R, K, N, x.data_ptr(), K, 0 if sc is None else sc.data_ptr(),
              0 if sh is None else sh.data_ptr(), w.data_ptr(), cen.data_ptr(), y.data_ptr(), N, stats.data_ptr(), _st())
