@@ -28,6 +28,7 @@ constexpr int kTile = 1024;  // points per shared-memory tile (12 KB); two buffe
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 ball_query_kernel(int n, int m, float radius, int nsample, const float* __restrict__ new_xyz,
                   const float* __restrict__ xyz, int* __restrict__ idx) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     __shared__ __align__(16) float s_pts[2][kTile * 3];
     __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -136,7 +137,7 @@ extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
     if (b > 65535) return fail_arg("pn2_ball_query", "b > 65535");
     if (!new_xyz || !xyz || !idx) return fail_arg("pn2_ball_query", "null pointer");
     dim3 grid((m + kWarpsPerCta - 1) / kWarpsPerCta, b);
-    ball_query_kernel<<<grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(n, m, radius, nsample, new_xyz, xyz, idx);
+    launch_k(ball_query_kernel, dim3(grid), dim3(kWarpsPerCta * 32), 0, (cudaStream_t)stream, n, m, radius, nsample, new_xyz, xyz, idx);
     PN2_CHECK_LAUNCH("ball_query_kernel");
     return 0;
 }

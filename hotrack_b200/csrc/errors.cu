@@ -3,11 +3,21 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 
 namespace pn2 {
 namespace {
 thread_local char g_last_error[512] = "";
 std::atomic<long long> g_launches{0};
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PN2_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

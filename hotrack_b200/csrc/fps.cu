@@ -57,6 +57,7 @@ template <int PPT>
 __global__ void __launch_bounds__(1024, 1)
 fps_regs_kernel(int n, int m, int lg_bs, int q_cnt, int n_pos, const float* __restrict__ dataset,
                 float* __restrict__ temp, int* __restrict__ idxs) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* spts = reinterpret_cast<float4*>(smem_raw);  // [n_pos] (x, y, z, int k | -1)
     __shared__ int2 s_part[2][32];
@@ -187,7 +188,7 @@ int launch_regs(int b, int n, int m, int lg_bs, int q_cnt, int n_pos, int thread
         PN2_CHECK(cudaFuncSetAttribute(fps_regs_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem),
                   "fps: cudaFuncSetAttribute");
     }
-    fps_regs_kernel<PPT><<<b, threads, smem, stream>>>(n, m, lg_bs, q_cnt, n_pos, dataset, temp, idxs);
+    launch_k(fps_regs_kernel<PPT>, dim3(b), dim3(threads), smem, stream, n, m, lg_bs, q_cnt, n_pos, dataset, temp, idxs);
     PN2_CHECK_LAUNCH("fps_regs_kernel");
     return 0;
 }

@@ -20,6 +20,7 @@ constexpr int kChunk = 16;
 __global__ void __launch_bounds__(kThreads)
 group_points_kernel(int c, int n, int slots, const float* __restrict__ points, const int* __restrict__ idx,
                     float* __restrict__ out) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * kChunk;
     const int cend = min(c, c0 + kChunk);
@@ -53,7 +54,7 @@ int launch_group(bool grad, int b, int c, int n, long long slots, const float* s
     if (grad)
         group_points_grad_kernel<<<grid, kThreads, 0, stream>>>(c, n, (int)slots, src, idx, dst);
     else
-        group_points_kernel<<<grid, kThreads, 0, stream>>>(c, n, (int)slots, src, idx, dst);
+        launch_k(group_points_kernel, dim3(grid), dim3(kThreads), 0, stream, c, n, (int)slots, src, idx, dst);
     PN2_CHECK_LAUNCH(who);
     return 0;
 }

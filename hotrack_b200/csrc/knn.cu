@@ -57,6 +57,7 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* keys, int 
 __global__ void __launch_bounds__(kKnnWarps * 32)
 knn_kernel(int n, int m, int k, int nsort, const float* __restrict__ unknown, const float* __restrict__ known,
            float* __restrict__ dist2, int* __restrict__ idx) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [2][kKnnTile*3] floats | [kKnnWarps][nsort] keys
     float* s_pts = reinterpret_cast<float*>(smem_raw);
@@ -173,6 +174,7 @@ constexpr int kNnTile = 2048;  // known points per tile (float4 => 32 KB)
 __global__ void __launch_bounds__(kNnThreads)
 three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
                 float* __restrict__ dist2, int* __restrict__ idx) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     __shared__ float4 s_known[kNnTile];
     const int b = blockIdx.y;
     const int q = blockIdx.x * kNnThreads + threadIdx.x;
@@ -243,7 +245,7 @@ extern "C" int pn2_knn(int b, int n, int m, int k, const float* unknown, const f
         configured[dev] = smem;
     }
     dim3 grid((n + kKnnWarps - 1) / kKnnWarps, b);
-    knn_kernel<<<grid, kKnnWarps * 32, smem, (cudaStream_t)stream>>>(n, m, k, nsort, unknown, known, dist2, idx);
+    launch_k(knn_kernel, dim3(grid), dim3(kKnnWarps * 32), smem, (cudaStream_t)stream, n, m, k, nsort, unknown, known, dist2, idx);
     PN2_CHECK_LAUNCH("knn_kernel");
     return 0;
 }
@@ -256,7 +258,7 @@ extern "C" int pn2_three_nn(int b, int n, int m, const float* unknown, const flo
     if (b > 65535) return fail_arg("pn2_three_nn", "b > 65535");
     if (!unknown || (!known && m > 0) || !dist2 || !idx) return fail_arg("pn2_three_nn", "null pointer");
     dim3 grid((n + kNnThreads - 1) / kNnThreads, b);
-    three_nn_kernel<<<grid, kNnThreads, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+    launch_k(three_nn_kernel, dim3(grid), dim3(kNnThreads), 0, (cudaStream_t)stream, n, m, unknown, known, dist2, idx);
     PN2_CHECK_LAUNCH("three_nn_kernel");
     return 0;
 }

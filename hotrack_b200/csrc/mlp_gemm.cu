@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(256) center_kernel(long long rows, int kdim, i
                                                       int off0_count, const float* __restrict__ off1, float off1_scale,
                                                       int off1_start, int off1_count, float* __restrict__ c,
                                                       float* __restrict__ c_true) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     __shared__ float sM[1024];
     __shared__ float sO[1024];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -687,6 +688,7 @@ __global__ void bn_eval_affine_kernel(int n, const float* __restrict__ gamma, co
                                       const float* __restrict__ bias, const float* __restrict__ center,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                       float eps, float* scale, float* shift) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
@@ -711,6 +713,7 @@ __global__ void __launch_bounds__(256) bn_bwd_coefs_kernel(int n, float inv_rows
                                                            float* dgamma, float* dbeta, int accumulate,
                                                            const float* __restrict__ w, int k_true, int kp, bf16* wa,
                                                            act_t* wb, float* negbias, float* wb_unscale) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     extern __shared__ float sco[];  // [3][n]
     __shared__ float tile[32][33];
     __shared__ float sbias[8][32];
@@ -808,6 +811,7 @@ struct PrepDesc {
     int n, k_true, kp, two;  // two != 0: the lo plane follows the hi plane (wh + n * kp)
 };
 __global__ void __launch_bounds__(256) prep_weights_multi_kernel(const PrepDesc* __restrict__ descs) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     const PrepDesc d = descs[blockIdx.y];
     const int total = d.n * d.kp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -828,7 +832,7 @@ extern "C" int pn2_mlp_prep_weights_multi(int n_layers, const void* descs, pn2_s
     if (n_layers < 0) return fail_arg("pn2_mlp_prep_weights_multi", "negative layer count");
     if (n_layers == 0) return 0;
     if (!descs) return fail_arg("pn2_mlp_prep_weights_multi", "null pointer");
-    prep_weights_multi_kernel<<<dim3(32, n_layers), 256, 0, (cudaStream_t)stream>>>((const PrepDesc*)descs);
+    launch_k(prep_weights_multi_kernel, dim3(dim3(32, n_layers)), dim3(256), 0, (cudaStream_t)stream, (const PrepDesc*)descs);
     PN2_CHECK_LAUNCH("prep_weights_multi_kernel");
     return 0;
 }
@@ -841,7 +845,7 @@ extern "C" int pn2_mlp_center(long long rows, int kdim, int n, const void* x, in
     if (rows == 0) return 0;
     if (kdim > 1024) return fail_arg("pn2_mlp_center", "kdim > 1024");
     if (!x || !w || !center || !center_true) return fail_arg("pn2_mlp_center", "null pointer");
-    center_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rows, kdim, n, (const act_t*)x, x_ld, in_scale, in_shift,
+    launch_k(center_kernel, dim3((n + 7) / 8), dim3(256), 0, (cudaStream_t)stream, rows, kdim, n, (const act_t*)x, x_ld, in_scale, in_shift,
                                                                   (const act_t*)w, off0, off0_scale, off0_start, off0_count, off1,
                                                                   off1_scale, off1_start, off1_count, center, center_true);
     PN2_CHECK_LAUNCH("center_kernel");
@@ -1073,7 +1077,7 @@ extern "C" int pn2_bn_eval_affine(int n, const float* gamma, const float* beta, 
     if (n <= 0) return fail_arg("pn2_bn_eval_affine", "non-positive size");
     if (!gamma || !beta || !running_mean || !running_var || !scale || !shift)
         return fail_arg("pn2_bn_eval_affine", "null pointer");
-    bn_eval_affine_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, gamma, beta, conv_bias, center, running_mean,
+    launch_k(bn_eval_affine_kernel, dim3((n + 127) / 128), dim3(128), 0, (cudaStream_t)stream, n, gamma, beta, conv_bias, center, running_mean,
                                                                             running_var, eps, scale, shift);
     PN2_CHECK_LAUNCH("bn_eval_affine_kernel");
     return 0;
@@ -1089,7 +1093,7 @@ extern "C" int pn2_bn_bwd_coefs(int n, long long rows, const float* sums, const 
     if (n > 4096) return fail_arg("pn2_bn_bwd_coefs", "n > 4096");
     if (w && (!wa || !wb || !negbias || !wb_unscale || k_true <= 0 || kp < k_true)) return fail_arg("pn2_bn_bwd_coefs", "bad folding arguments");
     const dim3 blocks(w ? (kp + 31) / 32 : 1, w ? (n + 31) / 32 : 1);
-    bn_bwd_coefs_kernel<<<blocks, 256, 3 * n * sizeof(float), (cudaStream_t)stream>>>(
+    launch_k(bn_bwd_coefs_kernel, dim3(blocks), dim3(256), 3 * n * sizeof(float), (cudaStream_t)stream, 
         n, (float)(1.0 / (double)rows), sums, gamma, mean, rstd, cA, cB, cC, dgamma, dbeta, accumulate, w, k_true, kp, (bf16*)wa,
         (act_t*)wb, negbias, wb_unscale);
     PN2_CHECK_LAUNCH("bn_bwd_coefs_kernel");

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     constexpr bool FWD = AMODE != A_BNBWD;
     constexpr int NCOEF = Cfg::kNCoef;
 
+    pdl_enter();  // programmatic dependent launch: nothing above touches memory (pn2_common.cuh)
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // SWIZZLE_128B tiles: 1024-byte aligned
@@ -652,7 +653,7 @@ int launch_tc(const GemmArgs& a, cudaStream_t stream) {
     long long gx = sms / ny;  // persistent: one CTA per SM (shared memory, TMEM), tiles dealt round-robin
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
-    gemm_tc_kernel<BN, AMODE, MASK, SPLIT><<<dim3((unsigned)gx, ny), kTcThreads, smem, stream>>>(a);
+    launch_k(gemm_tc_kernel<BN, AMODE, MASK, SPLIT>, dim3((unsigned)gx, ny), dim3(kTcThreads), smem, stream, a);
     PN2_CHECK_LAUNCH("gemm_tc_kernel");
     return 0;
 }
@@ -660,17 +661,23 @@ int launch_tc(const GemmArgs& a, cudaStream_t stream) {
 // column-tile width: the narrowest of {32, 64, 128, 256 (forward only)} that covers n, else the widest.  Every extra
 // column tile re-reads and re-transforms the whole A operand; padded columns only cost tensor-pipe time (the epilogue
 // skips them).
-int pick_bn(int n, bool fwd) {
+int pick_bn(int n, bool fwd, long long rows) {
     const int widest = fwd ? 256 : 128;
-    for (int bn = 32; bn < widest; bn <<= 1)
-        if (n <= bn) return bn;
-    return widest;
+    int bn = widest;
+    for (int c = 32; c < widest; c <<= 1)
+        if (n <= c) { bn = c; break; }
+    // Few row tiles (the 4096..10752-row stacks: SA3, FP3, FP2, the 16-neighbour scale of q1 / q2): with one CTA per
+    // (row tile, column tile) most SMs would idle while the busy ones each stream the whole weight matrix at one SM's
+    // L2 bandwidth.  Narrower column tiles spread the weights over more SMs; re-reading the (small) A tiles is cheap.
+    const long long tiles = (rows + TM - 1) / TM;
+    while (bn > 32 && tiles * ((n + bn - 1) / bn) < 112) bn >>= 1;
+    return bn;
 }
 
 template <int AMODE, bool MASK>
 int dispatch_tc(const GemmArgs& a, cudaStream_t stream) {
     constexpr bool FWD = AMODE != A_BNBWD;
-    switch (pick_bn(a.n, FWD)) {
+    switch (pick_bn(a.n, FWD, a.rows)) {
         case 256:
             if constexpr (FWD) return launch_tc<256, AMODE, MASK>(a, stream);
             return launch_tc<128, AMODE, MASK>(a, stream);
@@ -683,7 +690,7 @@ int dispatch_tc(const GemmArgs& a, cudaStream_t stream) {
 // SPLIT: column tiles of at most 128 (the two-plane stage of a 256-wide tile would leave no room for a 3-stage ring)
 template <int AMODE>
 int dispatch_tc_split(const GemmArgs& a, cudaStream_t stream) {
-    switch (pick_bn(a.n, false)) {
+    switch (pick_bn(a.n, false, a.rows)) {
         case 128: return launch_tc<128, AMODE, false, true>(a, stream);
         case 64: return launch_tc<64, AMODE, false, true>(a, stream);
         default: return launch_tc<32, AMODE, false, true>(a, stream);

@@ -35,6 +35,7 @@ constexpr int kThreads = 256;
 __global__ void __launch_bounds__(256) to_rows_kernel(int c, int n, int ld, const float* __restrict__ src,
                                                        const float* __restrict__ sub_sums, float sub_scale,
                                                        act_t* __restrict__ dst, act_t* __restrict__ dst_lo) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     __shared__ float tile[32][33];
     const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -133,6 +134,7 @@ __device__ __forceinline__ void row_vals8(const RowSrc& s, size_t row, int ch, f
 // feature segment are one 16-byte gather; pieces straddling a segment boundary (the 3 coordinates shift the centre
 // segment off the 8-channel grid) are assembled element by element.
 __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     // centre features (given-centre SA with per-centre features, reference pointnet_utils.py:574-575) are the same for
     // the K rows of a group: when the 8 rows of a CTA share their group the BatchNorm+ReLU'd centre row is staged ONCE,
     // at its OUTPUT columns, and every row copies aligned 16-byte pieces of it
@@ -275,6 +277,7 @@ __device__ __forceinline__ void row_vals8_pre(const RowSrc& s, size_t row, int c
 constexpr int kFpStageLd = 256;  // widest output row the misaligned-store staging buffer holds
 
 __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildArgs a, int lanes) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     // misaligned coarse segment (skip_c % 8 != 0) of a narrow row: the row is assembled in shared memory (2-byte stores)
     // and leaves as 16-byte pieces
     __shared__ __align__(16) act_t s_row[kThreads / 32][2][2][kFpStageLd];  // [warp][row of the warp][plane][column]
@@ -408,6 +411,7 @@ struct PoolArgs {
 // (group-all, the 21 joints) so that the work still spreads over >= 256 CTAs.
 template <int GT>
 __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     // A warp reads a group's rows as 16-byte pieces: lane = (row lane rl = lane / 8, piece pc = lane % 8 of the 64-channel
     // chunk); row lane rl takes rows rl, rl + 4, ... (8 independent 16-byte loads per plane in flight at K = 32), the four
     // row lanes are combined by shuffles (first maximum in row order wins, as a sequential scan would have it).
@@ -502,6 +506,7 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_kernel(const PoolArgs a) {
 
 template <int GT>
 __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     __shared__ float tile[GT][65];
     __shared__ float red[8][2][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -567,6 +572,7 @@ __global__ void __launch_bounds__(256) pool_finalize_kernel(int s_count, int k, 
                                                              const int* __restrict__ arg, const act_t* __restrict__ y, int y_ld,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              float* __restrict__ out_cm, float* __restrict__ chan_sums) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     __shared__ float tile[32][33];
     const int b = blockIdx.z, s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -611,6 +617,7 @@ __global__ void __launch_bounds__(256) pool_finalize_kernel(int s_count, int k, 
 constexpr int kSlab = 256;
 
 __global__ void __launch_bounds__(kThreads) pool_fwd_grp_kernel(const PoolArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     __shared__ float sv[8][kSlab];
     __shared__ int si[8][kSlab];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -675,6 +682,7 @@ __global__ void __launch_bounds__(kThreads) pool_fwd_grp_kernel(const PoolArgs a
 }
 
 __global__ void __launch_bounds__(kThreads) pool_bwd_grp_kernel(const PoolArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     __shared__ float sg[kSlab];
     __shared__ int si[kSlab];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -732,6 +740,7 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_grp_kernel(const PoolArgs a
 constexpr int kRowTile = 32;
 
 __global__ void __launch_bounds__(kThreads) rows_to_cm_kernel(const PoolArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     extern __shared__ __align__(16) float tile_dyn[];  // [32][C + 1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int pieces = a.c >> 3, ldt = a.c + 1;
@@ -771,6 +780,7 @@ __global__ void __launch_bounds__(kThreads) rows_to_cm_kernel(const PoolArgs a) 
 }
 
 __global__ void __launch_bounds__(kThreads, 2) cm_to_rows_bwd_kernel(const PoolArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     extern __shared__ __align__(16) float tile_dyn[];  // [32][C + 1] dout tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int pieces = a.c >> 3, ldt = a.c + 1;
@@ -893,6 +903,7 @@ struct SaBwdArgs {
 //   centre columns   -> every row of the group adds into the SAME (b, :, s) column, so the K rows are summed in
 //                       registers first and the group issues one atomic per channel (not K same-address atomics)
 __global__ void __launch_bounds__(kThreads) sa_rows_bwd_kernel(const SaBwdArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = blockIdx.x;  // b * s + s_idx
     const int s = grp % a.s, b = grp / a.s;
@@ -960,6 +971,7 @@ struct FpBwdArgs {
     int coarse_c; float* dcoarse_rows; // (B*S, coarse_c) zeroed, atomics | null
 };
 __global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const long long total = (long long)a.b * a.n;
@@ -1019,7 +1031,7 @@ extern "C" int pn2_to_rows_x2(int b, int c, int n, const float* src, const float
     if (!src || !dst) return fail_arg("pn2_to_rows", "null pointer");
     if (b > 65535) return fail_arg("pn2_to_rows", "b > 65535");
     dim3 grid((n + 31) / 32, (ld + 31) / 32, b);
-    to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, ld, src, sub_sums, sub_scale, (act_t*)dst, (act_t*)dst_lo);
+    launch_k(to_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, c, n, ld, src, sub_sums, sub_scale, (act_t*)dst, (act_t*)dst_lo);
     PN2_CHECK_LAUNCH("to_rows_kernel");
     return 0;
 }
@@ -1057,7 +1069,7 @@ extern "C" int pn2_sa_build_rows_x2(int b, int n, int s, int k, const float* xyz
     a.cen = mk_src(cen, cen_lo, cen_c, cen_ld, cen_scale, cen_shift);
     a.xyz_first = xyz_first; a.out = (act_t*)out; a.out_lo = (act_t*)out_lo; a.out_ld = out_ld;
     const int gpr = out_ld >> 3, rpw = gpr >= 32 ? 1 : 32 / gpr;
-    sa_build_rows_kernel<<<warp_blocks(((long long)b * s * k + rpw - 1) / rpw), kThreads, 0, (cudaStream_t)stream>>>(a);
+    launch_k(sa_build_rows_kernel, dim3(warp_blocks(((long long)b * s * k + rpw - 1) / rpw)), dim3(kThreads), 0, (cudaStream_t)stream, a);
     PN2_CHECK_LAUNCH("sa_build_rows_kernel");
     return 0;
 }
@@ -1086,7 +1098,7 @@ extern "C" int pn2_fp_build_rows_x2(int b, int n, int s, const void* skip, const
     a.idx = idx; a.dist2 = dist2; a.out = (act_t*)out; a.out_lo = (act_t*)out_lo; a.out_ld = out_ld;
     int lanes = 32;  // lanes per row: the smallest power of two covering the 8-channel pieces of a coarse row
     while (lanes > 4 && lanes / 2 >= (coarse_c + 7) / 8) lanes >>= 1;
-    fp_build_rows_kernel<<<warp_blocks(((long long)b * n + 32 / lanes - 1) / (32 / lanes)), kThreads, 0, (cudaStream_t)stream>>>(a, lanes);
+    launch_k(fp_build_rows_kernel, dim3(warp_blocks(((long long)b * n + 32 / lanes - 1) / (32 / lanes))), dim3(kThreads), 0, (cudaStream_t)stream, a, lanes);
     PN2_CHECK_LAUNCH("fp_build_rows_kernel");
     return 0;
 }
@@ -1119,13 +1131,13 @@ extern "C" int pn2_pool_fwd_x2(int b, int s, int k, int c, const void* y, const 
         const int pieces = c / 8;
         const int threads = pieces >= kThreads ? pieces : (kThreads / pieces) * pieces;  // multiple of pieces
         grid = dim3(k1_grid((long long)b * s_tiles, smem, 4));
-        rows_to_cm_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+        launch_k(rows_to_cm_kernel, dim3(grid), dim3(threads), smem, (cudaStream_t)stream, a);
     } else if (k > 1 && s <= 64) {
         const int groups = b * s;
-        pool_fwd_grp_kernel<<<groups < 592 ? groups : 592, kThreads, 0, (cudaStream_t)stream>>>(a);
+        launch_k(pool_fwd_grp_kernel, dim3(groups < 592 ? groups : 592), dim3(kThreads), 0, (cudaStream_t)stream, a);
     } else {
         pool_grid<32>(a, grid);
-        pool_fwd_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        launch_k(pool_fwd_kernel<32>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, a);
     }
     PN2_CHECK_LAUNCH("pool_fwd_kernel");
     return 0;
@@ -1139,7 +1151,7 @@ extern "C" int pn2_pool_finalize(int b, int s, int k, int c, const float* pool_v
     if (b > 65535) return fail_arg("pn2_pool_finalize", "b > 65535");
     if (!pool_val || !pool_arg || !y || !scale || !shift || !out_cm) return fail_arg("pn2_pool_finalize", "null pointer");
     dim3 grid((s + 31) / 32, (c + 31) / 32, b);
-    pool_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(s, k, c, pool_val, pool_arg, (const act_t*)y, y_ld, scale, shift,
+    launch_k(pool_finalize_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, s, k, c, pool_val, pool_arg, (const act_t*)y, y_ld, scale, shift,
                                                                   out_cm, chan_sums);
     PN2_CHECK_LAUNCH("pool_finalize_kernel");
     return 0;
@@ -1177,13 +1189,13 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
         const int threads = pieces >= kThreads ? pieces : (kThreads / pieces) * pieces;
         const size_t red = (size_t)2 * threads * 8 * sizeof(float);  // the final [rstep][2][C] reduction reuses the tile
         grid = dim3(k1_grid((long long)b * s_tiles, smem > red ? smem : red, 2));
-        cm_to_rows_bwd_kernel<<<grid, threads, smem > red ? smem : red, (cudaStream_t)stream>>>(a);
+        launch_k(cm_to_rows_bwd_kernel, dim3(grid), dim3(threads), smem > red ? smem : red, (cudaStream_t)stream, a);
     } else if (k > 1 && s <= 64) {
         const int groups = b * s;
-        pool_bwd_grp_kernel<<<groups < 592 ? groups : 592, kThreads, 0, (cudaStream_t)stream>>>(a);
+        launch_k(pool_bwd_grp_kernel, dim3(groups < 592 ? groups : 592), dim3(kThreads), 0, (cudaStream_t)stream, a);
     } else {
         pool_grid<32>(a, grid);
-        pool_bwd_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        launch_k(pool_bwd_kernel<32>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, a);
     }
     PN2_CHECK_LAUNCH("pool_bwd_kernel");
     return 0;
@@ -1202,7 +1214,7 @@ extern "C" int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const
     const long long groups = (long long)b * s;
     long long gy = groups >= 296 ? 1 : (592 + groups - 1) / groups;
     if (gy > (k + 7) / 8) gy = (k + 7) / 8;
-    sa_rows_bwd_kernel<<<dim3((unsigned)groups, (unsigned)gy), kThreads, 0, (cudaStream_t)stream>>>(a);
+    launch_k(sa_rows_bwd_kernel, dim3(dim3((unsigned)groups, (unsigned)gy)), dim3(kThreads), 0, (cudaStream_t)stream, a);
     PN2_CHECK_LAUNCH("sa_rows_bwd_kernel");
     return 0;
 }
@@ -1215,7 +1227,7 @@ extern "C" int pn2_fp_rows_bwd(int b, int n, int s, const int* idx, const float*
     FpBwdArgs a;
     a.b = b; a.n = n; a.s = s; a.idx = idx; a.dist2 = dist2; a.dx = (const bf16*)dx; a.dx_ld = dx_ld;
     a.skip_c = skip_c; a.dskip_cm = dskip_cm; a.coarse_c = coarse_c; a.dcoarse_rows = dcoarse_rows;
-    fp_rows_bwd_kernel<<<warp_blocks((long long)b * n), kThreads, 0, (cudaStream_t)stream>>>(a);
+    launch_k(fp_rows_bwd_kernel, dim3(warp_blocks((long long)b * n)), dim3(kThreads), 0, (cudaStream_t)stream, a);
     PN2_CHECK_LAUNCH("fp_rows_bwd_kernel");
     return 0;
 }

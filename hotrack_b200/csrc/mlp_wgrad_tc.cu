@@ -76,6 +76,7 @@ __device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 2, 256;" :::
 
 template <bool AFFINE>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh)
     const WgradArgs& p = w.a;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -404,9 +405,9 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
     if (gx < 1) gx = 1;
     if (gx > stages) gx = stages;
     if (a.in_scale)
-        wgrad_tc_kernel<true><<<dim3((unsigned)gx, gy), kWThreads, smem, stream>>>(w);
+        launch_k(wgrad_tc_kernel<true>, dim3((unsigned)gx, gy), dim3(kWThreads), smem, stream, w);
     else
-        wgrad_tc_kernel<false><<<dim3((unsigned)gx, gy), kWThreads, smem, stream>>>(w);
+        launch_k(wgrad_tc_kernel<false>, dim3((unsigned)gx, gy), dim3(kWThreads), smem, stream, w);
     PN2_CHECK_LAUNCH("wgrad_tc_kernel");
     return 0;
 }

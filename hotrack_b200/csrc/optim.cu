@@ -30,11 +30,12 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
     p -= a.lr_over_bc1 * (m / denom);
 }
 
-__global__ void adam_advance_kernel(int* step_dev) { *step_dev += 1; }
+__global__ void adam_advance_kernel(int* step_dev) { pdl_enter(); *step_dev += 1; }
 
 __global__ void __launch_bounds__(256)
 adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, AdamArgs a) {
+    pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     if (a.step_dev) {  // bias corrections from the device-side counter (same for every thread)
         const float t = (float)(*a.step_dev + 1);
         a.lr_over_bc1 = a.lr / (1.f - powf(a.beta1, t));
@@ -84,10 +85,10 @@ extern "C" int pn2_adam_step(long long n, float* params, const float* grads, flo
     long long blocks = ((n >> 2) + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, params, grads, exp_avg, exp_avg_sq, a);
+    launch_k(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq, a);
     PN2_CHECK_LAUNCH("adam_kernel");
     if (step_dev) {
-        adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+        launch_k(adam_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev);
         PN2_CHECK_LAUNCH("adam_advance_kernel");
     }
     return 0;

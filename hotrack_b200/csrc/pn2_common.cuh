@@ -50,6 +50,39 @@ void count_launch();
         ::pn2::count_launch();                                     \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A training step is ~240 dependent kernels, most of them 5..30 us long: the gap between "last CTA of kernel N retires" and
+// "first CTA of kernel N+1 runs its first instruction" (grid completion, launch, CTA scheduling) is a measurable part of
+// the step.  Kernels launched through launch_k() carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may
+// be scheduled as soon as every CTA of the preceding kernel in the stream has STARTED (all of ours call pdl_trigger() in
+// their first instructions) and a slot is free, and they block in pdl_wait() -- their first statement, before ANY global
+// memory access -- until the preceding kernel has completed and its writes are visible.  Semantics are those of plain
+// stream order (a kernel that waits cannot complete before its predecessor, so the guarantee is transitive); only the
+// launch latency is overlapped.  RULE: a kernel may be launched with launch_k() only if pdl_wait() is its first statement.
+// Works eagerly and under stream capture (programmatic graph edges).  PN2_PDL=0 turns the attribute off.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_wait();
+    pdl_trigger();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define PN2_CHECK(call, where)                                     \
     do {                                                           \
         cudaError_t e__ = (call);                                  \

@@ -203,7 +203,9 @@ def test_handtracknet_fused_engine(refnet, cuda):
         ours.canon_pose = lambda *a, **kw: canon  # same hand frame (see test_handtracknet_training_step_matches_reference)
         o = ours(data, flags)
     assert _rel(o["pred_kp_handframe"], t["pred_kp_handframe"]) < 1e-2
-    assert (o["pred_kp"] - t["pred_kp"]).abs().max().item() < 2e-3  # metres
+    # metres; measured 1.0e-3 .. 2.0e-3: the running statistics come from three training steps of the REFERENCE, whose
+    # atomics make them (and with them this deviation) differ from run to run
+    assert (o["pred_kp"] - t["pred_kp"]).abs().max().item() < 4e-3
 
 
 @pytest.mark.parametrize("graph,handframe", [(False, "camera"), (True, "camera"), (True, "kp")])
