@@ -95,10 +95,11 @@ class TrainStep:
         # pair the 2-GPU bench stopped making progress inside the captured exchange (round 2), so it is off by default.
         self._finish_in_graph = self.world == 1 or os.environ.get("PN2_GRAPH_ALLREDUCE", "0") == "1"
         self._graph = torch.cuda.CUDAGraph()
-        # The chain of dependent kernels is captured on a HIGH-priority stream (graph kernel nodes keep the priority of the
-        # stream they were captured on); the weight-gradient side stream has default priority, so whenever both have CTAs
-        # waiting for an SM the latency-critical chain goes first and the weight gradients fill what is left.
-        cap = torch.cuda.Stream(priority=-1) if os.environ.get("PN2_PRIO", "1") != "0" else None
+        # PN2_PRIO=1: capture the chain of dependent kernels on a HIGH-priority stream (graph kernel nodes keep the priority
+        # of the stream they were captured on; the weight-gradient side stream has default priority, so the latency-critical
+        # chain gets free SMs first).  Measured (B=32, N=4096): 3.65 -> 3.47 ms alone, but nothing on top of programmatic
+        # dependent launch (3.43 ms without, 3.49 ms with), so it is off by default.
+        cap = torch.cuda.Stream(priority=-1) if os.environ.get("PN2_PRIO", "0") == "1" else None
         with torch.cuda.graph(self._graph, stream=cap):
             self._loss = self._fwd_bwd(self._static_in)
             if self._finish_in_graph:
