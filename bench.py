@@ -183,34 +183,37 @@ def alg_bytes(name, a):
 
 
 _MS = None
+_MS_CONST = {}
 
 
-def _mean_square(t):
-    """mean(t^2), written so that the 201 MB backbone output is read once forward (one reduction kernel) and its
-    gradient 2 t / numel is one elementwise kernel backward -- torch's own composite (square().mean()) takes five
-    passes.  Plain torch ops in an autograd.Function; the loss is harness, not the path, and both arms pay for it."""
+def loss_fn(src2, f11, f13):
+    """mean(src2^2) + mean(f11^2) + mean(f13^2), as ONE autograd.Function of plain torch ops: each tensor is read once
+    forward (one reduction kernel; the backbone output alone is 201 MB) and its gradient 2 t / numel is one elementwise
+    kernel backward, the scalar bookkeeping is three small kernels forward and one backward -- torch's own composite
+    (square().mean() per term, summed) takes five passes per tensor and a dozen scalar kernels.  The loss is harness, not
+    the path, and both arms pay for it."""
     global _MS
     if _MS is None:
         import torch
 
-        class MeanSquare(torch.autograd.Function):
+        class MeanSquareSum(torch.autograd.Function):
             @staticmethod
-            def forward(ctx, x):
-                ctx.save_for_backward(x)
-                n = torch.linalg.vector_norm(x)
-                return n * n / x.numel()
+            def forward(ctx, *xs):
+                ctx.save_for_backward(*xs)
+                key = (xs[0].device, tuple(x.numel() for x in xs))
+                if key not in _MS_CONST:  # first call happens outside any graph capture (warm-up steps)
+                    _MS_CONST[key] = torch.tensor([1.0 / x.numel() for x in xs], dtype=torch.float32, device=xs[0].device)
+                ctx.inv = _MS_CONST[key]
+                n = torch.stack([torch.linalg.vector_norm(x) for x in xs])
+                return torch.dot(n * n, ctx.inv)
 
             @staticmethod
             def backward(ctx, g):
-                (x,) = ctx.saved_tensors
-                return x * (g * (2.0 / x.numel()))
+                s = ctx.inv * (g * 2.0)
+                return tuple(x * s[i] for i, x in enumerate(ctx.saved_tensors))
 
-        _MS = MeanSquare
-    return _MS.apply(t)
-
-
-def loss_fn(src2, f11, f13):
-    return _mean_square(src2) + _mean_square(f11) + _mean_square(f13)
+        _MS = MeanSquareSum
+    return _MS.apply(src2, f11, f13)
 
 
 def make_inputs(B, N, rank):
@@ -496,7 +499,7 @@ def main():
         fused.set_precise(args.precision)
     model = build_model(args.impl, engine, dev)
     if args.impl == "ours":
-        from hotrack_b200 import _lib
+        from hotrack_b200 import _lib, pointnet_utils as pu
         from hotrack_b200.train import TrainStep
 
         class FromPoints(torch.nn.Module):  # (B,N,3)/(B,21,3) -> the (B,3,N) layout canonicalize() hands the backbone
@@ -505,7 +508,11 @@ def main():
                 self.path = path
 
             def forward(self, xyz, kps):
-                return self.path(xyz.transpose(1, 2).contiguous(), kps.transpose(1, 2).contiguous())
+                # t_contig = .transpose(1, 2).contiguous(), remembered for the duration of the scope: the modules inside
+                # want the point-major twin back (FPS, ball query, kNN, three-NN) and find the original instead of
+                # transposing a second time
+                with pu.coord_scope():
+                    return self.path(pu.t_contig(xyz), pu.t_contig(kps))
 
         train = TrainStep(FromPoints(model), lambda out: loss_fn(*out[:3]), lr=1e-4, weight_decay=1e-4,
                           graph=not args.no_graph)

@@ -50,7 +50,7 @@ SIGNATURES = {
     "pn2_mlp_prep_weights": [_i, _i, _i, _p, _p, _p, _p],
     "pn2_mlp_prep_weights_multi": [_i, _p, _p],
     "pn2_sa_rows_bwd": [_i, _i, _i, _i, _p, _p, _i, _i, _p, _i, _i, _p, _i, _p],
-    "pn2_fp_rows_bwd": [_i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _p, _p],
+    "pn2_fp_rows_bwd": [_i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _p, _p],
     # two-plane (hi + lo) forward rows
     "pn2_to_rows_x2": [_i, _i, _i, _p, _p, _f, _p, _p, _i, _p],
     "pn2_sa_build_rows_x2": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _i, _p, _p, _i, _p],

@@ -61,6 +61,10 @@ class PointNet2Msg(nn.Module):
         self.device = cfg["device"]
 
     def forward(self, input):
+        with pu.coord_scope():
+            return self._forward(input)
+
+    def _forward(self, input):
         l0_xyz = input[:, :3]
         l0_points = input if self.use_xyz_feat else input[:, 3:]
         l1_xyz, l1_points = self.sa1(l0_xyz, l0_points)
@@ -93,6 +97,10 @@ class PointNet2Msg_fast(nn.Module):
         self.fp3.precise_layers = 1
 
     def forward(self, input):
+        with pu.coord_scope():  # coordinate transposes shared by SA1 / SA2 / FP2 / FP1 (pointnet_utils.t_contig)
+            return self._forward(input)
+
+    def _forward(self, input):
         B, C, N = input.shape
         input = input.reshape(B, 1, C, N)
         l0_xyz = input[:, :, :3]

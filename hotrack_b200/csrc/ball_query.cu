@@ -121,9 +121,11 @@ ball_query_kernel(int n, int m, float radius, int nsample, const float* __restri
     // left early with tile t+1 still in flight: the CTA must outlive its bulk copy
     if (use_bulk && tid == 0 && t + 1 < ntiles) mbar_wait(&s_bar[(t + 1) & 1], ((t + 1) >> 1) & 1);
 
-    // pad the remaining slots with the first hit (ball_query_gpu.cu:35-39)
-    if (active && found > 0 && found < nsample)
-        for (int s = found + lane; s < nsample; s += 32) out[s] = first;
+    // pad the remaining slots with the first hit (ball_query_gpu.cu:35-39); an empty ball keeps index 0 in every slot --
+    // the reference leaves its zero-initialised output untouched there (pointnet2_utils.py:184 of the reference); written
+    // here so that the caller need not zero the buffer first
+    if (active && found < nsample)
+        for (int s = found + lane; s < nsample; s += 32) out[s] = found > 0 ? first : 0;
 }
 
 }  // namespace

@@ -34,6 +34,6 @@ int fail_arg(const char* where, const char* what) {
 }
 }  // namespace pn2
 
-extern "C" int pn2_version(void) { return 200; /* 0.2.0: tcgen05 GEMMs; pn2_mlp_gemm_dgrad / pn2_bn_bwd_coefs / pn2_pool_bwd signatures changed */ }
+extern "C" int pn2_version(void) { return 201; /* 0.2.1: pn2_fp_rows_bwd takes skip_rows_major; pn2_pool_bwd takes extra_rows for k > 1; ball_query writes empty balls */ }
 extern "C" long long pn2_launch_count(void) { return pn2::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* pn2_last_error(void) { return pn2::g_last_error; }

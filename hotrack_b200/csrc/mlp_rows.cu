@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int cc = warp + j * 8, chn = c0 + cc, s = s0 + lane;
-                tile[lane][cc] = (chn < a.c && s < a.s) ? a.dout_cm[((size_t)b * a.c + chn) * a.s + s] : 0.f;
+                tile[lane][cc] = (a.dout_cm && chn < a.c && s < a.s) ? a.dout_cm[((size_t)b * a.c + chn) * a.s + s] : 0.f;
             }
         }
         __syncthreads();
@@ -536,18 +536,22 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_kernel(const PoolArgs a) {
             const size_t g = (size_t)b * a.s + s;
             int i0 = 0, i1 = 0;
             if (a.argmax) { const int2 am = *reinterpret_cast<const int2*>(a.argmax + g * a.c + ch); i0 = am.x; i1 = am.y; }
-            const float g0 = tile[gi][lane * 2], g1 = tile[gi][lane * 2 + 1];
+            float g0 = tile[gi][lane * 2], g1 = tile[gi][lane * 2 + 1];
+            if (a.extra_rows) {  // row-form gradients of fused consumers (fp32 [B*S][C], see pn2_sa_rows_bwd)
+                const float2 ex = *reinterpret_cast<const float2*>(a.extra_rows + g * a.c + ch);
+                g0 += ex.x; g1 += ex.y;
+            }
             const act_t* yr = a.y + (g * a.k) * a.y_ld + ch;
             bf16* dr = a.dz + (g * a.k) * a.dz_ld + ch;
-            for (int kk = 0; kk < a.k; ++kk) {
-                float d0 = 0.f, d1 = 0.f;
-                if (kk == i0 || kk == i1) {
-                    const float2 v = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)kk * a.y_ld));
-                    if (kk == i0 && fmaf(v.x, sc0, sh0) > 0.f) { d0 = g0; p1a += d0; p2a = fmaf(d0, (v.x - mu0) * rs0, p2a); }
-                    if (kk == i1 && fmaf(v.y, sc1, sh1) > 0.f) { d1 = g1; p1b += d1; p2b = fmaf(d1, (v.y - mu1) * rs1, p2b); }
-                }
-                *reinterpret_cast<uint32_t*>(dr + (size_t)kk * a.dz_ld) = f2_to_bf2(d0, d1);
-            }
+            // the two arg-max rows' values first (two independent loads), then a store-only loop over the K rows
+            const float y0 = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)i0 * a.y_ld)).x;
+            const float y1 = h2_to_f2(*reinterpret_cast<const uint32_t*>(yr + (size_t)i1 * a.y_ld)).y;
+            float d0 = 0.f, d1 = 0.f;
+            if (fmaf(y0, sc0, sh0) > 0.f) { d0 = g0; p1a += d0; p2a = fmaf(d0, (y0 - mu0) * rs0, p2a); }
+            if (fmaf(y1, sc1, sh1) > 0.f) { d1 = g1; p1b += d1; p2b = fmaf(d1, (y1 - mu1) * rs1, p2b); }
+#pragma unroll 8
+            for (int kk = 0; kk < a.k; ++kk)
+                *reinterpret_cast<uint32_t*>(dr + (size_t)kk * a.dz_ld) = f2_to_bf2(kk == i0 ? d0 : 0.f, kk == i1 ? d1 : 0.f);
         }
         __syncthreads();
     }
@@ -698,7 +702,8 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_grp_kernel(const PoolArgs a
                 const int b = g / a.s, s_ = g - b * a.s;
                 const int kk = a.argmax[(size_t)g * a.c + c];
                 const float yv = h_to_f(a.y[((size_t)g * a.k + kk) * a.y_ld + c]);
-                float d = a.dout_cm[((size_t)b * a.c + c) * a.s + s_];
+                float d = a.dout_cm ? a.dout_cm[((size_t)b * a.c + c) * a.s + s_] : 0.f;
+                if (a.extra_rows) d += a.extra_rows[(size_t)g * a.c + c];  // row-form gradients of fused consumers
                 d = fmaf(yv, sc, sh) > 0.f ? d : 0.f;
                 p1 += d;
                 p2 = fmaf(d, (yv - mu) * rs, p2);
@@ -967,7 +972,8 @@ struct FpBwdArgs {
     int b, n, s;
     const int* idx; const float* dist2;
     const bf16* dx; int dx_ld;
-    int skip_c; float* dskip_cm;       // (B,skip_c,N) plain stores | null
+    int skip_c; float* dskip_cm;       // (B,skip_c,N) plain stores | rows [B*N][skip_c] accumulated (skip_rows_major) | null
+    int skip_rows_major;
     int coarse_c; float* dcoarse_rows; // (B*S, coarse_c) zeroed, atomics | null
 };
 __global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a) {
@@ -978,9 +984,26 @@ __global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a
     if (row >= total) return;
     const int b = (int)(row / a.n), i = (int)(row % a.n);
     const bf16* d = a.dx + (size_t)row * a.dx_ld;
-    if (a.dskip_cm)
-        for (int col = lane; col < a.skip_c; col += 32)
-            a.dskip_cm[((size_t)b * a.skip_c + col) * a.n + i] = bf_to_f(d[col]);
+    if (a.dskip_cm) {
+        if (a.skip_rows_major) {  // fp32 rows [B*N][skip_c] shared with other consumers of the same producer: accumulate
+            float* dst = a.dskip_cm + (size_t)row * a.skip_c;
+            if ((a.skip_c & 3) == 0 && (a.dx_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dskip_cm) & 15) == 0) {
+                for (int col = lane * 4; col < a.skip_c; col += 128) {
+                    const uint2 q = __ldg(reinterpret_cast<const uint2*>(d + col));
+                    const float2 v0 = bf2_to_f2(q.x), v1 = bf2_to_f2(q.y);
+                    if (q.x | q.y) red_add_v4(dst + col, v0.x, v0.y, v1.x, v1.y);
+                }
+            } else {
+                for (int col = lane; col < a.skip_c; col += 32) {
+                    const float v = bf_to_f(d[col]);
+                    if (v != 0.f) atomicAdd(dst + col, v);
+                }
+            }
+        } else {
+            for (int col = lane; col < a.skip_c; col += 32)
+                a.dskip_cm[((size_t)b * a.skip_c + col) * a.n + i] = bf_to_f(d[col]);
+        }
+    }
     if (a.dcoarse_rows) {
         int id[3] = {0, 0, 0};
         float w[3] = {1.f, 0.f, 0.f};
@@ -989,15 +1012,32 @@ __global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a
             for (int j = 0; j < 3; ++j) id[j] = a.idx[row * 3 + j];
             nn_weights(a.dist2 + row * 3, w);
         }
-        for (int col = lane; col < a.coarse_c; col += 32) {
-            const float v = bf_to_f(d[a.skip_c + col]);
-            if (v == 0.f) continue;
-            if (a.s > 1) {
+        if ((a.coarse_c & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dcoarse_rows) & 15) == 0) {
+            // a lane owns four consecutive channels: 16-byte vector reductions (a quarter of the atomic operations)
+            for (int col = lane * 4; col < a.coarse_c; col += 128) {
+                const bf16* dp = d + a.skip_c + col;
+                const float v0 = bf_to_f(dp[0]), v1 = bf_to_f(dp[1]), v2 = bf_to_f(dp[2]), v3 = bf_to_f(dp[3]);
+                if (v0 == 0.f && v1 == 0.f && v2 == 0.f && v3 == 0.f) continue;
+                if (a.s > 1) {
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    atomicAdd(a.dcoarse_rows + ((size_t)b * a.s + id[j]) * a.coarse_c + col, v * w[j]);
-            } else {
-                atomicAdd(a.dcoarse_rows + (size_t)b * a.coarse_c + col, v);
+                    for (int j = 0; j < 3; ++j)
+                        red_add_v4(a.dcoarse_rows + ((size_t)b * a.s + id[j]) * a.coarse_c + col, v0 * w[j], v1 * w[j],
+                                   v2 * w[j], v3 * w[j]);
+                } else {
+                    red_add_v4(a.dcoarse_rows + (size_t)b * a.coarse_c + col, v0, v1, v2, v3);
+                }
+            }
+        } else {
+            for (int col = lane; col < a.coarse_c; col += 32) {
+                const float v = bf_to_f(d[a.skip_c + col]);
+                if (v == 0.f) continue;
+                if (a.s > 1) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        atomicAdd(a.dcoarse_rows + ((size_t)b * a.s + id[j]) * a.coarse_c + col, v * w[j]);
+                } else {
+                    atomicAdd(a.dcoarse_rows + (size_t)b * a.coarse_c + col, v);
+                }
             }
         }
     }
@@ -1166,10 +1206,9 @@ extern "C" int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, co
     if ((!dout_cm && !extra_rows && !extra_rows16) || !y || !scale || !shift || !mean || !rstd || !dz || !sums)
         return fail_arg("pn2_pool_bwd", "null pointer");
     if (k > 1 && !argmax) return fail_arg("pn2_pool_bwd", "argmax required when k > 1");
-    if ((extra_rows || extra_rows16) && !(k == 1 && c <= 1024))
-        return fail_arg("pn2_pool_bwd", "extra_rows needs k == 1 and c <= 1024");
+    if (extra_rows16 && k != 1) return fail_arg("pn2_pool_bwd", "extra_rows16 needs k == 1");
+    if ((extra_rows || extra_rows16) && k == 1 && c > 1024) return fail_arg("pn2_pool_bwd", "extra rows with k == 1 need c <= 1024");
     if (extra_rows16 && (extra16_ld < c || extra16_ld % 8)) return fail_arg("pn2_pool_bwd", "bad extra16_ld");
-    if (k > 1 && !dout_cm) return fail_arg("pn2_pool_bwd", "dout_cm required when k > 1");
     PoolArgs a{};
     a.b = b; a.s = s; a.k = k; a.c = c; a.y = (const act_t*)y; a.y_ld = y_ld; a.scale = scale; a.shift = shift;
     a.mean = mean; a.rstd = rstd; a.argmax = const_cast<int*>(argmax); a.dout_cm = dout_cm; a.extra_rows = extra_rows;
@@ -1220,13 +1259,15 @@ extern "C" int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const
 }
 
 extern "C" int pn2_fp_rows_bwd(int b, int n, int s, const int* idx, const float* dist2, const void* dx, int dx_ld,
-                               int skip_c, float* dskip_cm, int coarse_c, float* dcoarse_rows, pn2_stream_t stream) {
+                               int skip_c, float* dskip, int skip_rows_major, int coarse_c, float* dcoarse_rows,
+                               pn2_stream_t stream) {
     if (b < 0 || n <= 0 || s <= 0) return fail_arg("pn2_fp_rows_bwd", "bad size");
-    if (b == 0 || (!dskip_cm && !dcoarse_rows)) return 0;
+    if (b == 0 || (!dskip && !dcoarse_rows)) return 0;
     if (!dx || (s > 1 && dcoarse_rows && (!idx || !dist2))) return fail_arg("pn2_fp_rows_bwd", "null pointer");
     FpBwdArgs a;
     a.b = b; a.n = n; a.s = s; a.idx = idx; a.dist2 = dist2; a.dx = (const bf16*)dx; a.dx_ld = dx_ld;
-    a.skip_c = skip_c; a.dskip_cm = dskip_cm; a.coarse_c = coarse_c; a.dcoarse_rows = dcoarse_rows;
+    a.skip_c = skip_c; a.dskip_cm = dskip; a.skip_rows_major = skip_rows_major; a.coarse_c = coarse_c;
+    a.dcoarse_rows = dcoarse_rows;
     launch_k(fp_rows_bwd_kernel, dim3(warp_blocks((long long)b * n)), dim3(kThreads), 0, (cudaStream_t)stream, a);
     PN2_CHECK_LAUNCH("fp_rows_bwd_kernel");
     return 0;

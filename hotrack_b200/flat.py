@@ -18,7 +18,7 @@ class FlatParams:
     16-byte aligned so the Adam kernel can use float4 accesses on each tensor boundary too.
     """
 
-    def __init__(self, module, align=4):
+    def __init__(self, module, align=4, tail=0):
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
@@ -31,7 +31,10 @@ class FlatParams:
             off += (p.numel() + align - 1) // align * align
         self.numel = off
         self.data = torch.zeros(off, dtype=dt, device=dev)
-        self.grad = torch.zeros(off, dtype=dt, device=dev)
+        # ``tail`` extra floats behind the gradients, zeroed by the same memset (TrainStep's accumulator arena)
+        self._gbuf = torch.zeros(off + tail, dtype=dt, device=dev)
+        self.grad = self._gbuf[:off]
+        self.tail = self._gbuf[off:]
         for p, o in zip(self.params, self.offsets):
             n = p.numel()
             self.data[o:o + n].copy_(p.data.reshape(-1))
@@ -40,7 +43,7 @@ class FlatParams:
 
     def zero_grad(self):
         """One memset; keeps every p.grad aliased to the flat buffer (autograd accumulates in place)."""
-        self.grad.zero_()
+        self._gbuf.zero_()
         for p, o in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)

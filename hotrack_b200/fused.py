@@ -166,12 +166,16 @@ class ZeroArena:
     Bump allocation, nothing is returned; a stack that finds the arena absent or exhausted falls back to torch.zeros.
     Owned by TrainStep (static addresses: CUDA-graph friendly)."""
 
-    def __init__(self, device, floats=1 << 18):
-        self.buf = torch.zeros(floats, dtype=torch.float32, device=device)
+    def __init__(self, device=None, floats=1 << 18, buf=None):
+        # buf: a buffer somebody else zeroes at the top of every step (the tail of FlatParams' gradient buffer: one
+        # memset for gradients and accumulators together)
+        self.owned = buf is None
+        self.buf = torch.zeros(floats, dtype=torch.float32, device=device) if buf is None else buf
         self.off = 0
 
     def begin(self):
-        self.buf.zero_()
+        if self.owned:
+            self.buf.zero_()
         self.off = 0
 
     def take(self, n):
@@ -226,11 +230,12 @@ def reset_center_state(module):
 
 
 class _Sink:
-    __slots__ = ("rows", "c", "buf", "rows16")
+    __slots__ = ("rows", "c", "buf", "rows16", "k1")
 
-    def __init__(self, rows, c):
+    def __init__(self, rows, c, k1=True):
         self.rows, self.c, self.buf = rows, c, None
         self.rows16 = None  # (bf16 [rows][ld] tensor, ld): the input gradient of a dense consumer, left in row form
+        self.k1 = k1        # producer is a K=1 stack (pn2_pool_bwd takes rows16 only there)
 
 
 class Rows:
@@ -477,14 +482,25 @@ class _MlpStack(Function):
             out_rows = torch.empty(2 if two_out else 1, B * groups, C, dtype=_F16, device=dev)
             _lib.call("pn2_to_rows_x2", B, C, groups, out.data_ptr(), chan_sums.data_ptr(), inv, out_rows[0].data_ptr(),
                       out_rows[1].data_ptr() if two_out else 0, C, st)
-            _MlpStack.last_rows = Rows(out_rows[0], C, C, offset=(chan_sums, inv), lo=out_rows[1] if two_out else None)
-            ctx.out_sink = None
+            # pooled outputs offer a row-form gradient sink too: SA2 / SA3 gathering from SA1 / SA2's output and the FP
+            # layers' skip connections accumulate coalesced fp32 rows instead of strided channel-major atomics
+            ctx.out_sink = _Sink(B * groups, C, k1=False) if training else None
+            _MlpStack.last_rows = Rows(out_rows[0], C, C, offset=(chan_sums, inv), lo=out_rows[1] if two_out else None,
+                                       sink=ctx.out_sink)
         else:
             ctx.out_sink = _Sink(R, C) if (training and C <= 1024) else None
             _MlpStack.last_rows = Rows(last.y, C, C, last.scale, last.shift, sink=ctx.out_sink, lo=x_lo)
         # gather-type consumer of a producer that offers a sink: deliver the feature gradient in row form
         ctx.feat_sink = ra.sink if (kind in ("sa", "dense") and SPARSE_GRAD_SINK and training and ra is not None
                                     and ra.sink is not None and a is not None and a.requires_grad) else None
+        # FP layer on top of a fused K=1 producer (FP2 -> FP1, FP3 -> FP2): the coarse features' gradient is scattered
+        # straight into the producer's row-form sink instead of a zero-filled buffer that is then transposed to (B,C,S)
+        # for autograd and transposed back to rows by the producer's backward
+        ctx.skip_sink = ra.sink if (kind == "fp" and SPARSE_GRAD_SINK and training and ra is not None and ra.sink is not None
+                                    and a is not None and ra.sink.rows == a.shape[0] * a.shape[2] and ra.sink.c == ra.c
+                                    and a.requires_grad) else None
+        ctx.coarse_sink = rb.sink if (kind == "fp" and SPARSE_GRAD_SINK and training and rb is not None and rb.sink is not None
+                                      and rb.sink.rows == b.shape[0] * b.shape[2] and b.requires_grad) else None
         del x_lo, x0_lo  # lo planes are forward-only: backward reads the hi planes
 
         ctx.kind, ctx.meta, ctx.training = kind, meta, training
@@ -622,14 +638,25 @@ class _MlpStack(Function):
                 idx, dist2, N, S = ctx.meta[:4]
                 sc = ctx.a_shape[1] if ctx.a_shape is not None else 0
                 c2 = ctx.b_shape[1]
-                if need_a:
-                    da = torch.empty(ctx.a_shape, dtype=torch.float32, device=dev)
-                dcr = torch.zeros(B * S, c2, dtype=torch.float32, device=dev) if need_b else None
-                _lib.call("pn2_fp_rows_bwd", B, N, S, _p(idx), _p(dist2), dx0.data_ptr(), dx0.shape[1], sc, _p(da), c2,
-                          _p(dcr), st)
-                if need_b:
+                dskip, skip_rows = None, 0
+                if need_a and ctx.skip_sink is not None:
+                    if ctx.skip_sink.buf is None:
+                        ctx.skip_sink.buf = torch.zeros(ctx.skip_sink.rows, ctx.skip_sink.c, dtype=torch.float32, device=dev)
+                    dskip, skip_rows = ctx.skip_sink.buf, 1  # da stays None (see the sink hand-over above)
+                elif need_a:
+                    dskip = da = torch.empty(ctx.a_shape, dtype=torch.float32, device=dev)
+                sink = ctx.coarse_sink if need_b else None
+                if sink is not None:
+                    if sink.buf is None:
+                        sink.buf = torch.zeros(sink.rows, sink.c, dtype=torch.float32, device=dev)
+                    dcr = sink.buf  # db stays None: the producer's backward adds the buffer while it builds its dz
+                else:
+                    dcr = torch.zeros(B * S, c2, dtype=torch.float32, device=dev) if need_b else None
+                _lib.call("pn2_fp_rows_bwd", B, N, S, _p(idx), _p(dist2), dx0.data_ptr(), dx0.shape[1], sc, _p(dskip), skip_rows,
+                          c2, _p(dcr), st)
+                if need_b and sink is None:
                     db = dcr.view(B, S, c2).transpose(1, 2).contiguous()
-            elif ctx.feat_sink is not None and need_a:
+            elif ctx.feat_sink is not None and ctx.feat_sink.k1 and need_a:
                 # the producer's backward reads it as rows; da stays None (autograd still runs the producer's node,
                 # with an undefined gradient: ctx.set_materialize_grads(False))
                 if ctx.feat_sink.rows16 is not None:

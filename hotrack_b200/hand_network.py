@@ -20,7 +20,7 @@ import torch.nn as nn
 from .backbones import PointNet2Msg_fast
 from .hand_utils import canonicalize, decanonicalize, handkp2palmkp, ransac_rt
 from .head_blocks import PositionEmbeddingSine, TransT, attn_module, rearrange_module
-from .pointnet_utils import PointNetSetAbstractionMsg_GivenCenterPoints, knn_point
+from .pointnet_utils import PointNetSetAbstractionMsg_GivenCenterPoints, coord_scope, knn_point
 
 
 def L2_loss(x, y, mask=None):  # x, y: [B,3,n], mask: [B,1,n]
@@ -98,9 +98,10 @@ class HandTrackNet(nn.Module):
         cam = canonicalize(torch.cat([hand_points, jittered_kp], dim=1).transpose(2, 1), canon)
         xyz2, xyz1 = cam[..., :-kp_num], cam[..., -kp_num:]
 
-        src2 = self.bhand(xyz2)
-        f11, group_idx = self.q1(xyz2, src2, xyz1, None, return_group_idx=True)
-        f13 = self.q2(xyz2, src2, xyz1, self.r1(f11), pre_group_idx=group_idx)
+        with coord_scope():  # the backbone and q1 share the point-major twin of xyz2
+            src2 = self.bhand(xyz2)
+            f11, group_idx = self.q1(xyz2, src2, xyz1, None, return_group_idx=True)
+            f13 = self.q2(xyz2, src2, xyz1, self.r1(f11), pre_group_idx=group_idx)
         f14 = self.r2(f13)
         f15, _ = self.transt(src1=f14, pos1=None, src2=src2, pos2=None, attn=False, need_result2=False)
         fused = self.c3(f15, None, None, None, attn=False)

@@ -43,6 +43,17 @@ class HandTrackPointPath(nn.Module):
     def forward(self, xyz2, xyz1):
         """xyz2 (B,3,N) canonicalised hand cloud, xyz1 (B,3,21) canonicalised joints ->
         (src2 (B,384,N), f11 (B,384,21), f13 (B,384,21), group indices)."""
+        if not hasattr(self.q1, "group_indices"):  # the reference's classes (parity tests, bench.py's reference arm)
+            return self._forward(xyz2, xyz1)
+        from . import pointnet_utils as pu
+
+        with pu.coord_scope():  # one forward pass: the (B,N,3) twins of the coordinate tensors are made once
+            # ... and on THIS stream, before the side stream forks off (it reads them too)
+            pu.t_contig(xyz2)
+            pu.t_contig(xyz1)
+            return self._forward(xyz2, xyz1)
+
+    def _forward(self, xyz2, xyz1):
         pre = None
         if xyz2.is_cuda and hasattr(self.q1, "group_indices"):
             # q1's neighbour search needs the coordinates only: it runs on a side stream while the backbone starts

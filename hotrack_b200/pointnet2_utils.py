@@ -181,7 +181,8 @@ class BallQuery(Function):
         xyz = xyz.contiguous()
         B, N, _ = xyz.size()
         npoint = new_xyz.size(1)
-        idx = torch.zeros(B, npoint, nsample, dtype=torch.int32, device=xyz.device)
+        # the kernel writes every slot (index 0 for an empty ball: what the reference's zero-initialised buffer keeps)
+        idx = (torch.empty if N > 0 else torch.zeros)(B, npoint, nsample, dtype=torch.int32, device=xyz.device)
         pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
         ctx.mark_non_differentiable(idx)
         return idx

@@ -113,6 +113,51 @@ def _carry(src, dst):
     return dst
 
 
+# Coordinate layouts.  The reference API hands coordinates around channel-major, (B,3,N), while the neighbour-search
+# kernels take point-major (B,N,3): every module transposes what it is given (pointnet_utils.py:380,383,437 of the
+# reference), so one forward pass copies the same three coordinate sets again and again (l0 four times, l1 three times).
+# Inside a ``coord_scope()`` -- one forward pass, during which coordinates do not change -- the transposed twin of a tensor
+# is made once and found again by (address, shape, strides, version); entries keep their source alive, so an address
+# cannot be handed to another tensor while the scope is open.  Outside a scope nothing is remembered.
+_MEMO = None
+
+
+class coord_scope:
+    def __enter__(self):
+        global _MEMO
+        self.outer = _MEMO is not None
+        if not self.outer:
+            _MEMO = {}
+        return self
+
+    def __exit__(self, *exc):
+        global _MEMO
+        if not self.outer:
+            _MEMO = None
+        return False
+
+
+def _memo_key(t):
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version, t.dtype)
+
+
+def t_contig(t):
+    """``t.transpose(1, 2).contiguous()`` of a 3-D tensor, memoised while a ``coord_scope`` is open."""
+    v = t.transpose(1, 2)
+    if v.is_contiguous():
+        return v
+    if _MEMO is None or t.requires_grad:
+        return v.contiguous()
+    e = _MEMO.get(_memo_key(t))
+    if e is not None:
+        return e[1]
+    out = v.contiguous()
+    _MEMO[_memo_key(t)] = (t, out)
+    if t.is_contiguous():
+        _MEMO[_memo_key(out)] = (out, t)  # and back
+    return out
+
+
 # ------------------------------------------------------------------ building blocks -----------
 def _make_stack(in_channel, widths, conv_cls, bn_cls):
     convs, bns = nn.ModuleList(), nn.ModuleList()
@@ -135,6 +180,21 @@ def _neighbour_idx(use_knn, radius, K, xyz_t, new_xyz_t):
     if use_knn:
         return futils.knn(K, new_xyz_t, xyz_t)[1]
     return futils.ball_query(radius, K, xyz_t, new_xyz_t)
+
+
+def _as_long(idx32):
+    """int64 copy of an int32 index tensor (the type the reference API returns, pointnet_utils.py:12-24,140-154) that
+    remembers its int32 source: the kernels want int32, and q1's indices go back in twice per scale (q1, then q2)."""
+    out = idx32.long()
+    out._pn2_i32 = (idx32, out._version)
+    return out
+
+
+def _as_int(idx):
+    twin = getattr(idx, "_pn2_i32", None)
+    if twin is not None and twin[1] == idx._version and twin[0].shape == idx.shape:
+        return twin[0]
+    return idx.int()
 
 
 class _EngineMixin:
@@ -183,10 +243,10 @@ class PointNetSetAbstractionMsg(_MsgBase):
         self._build(radius_list, nsample_list, in_channel, mlp_list, knn)
 
     def forward(self, xyz, points):
-        xyz_t = xyz.transpose(1, 2).contiguous()
+        xyz_t = t_contig(xyz)
         fps_idx = futils.furthest_point_sample(xyz_t, self.npoint)
         new_xyz = futils.gather_operation(xyz.contiguous(), fps_idx)
-        new_xyz_t = new_xyz.transpose(1, 2).contiguous()
+        new_xyz_t = t_contig(new_xyz)
         outs = []
         for i, radius in enumerate(self.radius_list):
             idx = _neighbour_idx(self.knn, radius, self.nsample_list[i], xyz_t, new_xyz_t)
@@ -208,10 +268,10 @@ class PointNetSetAbstractionMsg_fast(_MsgBase):
         B, P, C, N = xyz.shape
         S = self.npoint
         xyz0 = xyz[:, 0].contiguous()
-        xyz_t = xyz0.transpose(1, 2).contiguous()
+        xyz_t = t_contig(xyz0)
         fps_idx = futils.furthest_point_sample(xyz_t, S)
         new_xyz = futils.gather_operation(xyz0, fps_idx)
-        new_xyz_t = new_xyz.transpose(1, 2).contiguous()
+        new_xyz_t = t_contig(new_xyz)
         feats = None
         if points is not None and points.shape[-2] > 0:
             feats = _carry(points, points.reshape(B * P, -1, N))
@@ -237,14 +297,14 @@ class PointNetSetAbstractionMsg_GivenCenterPoints(_MsgBase):
         """The per-scale group indices (int64 (B,S,K) each) ``forward`` would compute: they depend on the coordinates
         only, so a caller may ask for them ahead of time (e.g. on a side stream, while the backbone runs) and pass
         them back as ``pre_group_idx``."""
-        xyz_t = xyz.transpose(1, 2).contiguous()
-        new_xyz_t = new_xyz.transpose(1, 2).contiguous()
+        xyz_t = t_contig(xyz)
+        new_xyz_t = t_contig(new_xyz)
         if self.knn:
             # the k nearest come back ascending with a stable tie rule (interpolate_gpu.cu:30-56), so the K nearest
             # are the first K columns of the max(K) nearest: one search serves every scale
             knn_all = _neighbour_idx(True, self.radius_list[0], max(self.nsample_list), xyz_t, new_xyz_t)
-            return [knn_all[..., :k].long() for k in self.nsample_list]
-        return [_neighbour_idx(False, r, k, xyz_t, new_xyz_t).long() for r, k in zip(self.radius_list, self.nsample_list)]
+            return [_as_long(knn_all[..., :k].contiguous()) for k in self.nsample_list]
+        return [_as_long(_neighbour_idx(False, r, k, xyz_t, new_xyz_t)) for r, k in zip(self.radius_list, self.nsample_list)]
 
     def forward(self, xyz, points, new_xyz, new_points, return_4nn=False, pre_group_idx=None,
                 return_group_idx=False):
@@ -255,7 +315,7 @@ class PointNetSetAbstractionMsg_GivenCenterPoints(_MsgBase):
         for i, radius in enumerate(self.radius_list):
             idx = pre_group_idx[i]
             idx_list.append(idx)
-            outs.append(self._scale(i, xyz, points, new_xyz, idx.int(), new_points))
+            outs.append(self._scale(i, xyz, points, new_xyz, _as_int(idx), new_points))
         out = torch.cat(outs, dim=1)
         if return_4nn:
             rel = futils.grouping_operation(xyz.contiguous(), idx[..., :4].int().contiguous()) - new_xyz.unsqueeze(-1)
@@ -348,7 +408,7 @@ class PointNetFeaturePropagation(_FpBase):
         self._build(in_channel, mlp)
 
     def forward(self, xyz1, xyz2, points1, points2):
-        return self._propagate(xyz1.transpose(1, 2), xyz2.transpose(1, 2), points1, points2)
+        return self._propagate(t_contig(xyz1), t_contig(xyz2), points1, points2)
 
 
 class PointNetFeaturePropagation_fast(_FpBase):
@@ -363,6 +423,6 @@ class PointNetFeaturePropagation_fast(_FpBase):
         B, P, _, N = xyz1.shape
         S = xyz2.shape[-1]
         p1 = _carry(points1, points1.reshape(B * P, -1, N)) if points1 is not None else None
-        out = self._propagate(xyz1[:, 0].transpose(1, 2), xyz2[:, 0].transpose(1, 2), p1,
+        out = self._propagate(t_contig(xyz1[:, 0]), t_contig(xyz2[:, 0]), p1,
                               _carry(points2, points2.reshape(B * P, -1, S)), reps=P)
         return _carry(out, out.reshape(B, P, -1, N))

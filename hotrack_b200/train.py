@@ -21,8 +21,8 @@ class TrainStep:
         self._fused = fused
         self.weights = fused.WeightPlan()
         self.use_plan = os.environ.get("PN2_NO_WPLAN", "") == ""
-        self.arena = fused.ZeroArena(self.flat_device(model)) if self.use_plan else None
-        self.flat = FlatParams(model)
+        self.flat = FlatParams(model, tail=(1 << 18) if self.use_plan else 0)
+        self.arena = fused.ZeroArena(buf=self.flat.tail) if self.use_plan else None  # zeroed by flat.zero_grad()
         self.flat.broadcast(0)
         self.opt = FlatAdam(self.flat, lr=lr, weight_decay=weight_decay)
         self.use_graph = graph

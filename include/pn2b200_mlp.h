@@ -81,9 +81,10 @@ int pn2_pool_fwd(int b, int s, int k, int c, const void* y, int y_ld, const floa
                  float* out_cm, float* chan_sums, int* argmax, pn2_stream_t stream);
 
 /* Backward of pool_fwd: dz[rows][c] = dout at the arg-max row where the ReLU is active, else 0; sums[0..c) +=
- * sum(dz), sums[c..2c) += sum(dz * xhat)  (zeroed by the caller).  k == 1 only: extra_rows [B*S][c] fp32
- * (nullable) is a second output-gradient term in row form (what consumers that GATHER from this output
- * deliver, see pn2_sa_rows_bwd); dout_cm may then be NULL. */
+ * sum(dz), sums[c..2c) += sum(dz * xhat)  (zeroed by the caller).  extra_rows [B*S][c] fp32 (nullable) is a second
+ * output-gradient term in row form (what fused consumers of this output deliver, see pn2_sa_rows_bwd /
+ * pn2_fp_rows_bwd); dout_cm may then be NULL.  extra_rows16 (bf16 rows, a dense consumer's input gradient): k == 1
+ * only. */
 int pn2_pool_bwd(int b, int s, int k, int c, const float* dout_cm, const float* extra_rows, const void* extra_rows16,
                  int extra16_ld, const void* y, int y_ld,
                  const float* scale,
@@ -141,10 +142,11 @@ int pn2_sa_rows_bwd(int b, int n, int s, int k, const int* idx, const void* dx, 
                     float* dfeat_cm, int feat_rows_major, int cen_c, float* dcen_cm, int xyz_first,
                     pn2_stream_t stream);
 
-/* Gradient of fp_build_rows' output rows: dskip_cm (B,skip_c,N) plain stores; dcoarse_rows (B*S, coarse_c) fp32
- * rows, zeroed by the caller, atomics; either may be NULL. */
+/* Gradient of fp_build_rows' output rows: dskip (B,skip_c,N) channel-major, plain stores -- or, skip_rows_major != 0,
+ * fp32 rows [B*N][skip_c] zeroed by the caller and ACCUMULATED into (the form pn2_pool_bwd's extra_rows takes) --;
+ * dcoarse_rows (B*S, coarse_c) fp32 rows, zeroed by the caller, atomics; either may be NULL. */
 int pn2_fp_rows_bwd(int b, int n, int s, const int* idx, const float* dist2, const void* dx, int dx_ld, int skip_c,
-                    float* dskip_cm, int coarse_c, float* dcoarse_rows, pn2_stream_t stream);
+                    float* dskip, int skip_rows_major, int coarse_c, float* dcoarse_rows, pn2_stream_t stream);
 
 /* ---- TWO-PLANE ("x2") forward rows -------------------------------------------------------------------------------
  * A row matrix may come as a PAIR of fp16 planes (hi, lo) of the same shape and leading dimension with

@@ -40,7 +40,7 @@ def one():
     import torch
 
     import bench
-    from hotrack_b200 import _lib, fused
+    from hotrack_b200 import _lib, fused, pointnet_utils as pu
     from hotrack_b200.train import TrainStep
 
     name = os.environ.get("PN2_ABLATE", "none")
@@ -65,10 +65,11 @@ def one():
             self.path = path
 
         def forward(self, xyz, kps):
-            return self.path(xyz.transpose(1, 2).contiguous(), kps.transpose(1, 2).contiguous())
+            with pu.coord_scope():
+                return self.path(pu.t_contig(xyz), pu.t_contig(kps))
 
     if name == "loss_small":
-        loss = lambda out: bench._mean_square(out[2]) + bench._mean_square(out[1])
+        loss = lambda out: out[2].square().mean() + out[1].square().mean()
     else:
         loss = lambda out: bench.loss_fn(*out[:3])
     train = TrainStep(FromPoints(model), loss, lr=1e-4, weight_decay=1e-4, graph=True)
