@@ -46,6 +46,9 @@ constexpr int kTcThreads = (kEpiWarps + 1 + kProdWarps) * 32;
 constexpr int kMaxK = 1024;
 constexpr int kMaxKSplit = 256;  // AFFINE + SPLIT: layers > 0 of the SA stacks (kdim <= 128 on this network)
 constexpr int kSmemBudget = 225 * 1024;
+#ifndef PN2_WARP_ARRIVE
+#define PN2_WARP_ARRIVE 0     // 1: transforming producers arrive once per warp (after __syncwarp) instead of once per thread
+#endif
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     }
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) {
-            mbar_init(&full[i], kProdThreads);
+            mbar_init(&full[i], (PN2_WARP_ARRIVE && AMODE == A_AFFINE) ? kProdWarps : kProdThreads);
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -274,7 +277,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                     }
                 }
                 fence_proxy_async();  // generic-proxy writes (cp.async + the in-place transform) -> visible to the tensor core
+#if PN2_WARP_ARRIVE
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&full[p_slot]);
+#else
                 mbar_arrive(&full[p_slot]);
+#endif
                 if (++p_kc == KT) { p_kc = 0; p_tile += gridDim.x; }
                 if (++p_slot == NST) p_slot = 0;
             }

@@ -39,6 +39,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace pn2 {
 namespace {
@@ -46,7 +47,18 @@ namespace {
 constexpr int WR = 64;            // rows per stage (32-row stages measured slower: the per-stage hand-shakes dominate)
 constexpr int WSUB = WR / 16;     // MMA K steps per stage
 constexpr int MT = 128;           // output channels per CTA = UMMA M
-constexpr int kWEpiWarps = 4, kWMmaWarp = 4, kWProdWarps = 8, kWLoadWarps = 4;
+#ifndef PN2_WG_PROD_WARPS
+#define PN2_WG_PROD_WARPS 8   // transposer warps
+#endif
+#ifndef PN2_WG_SPW
+#define PN2_WG_SPW 2          // 16-row sub-tiles a transposer warp handles per channel block (independent chains in flight)
+#endif
+constexpr int kWEpiWarps = 4, kWMmaWarp = 4, kWProdWarps = PN2_WG_PROD_WARPS, kWLoadWarps = 4;
+constexpr int kSPW = PN2_WG_SPW;
+#ifndef PN2_WARP_ARRIVE
+#define PN2_WARP_ARRIVE 0     // 1: one mbarrier arrival per transposer warp (after __syncwarp) instead of one per thread
+#endif
+constexpr int kFullCount = PN2_WARP_ARRIVE ? kWProdWarps : kWProdWarps * 32;
 constexpr int kWProdThreads = kWProdWarps * 32;   // transposers: warps 5..12
 constexpr int kWLoadThreads = kWLoadWarps * 32;   // loaders: warps 13..16
 constexpr int kWLoadWarp0 = kWEpiWarps + 1 + kWProdWarps;
@@ -120,7 +132,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
     for (int i = tid; i < w.nt * t_bytes / 16; i += kWThreads) reinterpret_cast<uint4*>(sT)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
         for (int i = 0; i < w.nt; ++i) {
-            mbar_init(&full[i], kWProdThreads);
+            mbar_init(&full[i], kFullCount);
             mbar_init(&empty[i], 1);
         }
         mbar_init(done, 1);
@@ -150,37 +162,66 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         // and the X columns of its input-channel tile.
         const int lw = warp - kWLoadWarp0;
         const uint32_t raw0 = smem_u32(sRaw);
-        const int nn8 = nb * 2, upr = 2 * nn8 + 2 * kb;  // pieces per row: [dZ nn8][Y nn8][X 2 kb]
+        const int nn8 = nb * 2, upr = 2 * nn8 + 2 * kb;  // pieces per row: [dZ nn8][Y nn8][X 2 kb] <= 32 + 16
+        // A lane owns the same (at most two) 16-byte pieces of every row: everything that does not depend on the stage is
+        // worked out once, the per-row work is one 64-bit add, one 32-bit add and the copy (the first version recomputed
+        // 64-bit row offsets per copy: ~590 instructions per stage and warp, which made the LOADERS the kernel's
+        // bottleneck -- ncu: 2.5 us per 64-row stage whatever the transposers did)
+        static_assert(2 * (MT / 8) + kMaxKw / 8 <= 64, "a lane owns at most two pieces of a raw row");
+        const unsigned char* src[2];
+        long long step[2];   // 4 rows further (the loader warps interleave rows), in bytes
+        uint32_t cb[2];
+        bool has[2], ok[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = lane + 32 * h;
+            has[h] = j < upr;
+            long long ldb = 0;
+            src[h] = reinterpret_cast<const unsigned char*>(p.dz);
+            cb[h] = 0; ok[h] = false;
+            if (j < nn8) {
+                cb[h] = j * 16; ok[h] = j * 8 < n_here; ldb = 2LL * p.dz_ld;
+                src[h] = reinterpret_cast<const unsigned char*>(p.dz + n0 + j * 8);
+            } else if (j < 2 * nn8) {
+                const int jj = j - nn8;
+                cb[h] = 256 + jj * 16; ok[h] = jj * 8 < n_here; ldb = 2LL * p.y_ld;
+                src[h] = reinterpret_cast<const unsigned char*>(p.y + n0 + jj * 8);
+            } else if (j < upr) {
+                const int jj = j - 2 * nn8;
+                cb[h] = 512 + jj * 16; ok[h] = true; ldb = 2LL * p.x_ld;
+                src[h] = reinterpret_cast<const unsigned char*>(p.x + k0 + jj * 8);
+            }
+            step[h] = ldb * kWLoadWarps;
+            src[h] += ldb * lw;  // this warp's first row of a stage
+        }
+        constexpr int kRowsPerWarp = WR / kWLoadWarps;
+        const uint32_t dstep = (uint32_t)rp * kWLoadWarps;
         long long i_s = blockIdx.x;
         int slot = 0;
         uint32_t phase = 0;
         for (long long c = 0; c < mine; ++c) {
-            mbar_wait(&rempty[slot], phase ^ 1);  // the transposers have read this slot's previous stage
-            const uint32_t st = raw0 + slot * raw_bytes;
+            mbar_wait_parked(&rempty[slot], phase ^ 1);  // the transposers have read this slot's previous stage
+            const uint32_t st = raw0 + slot * raw_bytes + lw * rp;
             const long long row0 = i_s * WR;
-            for (int j = lane; j < upr; j += 32) {
-                int colbyte;            // byte offset of the piece inside the raw row
-                const unsigned char* src;
-                bool ok;
-                if (j < nn8) {
-                    colbyte = j * 16; ok = j * 8 < n_here;
-                    src = reinterpret_cast<const unsigned char*>(p.dz + n0 + j * 8);
-                } else if (j < 2 * nn8) {
-                    const int jj = j - nn8;
-                    colbyte = 256 + jj * 16; ok = jj * 8 < n_here;
-                    src = reinterpret_cast<const unsigned char*>(p.y + n0 + jj * 8);
-                } else {
-                    const int jj = j - 2 * nn8;
-                    colbyte = 512 + jj * 16; ok = true;
-                    src = reinterpret_cast<const unsigned char*>(p.x + k0 + jj * 8);
-                }
-                const long long ldb = 2LL * (j < nn8 ? p.dz_ld : (j < 2 * nn8 ? p.y_ld : p.x_ld));  // row pitch in bytes
+            const bool full_stage = row0 + WR <= p.rows;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!has[h]) continue;
+                const unsigned char* g = src[h] + (step[h] / kWLoadWarps) * row0;
+                uint32_t d = st + cb[h];
+                if (ok[h] && full_stage) {
+#pragma unroll
+                    for (int r = 0; r < kRowsPerWarp; ++r) {
+                        cp_async16_s(d, g, 16);
+                        g += step[h]; d += dstep;
+                    }
+                } else {  // the last stage / a padded half block: rows past the end and dead columns are zero-filled
 #pragma unroll 4
-                for (int r = 0; r < WR / kWLoadWarps; ++r) {
-                    const int prow = lw + r * kWLoadWarps;
-                    const long long row = row0 + prow;
-                    const bool in = ok && row < p.rows;   // past the end / padded half block: zero-fill
-                    cp_async16_s(st + prow * rp + colbyte, in ? src + row * ldb : src, in ? 16 : 0);
+                    for (int r = 0; r < kRowsPerWarp; ++r) {
+                        const bool in = ok[h] && row0 + lw + r * kWLoadWarps < p.rows;
+                        cp_async16_s(d, in ? g : reinterpret_cast<const unsigned char*>(p.dz), in ? 16 : 0);
+                        g += step[h]; d += dstep;
+                    }
                 }
             }
             cp_async_mbar_arrive_noinc(&rfull[slot]);
@@ -196,9 +237,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         // a warp owns the sub-tile PAIR pw & 1 (2 x 16 rows) of channel blocks pw >> 1, + 4, ...: no per-unit index
         // arithmetic, the per-channel constants are fetched once per block, and the two sub-tiles are two independent
         // ldmatrix -> arithmetic -> stmatrix chains in flight per warp
-        static_assert(WSUB == 4 && kWProdWarps == 8, "the warp -> (sub-tile pair, block) map assumes 4 sub-tiles, 8 warps");
-        const int sub0 = (pw & 1) * 2, blk0 = pw >> 1;
-        constexpr int kBlkStep = 4;
+        constexpr int kSubGroups = WSUB / kSPW;            // warps sharing a channel block
+        constexpr int kBlkStep = kWProdWarps / kSubGroups;  // channel blocks in flight per stage
+        static_assert(WSUB % kSPW == 0 && kWProdWarps % kSubGroups == 0, "warp -> (sub-tiles, block) map");
+        const int sub0 = (pw % kSubGroups) * kSPW, blk0 = pw / kSubGroups;
         // ldmatrix lane address: matrix q = lane / 8 -> rows (q & 1) * 8 + lane % 8, columns + (q >> 1) * 8
         const uint32_t ld_off = (uint32_t)(sub0 * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * rp + (lane >> 4) * 16;
         // stmatrix lane address: core matrix of q: channel group + (q >> 1), K half q & 1, row lane % 8
@@ -218,70 +260,84 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                 // rows past the end were zero-filled and must contribute nothing (cC and the ReLU shift alone are not
                 // zero): only the last stage can hold any
                 const int valid = (int)min((long long)WR, p.rows - srow0) - r_lo;  // this thread's rows r_lo + {0,1,8,9} < valid?
-                const bool tail = srow0 + WR > p.rows;
-                for (int blk = blk0; blk < nb; blk += kBlkStep) {
-                    const int ch = blk * 16 + ch_lo;
-                    const float ca0 = sCo[ch], cb0 = sCo[MT + ch], cc0 = sCo[2 * MT + ch];
-                    const float ca1 = sCo[ch + 8], cb1 = sCo[MT + ch + 8], cc1 = sCo[2 * MT + ch + 8];
-                    uint32_t rz[2][4], ry[2][4], o[2][4];
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2) {
-                        ldsm_x4_trans(rz[s2], rs + s2 * 16 * rp + blk * 32);
-                        ldsm_x4_trans(ry[s2], rs + s2 * 16 * rp + 256 + blk * 32);
-                    }
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float ca = (q >> 1) ? ca1 : ca0, cb = (q >> 1) ? cb1 : cb0, cc = (q >> 1) ? cc1 : cc0;
-                            const float2 dz = bf2_to_f2(rz[s2][q]), yy = h2_to_f2(ry[s2][q]);
-                            float v0 = fmaf(ca, dz.x, fmaf(cb, yy.x, cc)), v1 = fmaf(ca, dz.y, fmaf(cb, yy.y, cc));
-                            if (tail) {
-                                if (s2 * 16 + (q & 1) * 8 >= valid) v0 = 0.f;
-                                if (s2 * 16 + (q & 1) * 8 + 1 >= valid) v1 = 0.f;
-                            }
-                            o[s2][q] = f2_to_bf2(v0, v1);
-                        }
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2) stsm_x4(ts + (sub0 + s2) * sub_dy + blk * 512, o[s2]);
-                }
-                for (int blk = blk0; blk < kb; blk += kBlkStep) {
-                    uint32_t r[2][4], o[2][4];
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2) ldsm_x4_trans(r[s2], rs + s2 * 16 * rp + 512 + blk * 32);
-                    if (AFFINE) {
+                // the zero-fill masking of rows past the end costs ~20 % of the transposers' instructions: it is compiled
+                // into the last stage's copy of the loops only
+                auto do_stage = [&](auto tail_c) {
+                    constexpr bool tail = decltype(tail_c)::value;
+                    for (int blk = blk0; blk < nb; blk += kBlkStep) {
                         const int ch = blk * 16 + ch_lo;
-                        const float sc0 = sCo[3 * MT + ch], sh0 = sCo[3 * MT + w.kw + ch];
-                        const float sc1 = sCo[3 * MT + ch + 8], sh1 = sCo[3 * MT + w.kw + ch + 8];
-#pragma unroll
-                        for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
+                        const float ca0 = sCo[ch], cb0 = sCo[MT + ch], cc0 = sCo[2 * MT + ch];
+                        const float ca1 = sCo[ch + 8], cb1 = sCo[MT + ch + 8], cc1 = sCo[2 * MT + ch + 8];
+                        uint32_t rz[kSPW][4], ry[kSPW][4], o[kSPW][4];
+    #pragma unroll
+                        for (int s2 = 0; s2 < kSPW; ++s2) {
+                            ldsm_x4_trans(rz[s2], rs + s2 * 16 * rp + blk * 32);
+                            ldsm_x4_trans(ry[s2], rs + s2 * 16 * rp + 256 + blk * 32);
+                        }
+    #pragma unroll
+                        for (int s2 = 0; s2 < kSPW; ++s2)
+    #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const float sc = (q >> 1) ? sc1 : sc0, sh = (q >> 1) ? sh1 : sh0;
-                                const float2 v = h2_to_f2(r[s2][q]);
-                                float v0 = fmaxf(fmaf(v.x, sc, sh), 0.f), v1 = fmaxf(fmaf(v.y, sc, sh), 0.f);
+                                const float ca = (q >> 1) ? ca1 : ca0, cb = (q >> 1) ? cb1 : cb0, cc = (q >> 1) ? cc1 : cc0;
+                                const float2 dz = bf2_to_f2(rz[s2][q]), yy = h2_to_f2(ry[s2][q]);
+                                float v0 = fmaf(ca, dz.x, fmaf(cb, yy.x, cc)), v1 = fmaf(ca, dz.y, fmaf(cb, yy.y, cc));
                                 if (tail) {
                                     if (s2 * 16 + (q & 1) * 8 >= valid) v0 = 0.f;
                                     if (s2 * 16 + (q & 1) * 8 + 1 >= valid) v1 = 0.f;
                                 }
                                 o[s2][q] = f2_to_bf2(v0, v1);
                             }
-                    } else {
-#pragma unroll
-                        for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 v = h2_to_f2(r[s2][q]);
-                                o[s2][q] = f2_to_bf2(v.x, v.y);
-                            }
+    #pragma unroll
+                        for (int s2 = 0; s2 < kSPW; ++s2) stsm_x4(ts + (sub0 + s2) * sub_dy + blk * 512, o[s2]);
                     }
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2) stsm_x4(ts + t_x + (sub0 + s2) * sub_x + blk * 512, o[s2]);
-                }
+                    for (int blk = blk0; blk < kb; blk += kBlkStep) {
+                        uint32_t r[kSPW][4], o[kSPW][4];
+    #pragma unroll
+                        for (int s2 = 0; s2 < kSPW; ++s2) ldsm_x4_trans(r[s2], rs + s2 * 16 * rp + 512 + blk * 32);
+                        if (AFFINE) {
+                            const int ch = blk * 16 + ch_lo;
+                            const float sc0 = sCo[3 * MT + ch], sh0 = sCo[3 * MT + w.kw + ch];
+                            const float sc1 = sCo[3 * MT + ch + 8], sh1 = sCo[3 * MT + w.kw + ch + 8];
+    #pragma unroll
+                            for (int s2 = 0; s2 < kSPW; ++s2)
+    #pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float sc = (q >> 1) ? sc1 : sc0, sh = (q >> 1) ? sh1 : sh0;
+                                    const float2 v = h2_to_f2(r[s2][q]);
+                                    float v0 = fmaxf(fmaf(v.x, sc, sh), 0.f), v1 = fmaxf(fmaf(v.y, sc, sh), 0.f);
+                                    if (tail) {
+                                        if (s2 * 16 + (q & 1) * 8 >= valid) v0 = 0.f;
+                                        if (s2 * 16 + (q & 1) * 8 + 1 >= valid) v1 = 0.f;
+                                    }
+                                    o[s2][q] = f2_to_bf2(v0, v1);
+                                }
+                        } else {
+    #pragma unroll
+                            for (int s2 = 0; s2 < kSPW; ++s2)
+    #pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 v = h2_to_f2(r[s2][q]);
+                                    o[s2][q] = f2_to_bf2(v.x, v.y);
+                                }
+                        }
+    #pragma unroll
+                        for (int s2 = 0; s2 < kSPW; ++s2) stsm_x4(ts + t_x + (sub0 + s2) * sub_x + blk * 512, o[s2]);
+                    }
+                };
+                if (srow0 + WR > p.rows) do_stage(std::true_type{});
+                else do_stage(std::false_type{});
                 fence_proxy_async();
+#if PN2_WARP_ARRIVE
+                __syncwarp();  // every lane's stores and proxy fence are ordered before lane 0's arrival
+                if (lane == 0) {
+                    mbar_arrive(&full[t_slot]);
+                    mbar_arrive(&rempty[p_slot]);
+                }
+#else
                 mbar_arrive(&full[t_slot]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rempty[p_slot]);  // this warp has read everything it needs from the raw slot
+#endif
                 p_s += gridDim.x;
                 if (++p_slot == w.nr) { p_slot = 0; p_phase ^= 1; }
                 if (++t_slot == w.nt) { t_slot = 0; t_phase ^= 1; }
@@ -294,7 +350,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
         int slot = 0;
         uint32_t phase = 0;
         for (long long c = 0; c < mine; ++c) {
-            mbar_wait(&full[slot], phase);
+            mbar_wait_parked(&full[slot], phase);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t ts = smem_u32(sT + slot * t_bytes);
@@ -403,7 +459,17 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t stream) {
     const long long stages = (a.rows + WR - 1) / WR;
     long long gx = sms[dev] / gy;
     if (gx < 1) gx = 1;
-    if (gx > stages) gx = stages;
+    // Few rows: a CTA's fixed cost (prologue, pipeline fill, drain, the red.add epilogue over its whole tile) is worth ~8
+    // stages of streaming, and every extra row split adds a full tile of atomics.  At least kMinStages stages per CTA:
+    // small layers then occupy a fraction of the SMs and leave the rest to the backward chain running beside them.
+    static int min_stages = -1;
+    if (min_stages < 0) {
+        const char* e = getenv("PN2_WG_MIN_STAGES");
+        min_stages = e ? atoi(e) : 4;
+        if (min_stages < 1) min_stages = 1;
+    }
+    if (gx > stages / min_stages) gx = stages / min_stages;
+    if (gx < 1) gx = 1;
     if (a.in_scale)
         launch_k(wgrad_tc_kernel<true>, dim3((unsigned)gx, gy), dim3(kWThreads), smem, stream, w);
     else

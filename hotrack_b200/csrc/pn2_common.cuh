@@ -130,6 +130,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// ... with a suspend-time hint: the waiting thread may be parked by the hardware for up to `ns` nanoseconds per probe and
+// is resumed early when the phase completes -- for warps that wait most of the time (an MMA issuer, loader warps), whose
+// polling would otherwise take issue slots from the working warps of their scheduler
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns = 400) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITP_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONEP_%=;\n"
+        "bra WAITP_%=;\n"
+        "DONEP_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(ns)
+        : "memory");
+}
 // ... for waits that last a long time (an epilogue waiting for the whole main loop): back off between polls so the
 // spinning warps do not take issue slots from the working ones
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns = 256) {

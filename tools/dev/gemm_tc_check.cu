@@ -245,6 +245,10 @@ int main(int argc, char** argv) {
         time_dgrad(131072, 128, 128, true);
         return 0;
     }
+    if (argc > 1 && !strcmp(argv[1], "prof4")) {  // a square wgrad, one CTA per SM (for ncu)
+        time_wgrad(131072, 128, 128, true);
+        return 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "prof2")) {  // the smallest wgrad (for ncu)
         time_wgrad(262144, 64, 32, true);
         return 0;
