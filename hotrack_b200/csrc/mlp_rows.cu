@@ -178,9 +178,35 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
             if (ol) *reinterpret_cast<uint4*>(ol + col) = *reinterpret_cast<const uint4*>(&s_cen_lo[col]);
             continue;
         }
+        if (col >= fc + 3 + cc) {  // zero padding up to the GEMM's chunk granularity
+            *reinterpret_cast<uint4*>(o + col) = make_uint4(0u, 0u, 0u, 0u);
+            if (ol) *reinterpret_cast<uint4*>(ol + col) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
         float v[8];
         if (fvec && col + 8 <= fc) {
             row_vals8(a.feat, frow, col, v);
+        } else if ((fc == 0 || (f0 == 0 && col >= fc)) && (cc == 0 || staged)) {
+            // A piece without feature channels: relative coordinates, staged centre features, padding.  Kept apart from
+            // the general assembly below because the lanes of a warp take these branches side by side: one lane in the
+            // general path (eight branchy row_val calls with their global loads) used to cost the whole warp ~400
+            // instructions, twice per row of the given-centre stacks (ncu: 45 M warp instructions for 4 M of useful work).
+            if (!have_rel && col < x0 + 3 && col + 8 > x0) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float cx = a.new_xyz ? __ldg(a.new_xyz + ((size_t)b * 3 + d) * a.s + s) : 0.f;
+                    rel[d] = __ldg(a.xyz + ((size_t)b * 3 + d) * a.n + j) - cx;
+                }
+                have_rel = true;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = col + e, d = c - x0;
+                float t = 0.f;
+                if (d >= 0 && d < 3) t = d == 0 ? rel[0] : (d == 1 ? rel[1] : rel[2]);
+                else if (c >= c0 && c < c0 + cc) t = h_to_f(s_cen[c]) + h_to_f(s_cen_lo[c]);
+                v[e] = t;
+            }
         } else {
             if (!have_rel && col < x0 + 3 && col + 8 > x0) {
 #pragma unroll
@@ -266,6 +292,13 @@ __device__ __forceinline__ void row_vals8_pre(const RowSrc& s, size_t row, int c
             const float2 f = h2_to_f2(wl[e]);
             l[2 * e] = f.x; l[2 * e + 1] = f.y;
         }
+    }
+    if (!s.lo) {  // one plane: plain BatchNorm + ReLU (two instructions per channel instead of four)
+        if (s.scale) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], sc[e], sh[e]), 0.f);
+        }
+        return;
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -354,12 +387,16 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
         }
     }
     // skip columns, (non-vectorisable coarse columns,) zero padding
+    const int used = sc + cc, used8 = (used + 7) & ~7;   // columns that carry data; rounded up to whole 16-byte pieces
     if (live) {
-        for (int col = l; col < a.out_ld; col += lanes) {
+        // with vectorised coarse columns only the skip columns and the padding are left: the padding beyond the last
+        // piece that carries data goes out as 16-byte zero stores (straight to global memory in the staged case too)
+        const int scalar_end = cvec ? used8 : a.out_ld;
+        for (int col = l; col < scalar_end; col += lanes) {
             float v = 0.f;
             if (col < sc) {
                 v = row_val(a.skip, (size_t)row, col);
-            } else if (col < sc + cc) {
+            } else if (col < used) {
                 if (cvec) continue;
                 const int ch = col - sc;
                 if (a.s > 1) {
@@ -375,12 +412,19 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
             o[col] = h;
             if (ol) ol[col] = f_to_h(v - h_to_f(h));
         }
+        if (cvec) {
+            act_t* go = a.out + (size_t)row * a.out_ld;
+            for (int g = (used8 >> 3) + l; g < (a.out_ld >> 3); g += lanes) {
+                *reinterpret_cast<uint4*>(go + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+                if (a.out_lo) *reinterpret_cast<uint4*>(a.out_lo + (size_t)row * a.out_ld + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
     }
     if (staged) {
         __syncwarp();
         if (live) {
             act_t* go = a.out + (size_t)row * a.out_ld;
-            for (int g = l; g < (a.out_ld >> 3); g += lanes) {
+            for (int g = l; g < (used8 >> 3); g += lanes) {
                 *reinterpret_cast<uint4*>(go + g * 8) = *reinterpret_cast<const uint4*>(&s_row[warp][rsub][0][g * 8]);
                 if (a.out_lo)
                     *reinterpret_cast<uint4*>(a.out_lo + (size_t)row * a.out_ld + g * 8) =
