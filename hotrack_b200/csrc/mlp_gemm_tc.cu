@@ -67,7 +67,7 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 // below fp32 resolution); the output is written as such a pair too.  Used for the stacks in front of the backbone's
 // ill-conditioned spot (FP3 normalises a broadcast global feature: every rounding before it is amplified ~40x by the
 // end of the network), where fp16's 11 bits are not enough for the 1e-2 parity bar.
-template <int BN, int AMODE, bool SPLIT = false>
+template <int BN, int AMODE, bool SPLIT = false, bool POOL = false>
 struct TcCfg {
     static constexpr int kABytes = TM * 128;
     static constexpr bool kTwo = AMODE == A_BNBWD || SPLIT;
@@ -81,7 +81,7 @@ struct TcCfg {
     static constexpr int kSC = TM * kCLD * 2 * (SPLIT ? 2 : 1);  // SPLIT: hi tile + lo tile
     static constexpr int kNCoef = AMODE == A_AFFINE ? 2 : 0;
     static constexpr int kCoefK = SPLIT ? kMaxKSplit : kMaxK;
-    static constexpr int kPool = AMODE != A_BNBWD ? 9 * BN * 4 : 0;  // epilogue pooling: [BN] sign flags + [4][BN] values + [4][BN] rows
+    static constexpr int kPool = POOL ? 9 * BN * 4 : 0;  // epilogue pooling: [BN] sign flags + [4][BN] values + [4][BN] rows
     static constexpr int kFixed = kSC + kNCoef * kCoefK * 4 + 5 * BN * 4 + kPool + 256 + 1024;  // + barriers + alignment slack
     static constexpr int kNstRaw = (kSmemBudget - kFixed) / kStage;
     static constexpr int kNst = kNstRaw > 6 ? 6 : kNstRaw;
@@ -92,9 +92,13 @@ struct TcCfg {
     static_assert(kNst >= 3, "not enough shared memory for a three-stage ring");
 };
 
-template <int BN, int AMODE, bool MASK, bool SPLIT = false>
+// POOL: the max-pool-in-the-epilogue variant (pn2_mlp_gemm_fwd[_bn]_pool).  A template parameter, not a run-time test of
+// p.pool_k: the pooling code is a third of the kernel's instructions, and with it compiled in the hot path of the ordinary
+// variants no longer fits the instruction cache (ncu: stall_no_inst on ~15 % of the epilogue's samples).
+template <int BN, int AMODE, bool MASK, bool SPLIT = false, bool POOL = false>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p) {
-    using Cfg = TcCfg<BN, AMODE, SPLIT>;
+    using Cfg = TcCfg<BN, AMODE, SPLIT, POOL>;
+    static_assert(!POOL || AMODE != A_BNBWD, "pooling is a forward epilogue");
     static_assert(!SPLIT || (AMODE != A_BNBWD && !MASK), "SPLIT is a forward mode");
     constexpr bool TWO = Cfg::kTwo;
     constexpr int NST = Cfg::kNst, D = Cfg::kDist;
@@ -119,9 +123,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     float* sPrev = sCoef + NCOEF * kpad;        // [4][BN], MASK only
     float* sCen = sPrev + 4 * BN;               // [BN]
     uint32_t* sNeg = reinterpret_cast<uint32_t*>(sCen + BN);   // [BN] pooling: all-ones where gamma < 0 (the minimum is wanted)
-    uint32_t* sPoolV = sNeg + (FWD ? BN : 0);                   // [4][BN] per-quarter extremes (ordered-uint form), pool_k > 32
-    int* sPoolA = reinterpret_cast<int*>(sPoolV + (FWD ? 4 * BN : 0));  // [4][BN] their rows
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sPoolA + (FWD ? 4 * BN : 0));  // 8-byte aligned: every size above is a multiple of 8
+    uint32_t* sPoolV = sNeg + (POOL ? BN : 0);                   // [4][BN] per-quarter extremes (ordered-uint form), pool_k > 32
+    int* sPoolA = reinterpret_cast<int*>(sPoolV + (POOL ? 4 * BN : 0));  // [4][BN] their rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPoolA + (POOL ? 4 * BN : 0));  // 8-byte aligned: every size above is a multiple of 8
     uint64_t* full = bars;                      // [NST] producers -> MMA
     uint64_t* empty = bars + NST;               // [NST] MMA -> producers
     uint64_t* tfull = bars + 2 * NST;           // [2]   MMA -> epilogue
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
         sCoef[i] = c < p.kdim ? src[c] : 0.f;
     }
     for (int i = tid; i < BN; i += kTcThreads) sCen[i] = (p.center && n0 + i < p.n) ? p.center[n0 + i] : 0.f;
-    if (FWD && p.pool_k)
+    if (POOL)
         for (int i = tid; i < BN; i += kTcThreads) sNeg[i] = (n0 + i < p.n && p.pool_gamma[n0 + i] < 0.f) ? 0xFFFFFFFFu : 0u;
     if (MASK) {
         for (int i = tid; i < 4 * BN; i += kTcThreads) {
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
 #pragma unroll
                             for (int e = 0; e < LDW; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * yscale);
                         }
-                        if (FWD && p.pool_k) {
+                        if constexpr (POOL) {
                             // max-pool in the epilogue: this warp holds 32 consecutive rows (lane = row) of LDW columns.
                             // Values go to an order-preserving unsigned form (inverted where gamma < 0), one
                             // redux.sync.max per column, the first row holding it by ballot.
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                     mbar_arrive(&tempty[as]);
                 }
                 epi_bar();
-                if (FWD && p.pool_k > 32) {
+                if (POOL && p.pool_k > 32) {
                     // groups of 64 / 128 rows: combine the quarters' extremes (earlier quarter wins ties: first row in order)
                     const int qpg = p.pool_k >> 5;  // quarters per group: 2 or 4
                     for (int i = tid; i < EBN * (4 / qpg); i += kEpiThreads) {
@@ -644,14 +648,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     }
 }
 
-template <int BN, int AMODE, bool MASK, bool SPLIT = false>
-int launch_tc(const GemmArgs& a, cudaStream_t stream) {
-    using Cfg = TcCfg<BN, AMODE, SPLIT>;
+template <int BN, int AMODE, bool MASK, bool SPLIT = false, bool POOL = false>
+int launch_tc_(const GemmArgs& a, cudaStream_t stream) {
+    using Cfg = TcCfg<BN, AMODE, SPLIT, POOL>;
     const int kpad = (a.kdim + TK - 1) / TK * TK;
     const size_t smem = (size_t)Cfg::kNst * Cfg::kStage + Cfg::kSC + (size_t)Cfg::kNCoef * kpad * 4 + 5 * BN * 4 + Cfg::kPool + 256 + 1024;
     static DeviceOnce once;
     if (once.first()) {
-        PN2_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, MASK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PN2_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AMODE, MASK, SPLIT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemBudget),
                   "gemm_tc: cudaFuncSetAttribute");
     }
@@ -661,16 +665,29 @@ int launch_tc(const GemmArgs& a, cudaStream_t stream) {
     long long gx = sms / ny;  // persistent: one CTA per SM (shared memory, TMEM), tiles dealt round-robin
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
-    launch_k(gemm_tc_kernel<BN, AMODE, MASK, SPLIT>, dim3((unsigned)gx, ny), dim3(kTcThreads), smem, stream, a);
+    launch_k(gemm_tc_kernel<BN, AMODE, MASK, SPLIT, POOL>, dim3((unsigned)gx, ny), dim3(kTcThreads), smem, stream, a);
     PN2_CHECK_LAUNCH("gemm_tc_kernel");
     return 0;
+}
+
+template <int BN, int AMODE, bool MASK, bool SPLIT = false>
+int launch_tc(const GemmArgs& a, cudaStream_t stream) {
+    if constexpr (AMODE != A_BNBWD && !MASK) {
+        if (a.pool_k) return launch_tc_<BN, AMODE, MASK, SPLIT, true>(a, stream);
+    }
+    return launch_tc_<BN, AMODE, MASK, SPLIT, false>(a, stream);
 }
 
 // column-tile width: the narrowest of {32, 64, 128, 256 (forward only)} that covers n, else the widest.  Every extra
 // column tile re-reads and re-transforms the whole A operand; padded columns only cost tensor-pipe time (the epilogue
 // skips them).
 int pick_bn(int n, bool fwd, long long rows) {
-    const int widest = fwd ? 256 : 128;
+    static int fwd_max = -1;
+    if (fwd_max < 0) {  // PN2_TC_MAXBN=128: no 256-wide forward tiles (development switch)
+        const char* e = getenv("PN2_TC_MAXBN");
+        fwd_max = (e && atoi(e) == 128) ? 128 : 256;
+    }
+    const int widest = fwd ? fwd_max : 128;
     int bn = widest;
     for (int c = 32; c < widest; c <<= 1)
         if (n <= c) { bn = c; break; }

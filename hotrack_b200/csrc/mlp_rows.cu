@@ -143,15 +143,17 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
     const int lane = threadIdx.x & 31;
     const int gpr = a.out_ld >> 3;
     const int rpw = gpr >= 32 ? 1 : 32 / gpr;
-    const long long total = (long long)a.b * a.s * a.k;
-    const long long wrow = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * rpw;
+    // 32-bit row arithmetic (the host refuses more than 2^31 rows): the 64-bit divisions this used to do per warp cost
+    // more instructions than the row's useful work
+    const unsigned total = (unsigned)a.b * (unsigned)a.s * (unsigned)a.k;
+    const unsigned wrow = (blockIdx.x * (unsigned)(kThreads / 32) + (threadIdx.x >> 5)) * (unsigned)rpw;
     const int sub = gpr >= 32 ? 0 : lane / gpr;
-    const long long row = wrow + sub;
+    const unsigned row = wrow + sub;
     const int fc = a.feat.p ? a.feat.c : 0, cc = a.cen.p ? a.cen.c : 0;
     const int f0 = a.xyz_first ? 3 : 0, x0 = a.xyz_first ? 0 : fc, c0 = fc + 3;
     const bool staged = cc > 0 && rpw == 1 && (a.k & 7) == 0 && a.out_ld <= 1024;
     if (staged) {
-        const long long grp = ((long long)blockIdx.x * (kThreads / 32)) / a.k;  // b * s + s_idx of all 8 rows
+        const unsigned grp = (blockIdx.x * (unsigned)(kThreads / 32)) / (unsigned)a.k;  // b * s + s_idx of all 8 rows
         for (int col = (c0 & ~7) + threadIdx.x; col < a.out_ld; col += kThreads) {
             const float v = (col >= c0 && col < c0 + cc) ? row_val(a.cen, (size_t)grp, col - c0) : 0.f;
             const act_t h = f_to_h(v);
@@ -161,9 +163,9 @@ __global__ void __launch_bounds__(kThreads) sa_build_rows_kernel(const SaBuildAr
         __syncthreads();
     }
     if (row >= total || sub >= rpw) return;
-    const int kk = (int)(row % a.k);
-    const long long bs = row / a.k;
-    const int s = (int)(bs % a.s), b = (int)(bs / a.s);
+    const unsigned bs = row / (unsigned)a.k;
+    const int kk = (int)(row - bs * (unsigned)a.k);
+    const int b = (int)(bs / (unsigned)a.s), s = (int)(bs - (unsigned)b * (unsigned)a.s);
     const int j = a.idx ? __ldg(a.idx + row) : kk;
     const size_t frow = (size_t)b * a.n + j, crow = (size_t)b * a.s + s;
     const bool fvec = fc > 0 && f0 == 0 && (fc & 7) == 0 && (a.feat.ld & 7) == 0;
@@ -317,8 +319,8 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rpw = 32 / lanes;                      // rows per warp
     const int l = lane & (lanes - 1), rsub = lane / lanes;
-    const long long row = ((long long)blockIdx.x * (kThreads / 32) + warp) * rpw + rsub;
-    const long long total = (long long)a.b * a.n;
+    const unsigned row = (blockIdx.x * (unsigned)(kThreads / 32) + warp) * (unsigned)rpw + rsub;  // < 2^31 rows (host check)
+    const unsigned total = (unsigned)a.b * (unsigned)a.n;
     const bool live = row < total;
     const int sc = a.skip.p ? a.skip.c : 0;
     const int cc = a.coarse.c;
@@ -333,8 +335,8 @@ __global__ void __launch_bounds__(kThreads) fp_build_rows_kernel(const FpBuildAr
         b = (int)(row / a.n);
         if (a.s > 1) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) id[j] = a.idx[row * 3 + j];
-            nn_weights(a.dist2 + row * 3, w);
+            for (int j = 0; j < 3; ++j) id[j] = a.idx[(size_t)row * 3 + j];
+            nn_weights(a.dist2 + (size_t)row * 3, w);
         }
         o = staged ? &s_row[warp][rsub][0][0] : a.out + (size_t)row * a.out_ld;
         ol = a.out_lo ? (staged ? &s_row[warp][rsub][1][0] : a.out_lo + (size_t)row * a.out_ld) : nullptr;
@@ -1023,10 +1025,10 @@ struct FpBwdArgs {
 __global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a) {
     pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const long long total = (long long)a.b * a.n;
+    const unsigned row = blockIdx.x * (unsigned)(kThreads / 32) + (threadIdx.x >> 5);  // < 2^31 rows (host check)
+    const unsigned total = (unsigned)a.b * (unsigned)a.n;
     if (row >= total) return;
-    const int b = (int)(row / a.n), i = (int)(row % a.n);
+    const int b = (int)(row / (unsigned)a.n), i = (int)(row - (unsigned)b * (unsigned)a.n);
     const bf16* d = a.dx + (size_t)row * a.dx_ld;
     if (a.dskip_cm) {
         if (a.skip_rows_major) {  // fp32 rows [B*N][skip_c] shared with other consumers of the same producer: accumulate
@@ -1053,8 +1055,8 @@ __global__ void __launch_bounds__(kThreads) fp_rows_bwd_kernel(const FpBwdArgs a
         float w[3] = {1.f, 0.f, 0.f};
         if (a.s > 1) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) id[j] = a.idx[row * 3 + j];
-            nn_weights(a.dist2 + row * 3, w);
+            for (int j = 0; j < 3; ++j) id[j] = a.idx[(size_t)row * 3 + j];
+            nn_weights(a.dist2 + (size_t)row * 3, w);
         }
         if ((a.coarse_c & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dcoarse_rows) & 15) == 0) {
             // a lane owns four consecutive channels: 16-byte vector reductions (a quarter of the atomic operations)
@@ -1147,6 +1149,7 @@ extern "C" int pn2_sa_build_rows_x2(int b, int n, int s, int k, const float* xyz
     if (out_ld < need || out_ld % 8) return fail_arg("pn2_sa_build_rows", "out_ld too small or not a multiple of 8");
     if (xyz_first && cen) return fail_arg("pn2_sa_build_rows", "centre features are not part of the group-all layout");
     if (!idx && k != n) return fail_arg("pn2_sa_build_rows", "identity grouping needs k == n");
+    if ((long long)b * s * k >= (1LL << 31)) return fail_arg("pn2_sa_build_rows", "more than 2^31 rows");
     SaBuildArgs a;
     a.b = b; a.n = n; a.s = s; a.k = k; a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx;
     a.feat = mk_src(feat, feat_lo, feat_c, feat_ld, feat_scale, feat_shift);
@@ -1175,6 +1178,7 @@ extern "C" int pn2_fp_build_rows_x2(int b, int n, int s, const void* skip, const
     if (b == 0) return 0;
     if (!coarse || !out || (s > 1 && (!idx || !dist2))) return fail_arg("pn2_fp_build_rows", "null pointer");
     if (out_ld < (skip ? skip_c : 0) + coarse_c || out_ld % 8) return fail_arg("pn2_fp_build_rows", "bad out_ld");
+    if ((long long)b * n >= (1LL << 31)) return fail_arg("pn2_fp_build_rows", "more than 2^31 rows");
     FpBuildArgs a;
     a.b = b; a.n = n; a.s = s;
     a.skip = mk_src(skip, skip_lo, skip_c, skip_ld, skip_scale, skip_shift);
@@ -1308,6 +1312,7 @@ extern "C" int pn2_fp_rows_bwd(int b, int n, int s, const int* idx, const float*
     if (b < 0 || n <= 0 || s <= 0) return fail_arg("pn2_fp_rows_bwd", "bad size");
     if (b == 0 || (!dskip && !dcoarse_rows)) return 0;
     if (!dx || (s > 1 && dcoarse_rows && (!idx || !dist2))) return fail_arg("pn2_fp_rows_bwd", "null pointer");
+    if ((long long)b * n >= (1LL << 31)) return fail_arg("pn2_fp_rows_bwd", "more than 2^31 rows");
     FpBwdArgs a;
     a.b = b; a.n = n; a.s = s; a.idx = idx; a.dist2 = dist2; a.dx = (const bf16*)dx; a.dx_ld = dx_ld;
     a.skip_c = skip_c; a.dskip_cm = dskip; a.skip_rows_major = skip_rows_major; a.coarse_c = coarse_c;
