@@ -24,6 +24,8 @@
 // 6 FP ops + a branch-free top-3 update.
 #include "pn2_common.cuh"
 
+#include <cstdlib>
+
 namespace pn2 {
 namespace {
 
@@ -280,7 +282,16 @@ extern "C" int pn2_knn(int b, int n, int m, int k, const float* unknown, const f
     }
     // few queries (a warp-per-query grid would leave most SMs idle): one query per CTA, its warps share the scan
     const long long wpq_ctas = (long long)((n + kKnnWarps - 1) / kKnnWarps) * b;
-    if (wpq_ctas < 2LL * sm_count() && n <= 65535) {
+    static int force = -2;  // PN2_KNN_COOP=0|1: development switch
+    if (force == -2) {
+        const char* e = getenv("PN2_KNN_COOP");
+        force = e ? atoi(e) : -1;
+    }
+    // (the cooperative variant does more work in total -- eight looser thresholds, eight lists to fold, the final merge --
+    // so it only pays while the warp-per-query grid leaves most SMs idle.  Measured, 21 queries, K = 64: B=1 N=8192
+    // 119 -> 68 us, B=4 N=4096 86 -> 44 us, B=8 86 -> 55 us, B=32 86 -> 140 us)
+    const bool coop = force >= 0 ? force == 1 : wpq_ctas * 4 <= sm_count();
+    if (coop && n <= 65535) {
         launch_k(knn_kernel<true>, dim3(n, b), dim3(kKnnWarps * 32), smem, (cudaStream_t)stream, n, m, k, nsort, unknown, known,
                  dist2, idx);
         PN2_CHECK_LAUNCH("knn_kernel");
