@@ -804,13 +804,25 @@ __global__ void __launch_bounds__(kThreads) rows_to_cm_kernel(const PoolArgs a) 
     for (int gt = blockIdx.x; gt < a.b * s_tiles; gt += gridDim.x) {
         const int b = gt / s_tiles, t = gt - b * s_tiles;
         const int s0 = t * kRowTile;
-        for (int r = r0; r < kRowTile; r += rstep) {
-            if (s0 + r < a.s) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.y + ((size_t)b * a.s + s0 + r) * a.y_ld + pc * 8));
-                uint4 ql = make_uint4(0u, 0u, 0u, 0u);
-                if (a.y_lo) ql = __ldg(reinterpret_cast<const uint4*>(a.y_lo + ((size_t)b * a.s + s0 + r) * a.y_ld + pc * 8));
-                const uint32_t* v = reinterpret_cast<const uint32_t*>(&q);
-                const uint32_t* vl = reinterpret_cast<const uint32_t*>(&ql);
+        // four rows per thread at a time, every load of the batch issued before the first use (memory-level parallelism)
+        constexpr int RB = 4;
+        for (int rb = r0; rb < kRowTile; rb += RB * rstep) {
+            uint4 qb[RB], qlb[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                const int r = rb + u * rstep;
+                qb[u] = qlb[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (r < kRowTile && s0 + r < a.s) {
+                    qb[u] = __ldg(reinterpret_cast<const uint4*>(a.y + ((size_t)b * a.s + s0 + r) * a.y_ld + pc * 8));
+                    if (a.y_lo) qlb[u] = __ldg(reinterpret_cast<const uint4*>(a.y_lo + ((size_t)b * a.s + s0 + r) * a.y_ld + pc * 8));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                const int r = rb + u * rstep;
+                if (!(r < kRowTile && s0 + r < a.s)) continue;
+                const uint32_t* v = reinterpret_cast<const uint32_t*>(&qb[u]);
+                const uint32_t* vl = reinterpret_cast<const uint32_t*>(&qlb[u]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 f = h2_to_f2(v[e]);
@@ -849,14 +861,19 @@ __global__ void __launch_bounds__(kThreads, 2) cm_to_rows_bwd_kernel(const PoolA
         const int s0 = t * kRowTile;
         // channel-major side: 8 independent 128-byte runs in flight per warp (c is a multiple of 8)
         if (a.dout_cm) {
-            for (int ch0 = warp * 8; ch0 < a.c; ch0 += nwarps * 8) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    v[j] = (s0 + lane < a.s) ? __ldg(a.dout_cm + ((size_t)b * a.c + ch0 + j) * a.s + s0 + lane) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) tile_dyn[lane * ldt + j * pieces + (ch0 >> 3)] = v[j];
+            // 4-byte cp.async straight into the permuted tile: a warp's 48 (C = 384) 128-byte runs are ALL in flight at
+            // once and cost no registers (register-staged batches of 8 left ~15 KB per SM in flight: latency-bound)
+            const bool in = s0 + lane < a.s;
+            const float* src = a.dout_cm + (size_t)b * a.c * a.s + s0 + lane;
+            const uint32_t dst = smem_u32(tile_dyn) + (uint32_t)(lane * ldt) * 4u;
+            for (int ch = warp; ch < a.c; ch += nwarps) {
+                const uint32_t d = dst + (uint32_t)((ch & 7) * pieces + (ch >> 3)) * 4u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(in ? src + (size_t)ch * a.s : a.dout_cm),
+                             "r"(in ? 4 : 0)
+                             : "memory");
             }
+            cp_async_commit();
+            cp_async_wait_all();
         }
         __syncthreads();
         // row side, four rows per thread at a time: every global load of the batch is issued before the first store (a

@@ -252,6 +252,29 @@ class Rows:
         self.numel = self.version = None
 
 
+class _LazyPooledRows:
+    """Row form of a pooled stack's output, converted (pn2_to_rows_x2: fp32 (B,C,S) -> centred fp16 rows) when the first
+    fused consumer asks for it."""
+
+    __slots__ = ("out", "chan_sums", "inv", "dims", "two", "sink", "numel", "version", "rows")
+
+    def __init__(self, out, chan_sums, inv, B, C, groups, two, sink):
+        self.out, self.chan_sums, self.inv, self.dims, self.two, self.sink = out.detach(), chan_sums, inv, (B, C, groups), two, sink
+        self.numel = self.version = self.rows = None
+
+    def materialize(self):
+        if self.rows is None:
+            B, C, groups = self.dims
+            buf = torch.empty(2 if self.two else 1, B * groups, C, dtype=_F16, device=self.out.device)
+            with torch.cuda.device(self.out.device):
+                _lib.call("pn2_to_rows_x2", B, C, groups, self.out.data_ptr(), self.chan_sums.data_ptr(), self.inv,
+                          buf[0].data_ptr(), buf[1].data_ptr() if self.two else 0, C, _stream(self.out.device))
+            self.rows = Rows(buf[0], C, C, offset=(self.chan_sums, self.inv), lo=buf[1] if self.two else None, sink=self.sink)
+            self.rows.numel, self.rows.version = self.numel, self.version
+            self.out = None
+        return self.rows
+
+
 def attach_rows(t, rows):
     rows.numel, rows.version = t.numel(), t._version
     t._pn2_rows = rows
@@ -270,7 +293,7 @@ def rows_of(t, two=False):
     """Row source of a (B,C,N) fp32 tensor: the attached one if still valid, else a conversion (two-plane if asked)."""
     r = getattr(t, "_pn2_rows", None)
     if r is not None and r.numel == t.numel() and r.version == t._version:
-        return r
+        return r.materialize() if isinstance(r, _LazyPooledRows) else r
     B, C, N = t.shape
     t = t.contiguous()
     if t.dtype != torch.float32:
@@ -479,14 +502,12 @@ class _MlpStack(Function):
             # pooled features go to the next fused consumer as bf16 rows centred on their channel mean
             inv = 1.0 / (B * groups)
             two_out = last_two  # the last layer was two-plane: so are the pooled rows
-            out_rows = torch.empty(2 if two_out else 1, B * groups, C, dtype=_F16, device=dev)
-            _lib.call("pn2_to_rows_x2", B, C, groups, out.data_ptr(), chan_sums.data_ptr(), inv, out_rows[0].data_ptr(),
-                      out_rows[1].data_ptr() if two_out else 0, C, st)
             # pooled outputs offer a row-form gradient sink too: SA2 / SA3 gathering from SA1 / SA2's output and the FP
             # layers' skip connections accumulate coalesced fp32 rows instead of strided channel-major atomics
             ctx.out_sink = _Sink(B * groups, C, k1=False) if training else None
-            _MlpStack.last_rows = Rows(out_rows[0], C, C, offset=(chan_sums, inv), lo=out_rows[1] if two_out else None,
-                                       sink=ctx.out_sink)
+            # the conversion itself waits for the first fused consumer (rows_of): the outputs of q1 / q2's scales are
+            # concatenated by torch and never read in this form
+            _MlpStack.last_rows = _LazyPooledRows(out, chan_sums, inv, B, C, groups, two_out, ctx.out_sink)
         else:
             ctx.out_sink = _Sink(R, C) if (training and C <= 1024) else None
             _MlpStack.last_rows = Rows(last.y, C, C, last.scale, last.shift, sink=ctx.out_sink, lo=x_lo)
