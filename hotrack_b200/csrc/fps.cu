@@ -27,6 +27,7 @@
 #include "pn2_common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace pn2 {
 namespace {
@@ -210,8 +211,13 @@ extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float* dat
     const int q_cnt = (n + bs - 1) / bs;
     const int n_pos = bs * q_cnt;
 
+    static int max_threads = -1;
+    if (max_threads < 0) {  // PN2_FPS_THREADS=512: development switch (fewer warps to synchronise, more points per thread)
+        const char* e = getenv("PN2_FPS_THREADS");
+        max_threads = (e && atoi(e) >= 128 && atoi(e) <= 1024) ? atoi(e) : 1024;
+    }
     int threads = 32;
-    while (threads < n_pos && threads < 1024) threads <<= 1;
+    while (threads < n_pos && threads < max_threads) threads <<= 1;
     const int ppt = (n_pos + threads - 1) / threads;
     // 1024 threads cap the register file at 64/thread: 8 points (32 state registers) is the limit
     const bool fits = ppt <= 8 && (size_t)n_pos * sizeof(float4) <= (size_t)kMaxSmem;

@@ -615,8 +615,11 @@ def test_sparse_grad_sink_matches_dense_autograd_path(cuda):
 def test_row_form_sinks_match_autograd_on_the_whole_path(cuda):
     """Every row-form gradient hand-over at once (pooled SA outputs gathered by the next SA stack, FP skip and coarse
     inputs, the head's output gathered by q1 / q2): the whole backbone -> q1 -> q2 path must produce the same parameter
-    gradients with fused.SPARSE_GRAD_SINK on as through autograd's dense (B,C,N) tensors.  Same weights, same inputs, same
-    centring constants in both runs; what is left is the order of the atomics."""
+    gradients with fused.SPARSE_GRAD_SINK on as through autograd's dense (B,C,N) tensors.  Same weights, inputs and
+    centring constants in every run.  Two runs of the SAME code path already differ by several per cent at this size
+    (fp32 atomics reorder the BatchNorm statistics and the network amplifies it: DESIGN.md section 1.2, item 4; measured
+    by tools/dev/sink_vs_autograd.py: ~8 % on the backbone's tensors), so each path runs twice and the deviation between
+    the paths is held against the deviation within them; a hand-over that lost or doubled a contribution shows as ~100 %."""
     from hotrack_b200 import backbones, fused, pointnet_utils as pu
     from hotrack_b200.handtrack_path import HandTrackPointPath, init_weights
 
@@ -629,12 +632,12 @@ def test_row_form_sinks_match_autograd_on_the_whole_path(cuda):
     init_weights(m, seed=0)
     m = m.to(cuda).train()
     with torch.no_grad():
-        m(x, k)  # leaves the steady-state centring constants on the BatchNorm modules: both runs below read the same ones
+        m(x, k)  # leaves the steady-state centring constants on the BatchNorm modules: every run below reads the same ones
     state = {n_: b_.clone() for n_, b_ in m.named_buffers()}
     centers = {id(mod): mod._pn2_center.clone() for mod in m.modules() if hasattr(mod, "_pn2_center")}
     res = []
     try:
-        for sink in (False, True):
+        for sink in (False, False, True, True):
             fused.set_sparse_grad_sink(sink)
             with torch.no_grad():
                 for n_, b_ in m.named_buffers():
@@ -649,17 +652,13 @@ def test_row_form_sinks_match_autograd_on_the_whole_path(cuda):
             res.append({n_: p_.grad.clone() for n_, p_ in m.named_parameters() if p_.grad is not None})
     finally:
         fused.set_sparse_grad_sink(False)
-    assert res[0].keys() == res[1].keys()
-    gmax = max(g.abs().max().item() for g in res[0].values())
-    devs = []
+    assert res[0].keys() == res[2].keys()
+    checked = 0
     for n_, a in res[0].items():
-        if a.abs().max().item() < 1e-6 * gmax:
-            continue  # conv biases in front of BatchNorm: exactly zero gradient
-        devs.append((_rel(res[1][n_], a), n_))
-    assert len(devs) > 60
-    # Two runs of this engine on the same inputs differ by a few per cent in the gradients even with identical code paths
-    # (fp32 atomics reorder the BatchNorm statistics, the network amplifies: DESIGN.md section 1.2, item 4); a hand-over
-    # that lost or doubled a contribution shows as ~100 % on the tensors behind it.
-    assert max(devs)[0] < 2e-1, max(devs)
-    assert sorted(d for d, _ in devs)[len(devs) // 2] < 6e-2, sorted(devs)[len(devs) // 2]
-
+        same = max(_rel(res[1][n_], a), _rel(res[3][n_], res[2][n_]))  # noise within a path
+        if same > 0.3:
+            continue  # gradients that are mathematically ~0 (conv biases before BatchNorm, SA3's last shift): all noise
+        checked += 1
+        cross = _rel(res[2][n_], a)
+        assert cross < 2.5 * same + 2e-2, (n_, cross, same)
+    assert checked > 60
