@@ -112,7 +112,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     constexpr bool FWD = AMODE != A_BNBWD;
     constexpr int NCOEF = Cfg::kNCoef;
 
-    pdl_enter();  // programmatic dependent launch: nothing above touches memory (pn2_common.cuh)
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     unsigned char* base = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // SWIZZLE_128B tiles: 1024-byte aligned
@@ -138,22 +137,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
     const long long tiles = (p.rows + TM - 1) / TM;
     const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    // ---- one-time setup
-    for (int i = tid; i < NCOEF * kpad; i += kTcThreads) {
-        const int which = i / kpad, c = i - which * kpad;
-        const float* src = which == 0 ? p.c0 : (which == 1 ? p.c1 : p.c2);
-        sCoef[i] = c < p.kdim ? src[c] : 0.f;
-    }
-    for (int i = tid; i < BN; i += kTcThreads) sCen[i] = (p.center && n0 + i < p.n) ? p.center[n0 + i] : 0.f;
-    if (POOL)
-        for (int i = tid; i < BN; i += kTcThreads) sNeg[i] = (n0 + i < p.n && p.pool_gamma[n0 + i] < 0.f) ? 0xFFFFFFFFu : 0u;
-    if (MASK) {
-        for (int i = tid; i < 4 * BN; i += kTcThreads) {
-            const int which = i / BN, c = n0 + (i - which * BN);
-            const float* src = which == 0 ? p.p_scale : (which == 1 ? p.p_shift : (which == 2 ? p.p_mean : p.p_rstd));
-            sPrev[i] = c < p.n ? src[c] : 0.f;
-        }
-    }
+    // ---- one-time setup.  On-chip part first (barriers, TMEM): it overlaps the predecessor kernel's tail; everything that
+    // reads global memory comes after the programmatic-dependent-launch wait (pn2_common.cuh)
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) {
             mbar_init(&full[i], (PN2_WARP_ARRIVE && AMODE == A_AFFINE) ? kProdWarps : kProdThreads);
@@ -171,6 +156,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const GemmArgs p
                      "r"(kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_enter();
+    for (int i = tid; i < NCOEF * kpad; i += kTcThreads) {
+        const int which = i / kpad, c = i - which * kpad;
+        const float* src = which == 0 ? p.c0 : (which == 1 ? p.c1 : p.c2);
+        sCoef[i] = c < p.kdim ? src[c] : 0.f;
+    }
+    for (int i = tid; i < BN; i += kTcThreads) sCen[i] = (p.center && n0 + i < p.n) ? p.center[n0 + i] : 0.f;
+    if (POOL)
+        for (int i = tid; i < BN; i += kTcThreads) sNeg[i] = (n0 + i < p.n && p.pool_gamma[n0 + i] < 0.f) ? 0xFFFFFFFFu : 0u;
+    if (MASK) {
+        for (int i = tid; i < 4 * BN; i += kTcThreads) {
+            const int which = i / BN, c = n0 + (i - which * BN);
+            const float* src = which == 0 ? p.p_scale : (which == 1 ? p.p_shift : (which == 2 ? p.p_mean : p.p_rstd));
+            sPrev[i] = c < p.n ? src[c] : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();

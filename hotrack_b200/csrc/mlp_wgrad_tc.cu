@@ -88,7 +88,6 @@ __device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 2, 256;" :::
 
 template <bool AFFINE>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
-    pdl_enter();  // programmatic dependent launch (pn2_common.cuh)
     const WgradArgs& p = w.a;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -120,14 +119,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
     const long long stages = (p.rows + WR - 1) / WR;
     const long long mine = blockIdx.x < stages ? (stages - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    for (int i = tid; i < 3 * MT; i += kWThreads) {
-        const int which = i / MT, c = i - which * MT;
-        sCo[i] = c < n_here ? (which == 0 ? p.cA : (which == 1 ? p.cB : p.cC))[n0 + c] : 0.f;
-    }
-    for (int i = tid; i < 2 * w.kw; i += kWThreads) {
-        const int which = i / w.kw, c = i - which * w.kw;
-        sCo[3 * MT + i] = (AFFINE && c < kw_here) ? (which == 0 ? p.in_scale : p.in_shift)[k0 + c] : 0.f;
-    }
+    // on-chip setup first (it overlaps the predecessor kernel's tail), global reads after the programmatic-dependent-launch
+    // wait (pn2_common.cuh)
     // T tiles start zeroed: channel groups beyond n_here / kw_here are never written and must multiply as zero
     for (int i = tid; i < w.nt * t_bytes / 16; i += kWThreads) reinterpret_cast<uint4*>(sT)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
@@ -147,6 +140,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
                      "r"((uint32_t)w.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_enter();
+    for (int i = tid; i < 3 * MT; i += kWThreads) {
+        const int which = i / MT, c = i - which * MT;
+        sCo[i] = c < n_here ? (which == 0 ? p.cA : (which == 1 ? p.cB : p.cC))[n0 + c] : 0.f;
+    }
+    for (int i = tid; i < 2 * w.kw; i += kWThreads) {
+        const int which = i / w.kw, c = i - which * w.kw;
+        sCo[3 * MT + i] = (AFFINE && c < kw_here) ? (which == 0 ? p.in_scale : p.in_shift)[k0 + c] : 0.f;
     }
     fence_proxy_async();  // the zeroed T tiles (generic-proxy stores) are read by the tensor core
     tc_fence_before();

@@ -55,7 +55,8 @@ void count_launch();
 // "first CTA of kernel N+1 runs its first instruction" (grid completion, launch, CTA scheduling) is a measurable part of
 // the step.  Kernels launched through launch_k() carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may
 // be scheduled as soon as every CTA of the preceding kernel in the stream has STARTED (all of ours call pdl_trigger() in
-// their first instructions) and a slot is free, and they block in pdl_wait() -- their first statement, before ANY global
+// their first instructions) and a slot is free, and they block in pdl_wait() -- before ANY global memory access (only on-chip
+// set-up such as barrier initialisation and TMEM allocation may precede it) -- their first statement otherwise, before ANY global
 // memory access -- until the preceding kernel has completed and its writes are visible.  Semantics are those of plain
 // stream order (a kernel that waits cannot complete before its predecessor, so the guarantee is transitive); only the
 // launch latency is overlapped.  RULE: a kernel may be launched with launch_k() only if pdl_wait() is its first statement.
