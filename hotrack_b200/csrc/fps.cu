@@ -54,8 +54,8 @@ __device__ __forceinline__ WarpBest warp_argmax(int vbits, int pos) {
 }
 
 // Register-resident kernel: thread t owns positions t, t+T, ..., t+(PPT-1)T.
-template <int PPT>
-__global__ void __launch_bounds__(1024, 1)
+template <int PPT, int MAXT = 1024>
+__global__ void __launch_bounds__(MAXT, 1)
 fps_regs_kernel(int n, int m, int lg_bs, int q_cnt, int n_pos, const float* __restrict__ dataset,
                 float* __restrict__ temp, int* __restrict__ idxs) {
     pdl_enter();  // programmatic dependent launch (pn2_common.cuh): first statement, before any memory access
@@ -180,16 +180,16 @@ int ilog2(int v) {
     return l;
 }
 
-template <int PPT>
+template <int PPT, int MAXT = 1024>
 int launch_regs(int b, int n, int m, int lg_bs, int q_cnt, int n_pos, int threads, const float* dataset,
                 float* temp, int* idxs, cudaStream_t stream) {
     const size_t smem = (size_t)n_pos * sizeof(float4);
     static DeviceOnce once;
     if (once.first()) {
-        PN2_CHECK(cudaFuncSetAttribute(fps_regs_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem),
+        PN2_CHECK(cudaFuncSetAttribute(fps_regs_kernel<PPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem),
                   "fps: cudaFuncSetAttribute");
     }
-    launch_k(fps_regs_kernel<PPT>, dim3(b), dim3(threads), smem, stream, n, m, lg_bs, q_cnt, n_pos, dataset, temp, idxs);
+    launch_k(fps_regs_kernel<PPT, MAXT>, dim3(b), dim3(threads), smem, stream, n, m, lg_bs, q_cnt, n_pos, dataset, temp, idxs);
     PN2_CHECK_LAUNCH("fps_regs_kernel");
     return 0;
 }
@@ -211,19 +211,23 @@ extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float* dat
     const int q_cnt = (n + bs - 1) / bs;
     const int n_pos = bs * q_cnt;
 
-    static int max_threads = -1;
-    if (max_threads < 0) {  // PN2_FPS_THREADS=512: development switch (fewer warps to synchronise, more points per thread)
-        const char* e = getenv("PN2_FPS_THREADS");
-        max_threads = (e && atoi(e) >= 128 && atoi(e) <= 1024) ? atoi(e) : 1024;
-    }
     int threads = 32;
-    while (threads < n_pos && threads < max_threads) threads <<= 1;
+    while (threads < n_pos && threads < 1024) threads <<= 1;
     // 2049..4096 points: 512 threads x 8 points beat 1024 x 4 (16 warps to synchronise and to reduce over instead of 32;
-    // measured on the step at N = 4096: 105 -> 87 us)
-    if (!getenv("PN2_FPS_THREADS") && n_pos > 2048 && n_pos <= 4096) threads = 512;
+    // measured on the step at N = 4096: 105 -> 87 us; 256 x 16 is within noise of that)
+    if (n_pos > 2048 && n_pos <= 4096) threads = 512;
+    static int forced = -1;
+    if (forced < 0) {  // PN2_FPS_THREADS=256|512|1024: development switch, honoured where the cloud still fits the registers
+        const char* e = getenv("PN2_FPS_THREADS");
+        forced = e ? atoi(e) : 0;
+    }
+    if ((forced == 256 || forced == 512 || forced == 1024) && forced <= n_pos && (n_pos + forced - 1) / forced <= (forced == 256 ? 16 : 8))
+        threads = forced;
     const int ppt = (n_pos + threads - 1) / threads;
     // 1024 threads cap the register file at 64/thread: 8 points (32 state registers) is the limit
     const bool fits = ppt <= 8 && (size_t)n_pos * sizeof(float4) <= (size_t)kMaxSmem;
+    if (threads == 256 && ppt > 8 && ppt <= 16 && (size_t)n_pos * sizeof(float4) <= (size_t)kMaxSmem)  // PN2_FPS_THREADS=256
+        return launch_regs<16, 256>(b, n, m, lg_bs, q_cnt, n_pos, threads, dataset, temp, idxs, stream);
     if (fits) {
         if (ppt <= 1) return launch_regs<1>(b, n, m, lg_bs, q_cnt, n_pos, threads, dataset, temp, idxs, stream);
         if (ppt <= 2) return launch_regs<2>(b, n, m, lg_bs, q_cnt, n_pos, threads, dataset, temp, idxs, stream);
