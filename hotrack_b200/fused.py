@@ -195,21 +195,24 @@ ACTIVE_ARENA = None  # set by TrainStep for the whole step (forward and backward
 # pn2_mlp_gemm_wgrad is forked onto a second stream and joined once, before the optimiser (join_wgrad()).  The operands
 # of the in-flight kernels are kept alive until the join.
 WGRAD_SIDE_STREAM = False
-_WGRAD_SIDE = {}  # device index -> [stream, keep-alive list]
+WGRAD_STREAMS = max(1, int(__import__("os").environ.get("PN2_WGRAD_STREAMS", "1")))  # side streams, used round-robin
+_WGRAD_SIDE = {}  # device index -> [streams, keep-alive list, launch counter]
 
 
 def _wgrad_side(dev):
     e = _WGRAD_SIDE.get(dev.index)
     if e is None:
-        e = _WGRAD_SIDE[dev.index] = [torch.cuda.Stream(device=dev), []]
-    return e
+        e = _WGRAD_SIDE[dev.index] = [[torch.cuda.Stream(device=dev) for _ in range(WGRAD_STREAMS)], [], 0]
+    e[2] += 1
+    return e[0][e[2] % len(e[0])], e[1]
 
 
 def join_wgrad():
-    """Make the current stream of every device wait for the weight-gradient stream (call once after backward)."""
-    for idx, (side, keep) in _WGRAD_SIDE.items():
+    """Make the current stream of every device wait for the weight-gradient stream(s) (call once after backward)."""
+    for idx, (sides, keep, _) in _WGRAD_SIDE.items():
         if keep:
-            torch.cuda.current_stream(torch.device("cuda", idx)).wait_stream(side)
+            for side in sides:
+                torch.cuda.current_stream(torch.device("cuda", idx)).wait_stream(side)
             keep.clear()
 
 
