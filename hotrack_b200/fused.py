@@ -747,6 +747,24 @@ def sa_group_all(xyz, points, convs, bns, training, precise=0):
     return _run("sa", meta, convs, bns, training, points, None, precise)
 
 
+def three_nn_sq(xyz1_t, xyz2_t):
+    """Squared distances (B,N,3) and int32 indices (B,N,3) of the three nearest xyz2 points of every xyz1 point --
+    coordinates only, so remembered per forward pass (pointnet_utils.memo_call: the backbone asks for FP1's and FP2's ahead
+    of time, on a side stream)."""
+    from . import pointnet_utils as pu
+
+    u, k = xyz1_t.contiguous().float(), xyz2_t.contiguous().float()
+
+    def run():
+        B, N, _ = u.shape
+        d2 = torch.empty(B, N, 3, dtype=torch.float32, device=u.device)
+        ix = torch.empty(B, N, 3, dtype=torch.int32, device=u.device)
+        pc.three_nn_wrapper(B, N, k.shape[1], u, k, d2, ix)
+        return d2, ix
+
+    return pu.memo_call("three_nn", (u, k), (), run)
+
+
 def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1, rows_only=False, precise=0):
     """FP layer.  xyz1_t (B,N,3), xyz2_t (B,S,3), points1 (B*reps,D1,N)|None, points2 (B*reps,D2,S) -> (B*reps,Cout,N).
     rows_only: the returned fp32 tensor is left UNINITIALISED (only its attached row form is valid) -- for a caller that
@@ -756,10 +774,7 @@ def fp_layer(xyz1_t, xyz2_t, points1, points2, convs, bns, training, reps=1, row
     S = xyz2_t.shape[1]
     idx = dist2 = None
     if S > 1:
-        u, k = xyz1_t.contiguous().float(), xyz2_t.contiguous().float()
-        dist2 = torch.empty(B, N, 3, dtype=torch.float32, device=u.device)
-        idx = torch.empty(B, N, 3, dtype=torch.int32, device=u.device)
-        pc.three_nn_wrapper(B, N, S, u, k, dist2, idx)
+        dist2, idx = three_nn_sq(xyz1_t, xyz2_t)
         if reps > 1:
             dist2, idx = dist2.repeat_interleave(reps, dim=0), idx.repeat_interleave(reps, dim=0)
     return _run("fp", (idx, dist2, N, S, bool(rows_only)), convs, bns, training, points1, points2, precise)

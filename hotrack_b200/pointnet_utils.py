@@ -158,6 +158,35 @@ def t_contig(t):
     return out
 
 
+def memo_call(tag, tensors, scalars, fn):
+    """``fn()`` -- a neighbour search that depends on coordinates only -- remembered while a ``coord_scope`` is open, keyed
+    by the operation, its scalar arguments and the identity of its input tensors.  Lets a caller run the SAME search
+    early on another stream (backbones.PointNet2Msg_fast prefetches SA2's sampling / ball query and the FP layers' three-NN
+    while SA1's MLP runs): the module that needs the result later finds it here and makes its stream wait for the event
+    recorded behind the search."""
+    if _MEMO is None or any(t.requires_grad for t in tensors):
+        return fn()
+    key = (tag, scalars) + tuple(_memo_key(t) for t in tensors)
+    e = _MEMO.get(key)
+    if e is None:
+        out = fn()
+        ev = st = None
+        if tensors[0].is_cuda:
+            st = torch.cuda.current_stream(tensors[0].device)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        _MEMO[key] = (tensors, out, ev, st)  # the inputs stay alive with the entry: their addresses cannot be reused
+        return out
+    _, out, ev, st = e
+    if ev is not None:
+        cur = torch.cuda.current_stream(tensors[0].device)
+        if cur != st:
+            cur.wait_event(ev)
+            for t in (out if isinstance(out, (tuple, list)) else (out,)):
+                t.record_stream(cur)
+    return out
+
+
 # ------------------------------------------------------------------ building blocks -----------
 def _make_stack(in_channel, widths, conv_cls, bn_cls):
     convs, bns = nn.ModuleList(), nn.ModuleList()
@@ -264,21 +293,32 @@ class PointNetSetAbstractionMsg_fast(_MsgBase):
         self.npoint = npoint
         self._build(radius_list, nsample_list, in_channel, mlp_list, knn)
 
-    def forward(self, xyz, points):
-        B, P, C, N = xyz.shape
+    def search(self, xyz):
+        """Sampling and grouping of ``forward`` -- everything that depends on the coordinates alone: xyz (B,P,3,N) ->
+        (xyz0 (B,3,N), new_xyz (B,3,S), [idx (B,S,K) int32 per scale]).  Inside a ``coord_scope`` the results are
+        remembered (``memo_call``), so a caller may run it ahead of time, on another stream."""
         S = self.npoint
         xyz0 = xyz[:, 0].contiguous()
         xyz_t = t_contig(xyz0)
-        fps_idx = futils.furthest_point_sample(xyz_t, S)
-        new_xyz = futils.gather_operation(xyz0, fps_idx)
+        fps_idx = memo_call("fps", (xyz_t,), (S,), lambda: futils.furthest_point_sample(xyz_t, S))
+        new_xyz = memo_call("gather", (xyz0, fps_idx), (), lambda: futils.gather_operation(xyz0, fps_idx))
         new_xyz_t = t_contig(new_xyz)
+        idxs = [memo_call("group", (xyz_t, new_xyz_t), (bool(self.knn), float(radius), int(k)),
+                          lambda radius=radius, k=k: _neighbour_idx(self.knn, radius, k, xyz_t, new_xyz_t))
+                for radius, k in zip(self.radius_list, self.nsample_list)]
+        return xyz0, new_xyz, idxs
+
+    def forward(self, xyz, points):
+        B, P, C, N = xyz.shape
+        S = self.npoint
+        xyz0, new_xyz, idxs = self.search(xyz)
         feats = None
         if points is not None and points.shape[-2] > 0:
             feats = _carry(points, points.reshape(B * P, -1, N))
         rep = (lambda t: t) if P == 1 else (lambda t: t.repeat_interleave(P, dim=0))
         outs = []
         for i, radius in enumerate(self.radius_list):
-            idx = _neighbour_idx(self.knn, radius, self.nsample_list[i], xyz_t, new_xyz_t)
+            idx = idxs[i]
             outs.append(self._scale(i, rep(xyz0), feats, rep(new_xyz), rep(idx)))
         out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
         return new_xyz.unsqueeze(1).expand(B, P, C, S), _carry(out, out.reshape(B, P, -1, S))
@@ -390,7 +430,8 @@ class _FpBase(nn.Module, _EngineMixin):
         if S == 1:
             interpolated = points2.expand(-1, -1, N)
         else:
-            dist, idx = futils.three_nn(xyz1_t.contiguous(), xyz2_t.contiguous())
+            u_, k_ = xyz1_t.contiguous(), xyz2_t.contiguous()
+            dist, idx = memo_call("three_nn_ops", (u_, k_), (), lambda: futils.three_nn(u_, k_))
             recip = 1.0 / (dist + 1e-8)
             weight = recip / recip.sum(dim=2, keepdim=True)
             if reps > 1:

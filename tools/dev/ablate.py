@@ -31,12 +31,12 @@ FAMILIES = {
     "pdl_off": [],
     "prio_off": [],
     "pdl_prio_off": [],
-    "wg_min1": [], "wg_min2": [], "wg_min8": [], "wg_min16": [], "wgs2": [], "wgs3": [], "fps512": [], "fps256": [], "fps1024": [], "maxbn128": [],
+    "wg_min1": [], "wg_min2": [], "wg_min8": [], "wg_min16": [], "wgs2": [], "wgs3": [], "no_prefetch": [], "fps512": [], "fps256": [], "fps1024": [], "maxbn128": [],
 }
 ENV = {"no_wgrad_stream": {"PN2_WGRAD_STREAM": "0"}, "pdl_off": {"PN2_PDL": "0"}, "prio_off": {"PN2_PRIO": "0"},
        "pdl_prio_off": {"PN2_PDL": "0", "PN2_PRIO": "0"},
        "wg_min1": {"PN2_WG_MIN_STAGES": "1"}, "wg_min2": {"PN2_WG_MIN_STAGES": "2"}, "wg_min8": {"PN2_WG_MIN_STAGES": "8"},
-       "wg_min16": {"PN2_WG_MIN_STAGES": "16"}, "wgs2": {"PN2_WGRAD_STREAMS": "2"}, "wgs3": {"PN2_WGRAD_STREAMS": "3"}, "fps512": {"PN2_FPS_THREADS": "512"}, "fps256": {"PN2_FPS_THREADS": "256"}, "fps1024": {"PN2_FPS_THREADS": "1024"}, "maxbn128": {"PN2_TC_MAXBN": "128"}}
+       "wg_min16": {"PN2_WG_MIN_STAGES": "16"}, "no_prefetch": {"PN2_SEARCH_PREFETCH": "0"}, "wgs2": {"PN2_WGRAD_STREAMS": "2"}, "wgs3": {"PN2_WGRAD_STREAMS": "3"}, "fps512": {"PN2_FPS_THREADS": "512"}, "fps256": {"PN2_FPS_THREADS": "256"}, "fps1024": {"PN2_FPS_THREADS": "1024"}, "maxbn128": {"PN2_TC_MAXBN": "128"}}
 
 
 def one():
