@@ -84,7 +84,6 @@ __device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 template <bool AFFINE>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const WgTc w) {
