@@ -21,9 +21,11 @@ their gradient is exactly zero.
 
 Kernels behind it: forward and input-gradient GEMMs on tcgen05 / TMEM (csrc/mlp_gemm_tc.cu; BatchNorm
 finalisation in the forward GEMM's tail, BatchNorm-backward coefficients folded into the weights for the backward one),
-weight gradient on warp-level mma.sync (csrc/mlp_gemm.cu), row builders / poolers / scatters in csrc/mlp_rows.cu.
-Step-level helpers owned by train.TrainStep: WeightPlan (one weight-conversion launch per step) and ZeroArena (one memset
-for every accumulator of the step).  Training leaves one piece of state outside state_dict: ``bn._pn2_center``, the
+weight gradient on tcgen05 too (csrc/mlp_wgrad_tc.cu; the warp-level mma.sync kernel of csrc/mlp_gemm.cu is the cross-check,
+PN2_WGRAD_IMPL=mma), row builders / poolers / scatters in csrc/mlp_rows.cu.  Gradients between fused stacks travel as fp32
+rows in the producer's sink (_Sink), the row form of a pooled output is made when a fused consumer first asks (_LazyPooledRows).
+Step-level helpers owned by train.TrainStep: WeightPlan (one weight-conversion launch per step) and ZeroArena (the
+accumulators of the step, zeroed with the gradients by one memset).  Training leaves one piece of state outside state_dict: ``bn._pn2_center``, the
 centring constant of each fused BatchNorm (reset_center_state() forgets it).
 """
 import torch

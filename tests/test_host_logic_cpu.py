@@ -60,3 +60,26 @@ def test_flat_params_tail_is_zeroed_with_the_gradients():
     own.take(8).fill_(1.0)
     own.begin()                                # an arena that owns its buffer zeroes it itself
     assert float(own.buf.sum()) == 0.0 and own.take(20) is None
+
+
+def test_memo_call_remembers_by_operation_scalars_and_tensor_identity():
+    x, y = torch.randn(2, 16, 3), torch.randn(2, 4, 3)
+    calls = []
+
+    def search():
+        calls.append(1)
+        return torch.cdist(y, x).argmin(-1)
+
+    assert pu.memo_call("nn", (x, y), (1,), search) is not pu.memo_call("nn", (x, y), (1,), search)  # no scope: no memo
+    assert len(calls) == 2
+    with pu.coord_scope():
+        a = pu.memo_call("nn", (x, y), (1,), search)
+        assert pu.memo_call("nn", (x, y), (1,), search) is a and len(calls) == 3
+        assert pu.memo_call("nn", (x, y), (2,), search) is not a and len(calls) == 4       # other scalars
+        assert pu.memo_call("other", (x, y), (1,), search) is not a and len(calls) == 5    # other operation
+        assert pu.memo_call("nn", (x[:], y), (1,), search) is a                            # same memory, new view object
+        assert pu.memo_call("nn", (x.clone(), y), (1,), search) is not a and len(calls) == 6
+        g = x.clone().requires_grad_(True)
+        pu.memo_call("nn", (g, y), (1,), search), pu.memo_call("nn", (g, y), (1,), search)
+        assert len(calls) == 8                                                             # autograd-tracked inputs: never
+    assert pu._MEMO is None
